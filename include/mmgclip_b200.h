@@ -1,0 +1,144 @@
+/*
+ * mmgclip_b200 -- C ABI of the B200-native contrastive hot path of abdel-habib/mmg-clip.
+ *
+ * The reference (pure Python / eager PyTorch) has no FFI of its own; its "plugin API" for this path is the set of
+ * nn.Module / loss callables resolved by name in mmgclip/networks/projection_controller.py:3-24 and
+ * mmgclip/loss/loss_controller.py:3-23.  The Python mirror of those classes lives in mmgclip_b200/ and reaches the
+ * GPU only through the entry points below (ctypes).  Each entry point cites the reference lines
+ * whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit sizes/strides, no torch types, no exceptions across the boundary;
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (an opaque void*), never synchronises the
+ *     device and never allocates or frees user-visible memory (the caller owns all buffers, including workspaces);
+ *   - return value: 0 = ok, negative = MMG_ERR_*; mmg_last_error_string() gives the thread-local reason;
+ *   - there is NO CPU fallback: host pointers or a missing GPU are errors;
+ *   - `prec` selects the arithmetic: MMG_PREC_FP32 = fp32 operands, fp32 FFMA accumulation (reference-faithful,
+ *     parity 1e-5); MMG_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM (2e-3).
+ */
+#ifndef MMGCLIP_B200_H_
+#define MMGCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMG_OK 0
+#define MMG_ERR_BAD_ARG (-1)
+#define MMG_ERR_BAD_ALIGN (-2)
+#define MMG_ERR_UNSUPPORTED_SHAPE (-3)
+#define MMG_ERR_CUDA (-4)
+#define MMG_ERR_NO_DEVICE (-5)
+
+#define MMG_PREC_FP32 0
+#define MMG_PREC_BF16 1
+
+/* C store modes of the dense contraction */
+#define MMG_STORE 0      /* C  = v                      */
+#define MMG_ACCUMULATE 1 /* C += v  (caller guarantees exclusive ownership of C) */
+#define MMG_ATOMIC_ADD 2 /* C += v  via red.global.add (needed when k_splits > 1) */
+
+typedef void* mmg_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int mmg_version(void);                    /* 10000*major + 100*minor + patch */
+const char* mmg_last_error_string(void);  /* thread-local, never NULL */
+int mmg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense contraction: C[M,N] (op)= alpha * A . B^T (+bias) (ReLU) ------------------------------------- */
+/* Replaces nn.Linear forward / backward: mmgclip/networks/projection.py:17,33 (LinearProjectionLayer),
+ * :45-59 (MultiLinearHead), :88-97 (MLPProjectionHead) and their autograd transposes.
+ *   A: a_mn == 0 -> row-major [M, K] (lda = row pitch in elements), a_mn == 1 -> row-major [K, M];
+ *   B: b_mn == 0 -> row-major [N, K],                               b_mn == 1 -> row-major [K, N];
+ *   C: fp32 row-major [M, N]; bias: fp32 [N] or NULL.
+ * prec BF16: A, B are bf16 (pitches multiple of 8 elements, 16-byte aligned pointers), tcgen05/TMA kernel.
+ * prec FP32: A, B are fp32, SIMT FFMA kernel.  k_splits > 1 requires mode == MMG_ATOMIC_ADD. */
+int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, float* C,
+             long long ldc, int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits,
+             mmg_stream_t stream);
+
+/* ---- element-wise helpers -------------------------------------------------------------------------------- */
+int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream);
+
+/* Row-wise L2 normalisation y = u / ||u||_2, no epsilon (mmgclip/networks/mmgclip_model.py:128-129,163;
+ * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_bf16 (nullable) receives a bf16 copy. */
+int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream);
+/* du = (dy - y * <y, dy>) * inv_norm   (autograd of the line above).  du_bf16 nullable. */
+int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
+                   mmg_stream_t stream);
+
+/* Hidden-layer pieces of MultiLinearHead (projection.py:54-61): ReLU/inverted-dropout backward and bias gradient.
+ *   dz[i] = dy[i] * (y ? y[i] > 0 : 1) * (mask ? mask[i] * keep_scale : 1)      db[n] = sum_rows dz[:, n]
+ * (y = layer output after ReLU+dropout, NULL = no ReLU; mask NULL = no dropout) */
+int mmg_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, mmg_stream_t stream);
+int mmg_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
+                         long long n, mmg_stream_t stream);
+int mmg_colsum(const float* x, int rows, int cols, float* out, mmg_stream_t stream);
+
+/* MLPProjectionHead pieces (projection.py:85-101): exact-erf GELU and LayerNorm(eps) over the last dim. */
+int mmg_gelu_fwd(const float* x, float* y, long long n, mmg_stream_t stream);
+int mmg_gelu_bwd(const float* dy, const float* x, float* dx, long long n, mmg_stream_t stream);
+int mmg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                      float* mean, float* rstd, mmg_stream_t stream);
+int mmg_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      int rows, int cols, float* dx, float* dgamma, float* dbeta, mmg_stream_t stream);
+
+/* ---- fused symmetric InfoNCE over normalised embeddings --------------------------------------------------- */
+/* Replaces: logits_per_image / logits_per_text (mmgclip_model.py:135-136; losses.py:73-74,85-86) and the two
+ * F.cross_entropy calls with labels = arange(n) (losses.py:39-43,78-82,88-91), forward and backward, WITHOUT
+ * materialising the [rows x cols] logit matrix.  a_hat: [rows, D] (the local row shard), b_hat: [cols, D] (all
+ * columns), fp32 or bf16 per `prec`, row-major, D contiguous.  `diag_offset` is the global column index paired with
+ * local row 0 (0 on one GPU, rank*rows in the sharded case).  `scale` is a DEVICE pointer to s = exp(logit_scale).
+ *
+ * Forward accumulates (caller zero-fills first):
+ *     rowsum[r] += sum_c exp(s*cos[r,c] - s)     colsum[c] += sum_r exp(s*cos[r,c] - s)     diag[r] = s*cos[r,r']
+ * The fixed shift m = s is valid because |cos| <= 1, so partial sums from different tiles and GPUs add. */
+size_t mmg_infonce_workspace_bytes(int prec, int rows, int cols, int D);
+int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                    const float* scale, float* rowsum, float* colsum, float* diag, void* workspace,
+                    size_t workspace_bytes, mmg_stream_t stream);
+
+/* loss_out[0] = inv_two_b * sum_{i<n} ( log rowsum[i] + log colsum[i] + 2*s - 2*diag[i] )
+ * = (CE_rows + CE_cols)/2 of losses.py:40-43 when n == B and inv_two_b == 1/(2B).  Deterministic reduction. */
+int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
+                     float inv_two_b, float* loss_out, mmg_stream_t stream);
+
+/* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c], scal[0] = dcoef = 2*s*gl*inv_two_b.
+ * grad_loss is a DEVICE scalar (upstream gradient of the loss; 1 for a bare loss.backward()). */
+int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+                         const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
+                         mmg_stream_t stream);
+
+/* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
+ *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - dcoef*[c == r + diag_offset]      ( = s * dloss/dlogit )
+ * dA, dB, dlogscale_acc are fp32 and must be zero-filled (or hold a running sum) by the caller.
+ * Works block by block (block_rows x block_cols, 0 = library default) through `workspace`. */
+int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                    const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA, float* dB,
+                    float* dlogscale_acc, int block_rows, int block_cols, void* workspace, size_t workspace_bytes,
+                    mmg_stream_t stream);
+
+/* ---- literal CLIPLoss on materialised logits (losses.py:28-44) ------------------------------------------- */
+/* logits: fp32 row-major [n, m] (m >= n), labels = arange(n).  lse[n] kept for the backward.
+ * loss_out[0] += coef * sum_r (lse[r] - logits[r,r]). */
+int mmg_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
+                      mmg_stream_t stream);
+/* dlogits[r,c] = coef * gl * (exp(logits[r,c] - lse[r]) - [r == c]) */
+int mmg_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
+                      float coef, float* dlogits, long long ldd, mmg_stream_t stream);
+
+/* ---- zero-shot prompt scoring (mmgclip_model.py:201-209; evaluator.py:182-188,282-299,354-368) ------------- */
+/* logits[n,c] = (s*img[n,:]) . txt[c,:] in fp32 (scale-then-multiply, as the reference's operator precedence does),
+ * probs = softmax over c, argmax with ties -> lowest index, top-k ordered (value desc, index asc).
+ * img: [N, D], txt: [C, D] fp32 row-major, C <= 64, k <= 8.  Any output pointer may be NULL. */
+int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                       float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
+                       mmg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMGCLIP_B200_H_ */

@@ -1,0 +1,375 @@
+// mmgclip_b200 -- extern "C" boundary (see include/mmgclip_b200.h).  Argument validation, error reporting and the
+// block loops of the fused InfoNCE; all arithmetic lives in simt_kernels.cu / gemm_tc.cuh.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mmgclip_b200.h"
+#include "kernels.h"
+
+namespace mmg {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return set_error(MMG_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// There is no CPU path: anything that is not device (or managed) memory is rejected.
+static int require_device(const void* p, const char* name) {
+  if (p == nullptr) return set_error(MMG_ERR_BAD_ARG, "%s is NULL", name);
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(MMG_ERR_NO_DEVICE, "%s: cannot query pointer (%s) -- is a CUDA device present?", name,
+                     cudaGetErrorString(e));
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+    return set_error(MMG_ERR_BAD_ARG, "%s must be device memory (mmgclip_b200 has no CPU fallback)", name);
+  return 0;
+}
+
+static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+static const int kDefaultBlockBf16 = 4096;  // G block 4096 x 4096 bf16 = 32 MiB, resident in the 126 MB L2
+static const int kDefaultBlockFp32 = 2048;  // S block 2048 x 2048 fp32 = 16 MiB
+
+}  // namespace mmg
+
+using namespace mmg;
+
+#define MMG_REQ(p)                                      \
+  do {                                                  \
+    int rc__ = require_device((p), #p);                 \
+    if (rc__ != 0) return rc__;                         \
+  } while (0)
+#define MMG_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != 0) return rc__;    \
+  } while (0)
+
+extern "C" {
+
+int mmg_version(void) { return 100; }
+
+const char* mmg_last_error_string(void) { return g_err; }
+
+int mmg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(MMG_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(MMG_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, float* C,
+             long long ldc, int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits,
+             mmg_stream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: empty problem %dx%dx%d", M, N, K);
+  if (mode < 0 || mode > 2) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: bad store mode %d", mode);
+  MMG_REQ(A);
+  MMG_REQ(B);
+  MMG_REQ(C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (prec == MMG_PREC_BF16) {
+    TcOperand a{A, lda, a_mn}, b{B, ldb, b_mn};
+    return tc_gemm_store(a, b, C, ldc, M, N, K, alpha, bias, relu, mode, k_splits, st);
+  }
+  if (prec == MMG_PREC_FP32)
+    return simt_gemm(static_cast<const float*>(A), lda, a_mn, static_cast<const float*>(B), ldb, b_mn, C, ldc, M, N, K,
+                     alpha, bias, relu, mode, k_splits, st);
+  return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: unknown precision %d", prec);
+}
+
+int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream) {
+  if (n < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_cast: negative length");
+  if (n == 0) return 0;
+  MMG_REQ(x);
+  MMG_REQ(y_bf16);
+  return simt_cast_bf16(x, y_bf16, n, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream) {
+  if (B < 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_fwd: bad shape %dx%d", B, D);
+  if (B == 0) return 0;
+  MMG_REQ(u);
+  MMG_REQ(y);
+  return simt_l2norm_fwd(u, B, D, y, inv_norm, y_bf16, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
+                   mmg_stream_t stream) {
+  if (B < 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_bwd: bad shape %dx%d", B, D);
+  if (B == 0) return 0;
+  MMG_REQ(dy);
+  MMG_REQ(y);
+  MMG_REQ(inv_norm);
+  if (du == nullptr && du_bf16 == nullptr) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_bwd: no output");
+  return simt_l2norm_bwd(dy, y, inv_norm, B, D, du, du_bf16, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, mmg_stream_t stream) {
+  if (n <= 0) return 0;
+  MMG_REQ(y);
+  MMG_REQ(mask);
+  return simt_dropout_apply(y, mask, keep_scale, n, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
+                         long long n, mmg_stream_t stream) {
+  if (n <= 0) return 0;
+  MMG_REQ(dy);
+  MMG_REQ(dz);
+  return simt_relu_dropout_bwd(dy, y, mask, keep_scale, dz, n, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_colsum(const float* x, int rows, int cols, float* out, mmg_stream_t stream) {
+  if (rows < 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_colsum: bad shape");
+  MMG_REQ(x);
+  MMG_REQ(out);
+  return simt_colsum(x, rows, cols, out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_gelu_fwd(const float* x, float* y, long long n, mmg_stream_t stream) {
+  if (n <= 0) return 0;
+  MMG_REQ(x);
+  MMG_REQ(y);
+  return simt_gelu_fwd(x, y, n, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_gelu_bwd(const float* dy, const float* x, float* dx, long long n, mmg_stream_t stream) {
+  if (n <= 0) return 0;
+  MMG_REQ(dy);
+  MMG_REQ(x);
+  MMG_REQ(dx);
+  return simt_gelu_bwd(dy, x, dx, n, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                      float* mean, float* rstd, mmg_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_layernorm_fwd: bad shape");
+  MMG_REQ(x);
+  MMG_REQ(gamma);
+  MMG_REQ(beta);
+  MMG_REQ(y);
+  MMG_REQ(mean);
+  MMG_REQ(rstd);
+  return simt_layernorm_fwd(x, gamma, beta, rows, cols, eps, y, mean, rstd, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      int rows, int cols, float* dx, float* dgamma, float* dbeta, mmg_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_layernorm_bwd: bad shape");
+  MMG_REQ(dy);
+  MMG_REQ(x);
+  MMG_REQ(dx);
+  MMG_REQ(dgamma);
+  MMG_REQ(dbeta);
+  return simt_layernorm_bwd(dy, x, gamma, mean, rstd, rows, cols, dx, dgamma, dbeta,
+                            static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused InfoNCE
+// ---------------------------------------------------------------------------------------------------------
+size_t mmg_infonce_workspace_bytes(int prec, int rows, int cols, int D) {
+  (void)D;
+  if (rows <= 0 || cols <= 0) return 0;
+  if (prec == MMG_PREC_BF16) {
+    const long long rb = rows < kDefaultBlockBf16 ? rows : kDefaultBlockBf16;
+    const long long cb = round_up(cols < kDefaultBlockBf16 ? cols : kDefaultBlockBf16, 64);
+    return (size_t)(rb * cb * 2 + 256);
+  }
+  const long long rb = rows < kDefaultBlockFp32 ? rows : kDefaultBlockFp32;
+  const long long cb = round_up(cols < kDefaultBlockFp32 ? cols : kDefaultBlockFp32, 4);
+  return (size_t)(rb * cb * 4 + 256);
+}
+
+static int check_infonce_args(const char* fn, int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D,
+                              int diag_offset, const float* scale) {
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_FP32) return set_error(MMG_ERR_BAD_ARG, "%s: unknown precision", fn);
+  if (rows <= 0 || cols <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "%s: bad shape %dx%dx%d", fn, rows, cols, D);
+  if (diag_offset < 0 || diag_offset + rows > cols)
+    return set_error(MMG_ERR_BAD_ARG, "%s: rows [%d, %d) have no matching columns in [0, %d)", fn, diag_offset,
+                     diag_offset + rows, cols);
+  if (prec == MMG_PREC_BF16 && (D % 8) != 0)
+    return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "%s: bf16 path needs D %% 8 == 0 (TMA pitch), got %d", fn, D);
+  int rc;
+  if ((rc = require_device(a_hat, "a_hat")) != 0) return rc;
+  if ((rc = require_device(b_hat, "b_hat")) != 0) return rc;
+  if ((rc = require_device(scale, "scale")) != 0) return rc;
+  return 0;
+}
+
+int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                    const float* scale, float* rowsum, float* colsum, float* diag, void* workspace,
+                    size_t workspace_bytes, mmg_stream_t stream) {
+  MMG_TRY(check_infonce_args("mmg_infonce_fwd", prec, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  MMG_REQ(rowsum);
+  MMG_REQ(colsum);
+  MMG_REQ(diag);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (prec == MMG_PREC_BF16) {
+    // One persistent launch over all logit tiles; the tile lives only in TMEM.
+    return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, st);
+  }
+  if (workspace_bytes < mmg_infonce_workspace_bytes(prec, rows, cols, D))
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_fwd: workspace too small");
+  MMG_REQ(workspace);
+  const float* a = static_cast<const float*>(a_hat);
+  const float* b = static_cast<const float*>(b_hat);
+  float* S = static_cast<float*>(workspace);
+  const int Rb = rows < kDefaultBlockFp32 ? rows : kDefaultBlockFp32;
+  const int Cb = cols < kDefaultBlockFp32 ? cols : kDefaultBlockFp32;
+  const long long lds = round_up(Cb, 4);
+  for (int r0 = 0; r0 < rows; r0 += Rb) {
+    const int rb = rows - r0 < Rb ? rows - r0 : Rb;
+    for (int c0 = 0; c0 < cols; c0 += Cb) {
+      const int cb = cols - c0 < Cb ? cols - c0 : Cb;
+      MMG_TRY(simt_gemm(a + (long long)r0 * D, D, 0, b + (long long)c0 * D, D, 0, S, lds, rb, cb, D, 1.f, nullptr, 0,
+                        0, 1, st));
+      MMG_TRY(simt_lse_block(S, lds, rb, cb, r0, c0, diag_offset, scale, rowsum, colsum, diag, st));
+    }
+  }
+  return 0;
+}
+
+int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
+                     float inv_two_b, float* loss_out, mmg_stream_t stream) {
+  if (n <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_loss: n must be positive");
+  MMG_REQ(rowsum);
+  MMG_REQ(colsum);
+  MMG_REQ(diag);
+  MMG_REQ(scale);
+  MMG_REQ(loss_out);
+  return simt_infonce_loss(rowsum, colsum, diag, n, scale, inv_two_b, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+                         const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
+                         mmg_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep: bad shape");
+  MMG_REQ(rowsum);
+  MMG_REQ(colsum);
+  MMG_REQ(scale);
+  MMG_REQ(grad_loss);
+  MMG_REQ(rinv);
+  MMG_REQ(cinv);
+  MMG_REQ(scal);
+  return simt_infonce_bwd_prep(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b, rinv, cinv, scal,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                    const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA, float* dB,
+                    float* dlogscale_acc, int block_rows, int block_cols, void* workspace, size_t workspace_bytes,
+                    mmg_stream_t stream) {
+  MMG_TRY(check_infonce_args("mmg_infonce_bwd", prec, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  MMG_REQ(rinv);
+  MMG_REQ(cinv);
+  MMG_REQ(scal);
+  MMG_REQ(dA);
+  MMG_REQ(dB);
+  MMG_REQ(dlogscale_acc);
+  MMG_REQ(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dflt = prec == MMG_PREC_BF16 ? kDefaultBlockBf16 : kDefaultBlockFp32;
+  const int esz = prec == MMG_PREC_BF16 ? 2 : 4;
+  const int pad = prec == MMG_PREC_BF16 ? 64 : 4;
+  int Rb = block_rows > 0 ? block_rows : dflt;
+  int Cb = block_cols > 0 ? block_cols : dflt;
+  if (Rb > rows) Rb = rows;
+  if (Cb > cols) Cb = cols;
+  long long ldg = round_up(Cb, pad);
+  // shrink the block until it fits the caller's workspace
+  while ((size_t)((long long)Rb * ldg * esz) > workspace_bytes && Rb > 128) Rb = (Rb + 1) / 2;
+  if ((size_t)((long long)Rb * ldg * esz) > workspace_bytes)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd: workspace too small (%zu bytes)", workspace_bytes);
+
+  for (int r0 = 0; r0 < rows; r0 += Rb) {
+    const int rb = rows - r0 < Rb ? rows - r0 : Rb;
+    for (int c0 = 0; c0 < cols; c0 += Cb) {
+      const int cb = cols - c0 < Cb ? cols - c0 : Cb;
+      const int doff = r0 + diag_offset - c0;
+      if (prec == MMG_PREC_BF16) {
+        const char* a = static_cast<const char*>(a_hat) + (long long)r0 * D * 2;
+        const char* b = static_cast<const char*>(b_hat) + (long long)c0 * D * 2;
+        // (1) recompute the cosine block on tensor cores; epilogue turns it into bf16 gradient coefficients g
+        MMG_TRY(tc_infonce_grad_block(a, b, rb, cb, D, doff, scale, rinv + r0, cinv + c0, scal, workspace, ldg,
+                                      dlogscale_acc, st));
+        // (2) dA[r0:, :] += g . b_blk   and   dB[c0:, :] += g^T . a_blk   in one launch
+        TcOperand A0{workspace, ldg, 0}, B0{b, D, 1};
+        TcOperand A1{workspace, ldg, 1}, B1{a, D, 1};
+        MMG_TRY(tc_gemm_dual_accumulate(A0, B0, dA + (long long)r0 * D, D, rb, D, cb, A1, B1, dB + (long long)c0 * D,
+                                        D, cb, D, rb, st));
+      } else {
+        const float* a = static_cast<const float*>(a_hat) + (long long)r0 * D;
+        const float* b = static_cast<const float*>(b_hat) + (long long)c0 * D;
+        float* S = static_cast<float*>(workspace);
+        MMG_TRY(simt_gemm(a, D, 0, b, D, 0, S, ldg, rb, cb, D, 1.f, nullptr, 0, 0, 1, st));
+        MMG_TRY(simt_grad_block(S, ldg, rb, cb, 0, 0, doff, scale, rinv + r0, cinv + c0, scal, dlogscale_acc, st));
+        MMG_TRY(simt_gemm(S, ldg, 0, b, D, 1, dA + (long long)r0 * D, D, rb, D, cb, 1.f, nullptr, 0, 1, 1, st));
+        MMG_TRY(simt_gemm(S, ldg, 1, a, D, 1, dB + (long long)c0 * D, D, cb, D, rb, 1.f, nullptr, 0, 1, 1, st));
+      }
+    }
+  }
+  return 0;
+}
+
+int mmg_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
+                      mmg_stream_t stream) {
+  if (n <= 0 || m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_arange_fwd: need 0 < n <= m (got %d, %d)", n, m);
+  MMG_REQ(logits);
+  MMG_REQ(lse);
+  MMG_REQ(loss_out);
+  return simt_ce_arange_fwd(logits, ld, n, m, coef, lse, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
+                      float coef, float* dlogits, long long ldd, mmg_stream_t stream) {
+  if (n <= 0 || m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_arange_bwd: need 0 < n <= m (got %d, %d)", n, m);
+  MMG_REQ(logits);
+  MMG_REQ(lse);
+  MMG_REQ(grad_loss);
+  MMG_REQ(dlogits);
+  return simt_ce_arange_bwd(logits, ld, n, m, lse, grad_loss, coef, dlogits, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                       float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
+                       mmg_stream_t stream) {
+  if (N < 0 || C <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score: bad shape %dx%dx%d", N, C, D);
+  if (C > 64) return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "mmg_zeroshot_score: at most 64 prompts (got %d)", C);
+  if (k < 0 || k > 8 || k > C) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score: need 0 <= k <= min(8, C)");
+  if (N == 0) return 0;
+  MMG_REQ(img);
+  MMG_REQ(txt);
+  MMG_REQ(scale);
+  return simt_zeroshot(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k, topk_idx_out, topk_val_out,
+                       static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// mmgclip_b200 -- the one tensor-core mainloop every dense contraction on the hot path runs through.
+//
+//   acc[128 x BN] (fp32, TMEM) = A[128 x K] * B[BN x K]^T      (bf16 operands, tcgen05.mma kind::f16)
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled shared-memory ring (kStages deep)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes tiles
+//   warp 2      TMEM allocator : 2 accumulator stages x BN columns (BN = 256 -> all 512 TMEM columns)
+//   warps 4..11 epilogue       : tcgen05.ld the accumulator (32 lanes x 32 columns at a time) and apply a fused
+//                                epilogue while the MMA warp already works on the next tile in the other stage
+//
+// Each operand may be K-major (row-major [rows x K]) or MN-major ([K x rows], rows contiguous), chosen at run time
+// per problem, so no transposed copies of embeddings / gradients are ever made.  A launch can carry two independent
+// problems (used for dI and dT of one logit block, which alone would each fill < half the SMs) and a split-K factor.
+//
+// The epilogues are where the CLIP-specific fusion lives (see EpiLse / EpiGrad below): the logit tile is consumed
+// straight out of TMEM and never written to HBM.
+#pragma once
+
+#include "common.cuh"
+
+namespace mmg {
+
+constexpr int kBM = 128;        // UMMA M (rows per tile)
+constexpr int kBK = 64;         // K elements per pipeline stage (= one 128-byte swizzle span of bf16)
+constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit operands
+constexpr int kEpiWarps = 8;    // warps 4..11
+constexpr int kGemmThreads = 32 * (4 + kEpiWarps);
+
+struct GemmProblem {
+  int M, N, K;           // logical extents (ragged edges are zero-filled by TMA and masked in the epilogue)
+  int tiles_m, tiles_n;  // ceil(M/128), ceil(N/BN)
+  int k_splits;          // >= 1; each split handles a contiguous range of 64-wide K blocks
+  int a_mn, b_mn;        // 0 = K-major operand, 1 = MN-major operand
+  __host__ __device__ int num_tiles() const { return tiles_m * tiles_n * k_splits; }
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kTotal = kStages * (kABytes + kBBytes) + kBarBytes + 1024 /* alignment slack */;
+};
+
+struct TileCoord {
+  int prob, m_blk, n_blk, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int t, const GemmProblem& p0, const GemmProblem& p1) {
+  TileCoord c;
+  const int t0 = p0.tiles_m * p0.tiles_n * p0.k_splits;
+  c.prob = (t >= t0) ? 1 : 0;
+  const GemmProblem& p = c.prob ? p1 : p0;
+  if (c.prob) t -= t0;
+  const int mn = p.tiles_m * p.tiles_n;
+  const int split = t / mn;
+  const int r = t - split * mn;
+  c.m_blk = r / p.tiles_n;
+  c.n_blk = r - c.m_blk * p.tiles_n;
+  const int nkb = (p.K + kBK - 1) / kBK;
+  const int per = (nkb + p.k_splits - 1) / p.k_splits;
+  c.kb_begin = split * per;
+  c.kb_end = min(nkb, c.kb_begin + per);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogues.  Every epilogue warp owns 32 accumulator rows (TMEM lanes 32q..32q+31, q = warp % 4, one row per
+// thread) and half of the tile's columns (h = (warp-4)/4), visited 32 columns at a time.
+// ---------------------------------------------------------------------------------------------------------
+
+// C = alpha * acc (+ bias[col]) (ReLU) stored / accumulated / atomically added to fp32 row-major C.
+struct EpiStoreF32 {
+  struct Params {
+    float* C;
+    long long ldc;
+    const float* bias;  // per output column, may be null
+    float alpha;
+    int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
+    int relu;
+  };
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                             int q, int lane) {
+    const int row = m0 + q * 32 + lane;
+    float* crow = P.C + static_cast<long long>(row) * P.ldc;
+    const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 64; ++ch) {
+      const int cl = half * (BN / 2) + ch * 32;
+      const int c0 = n0 + cl;
+      if (c0 >= N) break;  // warp-uniform
+      float v[32];
+      tmem_ld_32x32b_x32(tacc + cl, v);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] * P.alpha;
+          if (P.bias != nullptr && c0 + j < N) x += __ldg(P.bias + c0 + j);
+          if (P.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (vec_ok && c0 + 32 <= N && P.mode != 2) {
+          float4* dst = reinterpret_cast<float4*>(crow + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (P.mode == 1) {
+              const float4 old = dst[j];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            dst[j] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < N) {
+              if (P.mode == 0) crow[c0 + j] = v[j];
+              else if (P.mode == 1) crow[c0 + j] += v[j];
+              else atomicAdd(crow + c0 + j, v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+// Forward InfoNCE epilogue: the accumulator holds cosines cos[r][c] of a logit tile.  With the fixed shift m = s
+// (|cos| <= 1 => logits in [-s, s]) E = exp(s*cos - s) feeds the row sums AND the column sums with a single exp per
+// logit, and partial sums from different tiles / GPUs simply add.  Nothing of the tile is written to memory except
+//   rowsum[r] += sum_c E      colsum[c] += sum_r E      diag[r] = s * cos[r][r]
+struct EpiLse {
+  struct Params {
+    float* rowsum;            // [M]   (atomic accumulate; zero-initialised by the caller)
+    float* colsum;            // [N]
+    float* diag;              // [M]   logit of the matching pair
+    const float* scale_ptr;   // device scalar s = exp(logit_scale)
+    int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
+  };
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                             int q, int lane) {
+    const float s = __ldg(P.scale_ptr);
+    const float sl2 = s * 1.4426950408889634f;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    const int dcol = row + P.diag_offset;
+    float racc = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 64; ++ch) {
+      const int cl = half * (BN / 2) + ch * 32;
+      const int c0 = n0 + cl;
+      if (c0 >= N) break;  // warp-uniform
+      float v[32];
+      tmem_ld_32x32b_x32(tacc + cl, v);
+      tmem_ld_wait();
+      if (row_ok && dcol >= c0 && dcol < c0 + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j == dcol) P.diag[row] = v[j] * s;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float e = ex2_approx(fmaf(v[j], sl2, -sl2));
+        v[j] = (row_ok && c0 + j < N) ? e : 0.f;
+        racc += v[j];
+      }
+      // Column sums over this warp's 32 rows: transposing butterfly, 31 shuffles for 32 columns.
+      // After the last step lane j holds sum over lanes of v[j].
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool up = lane & 16;
+        const float keep = up ? v[j + 16] : v[j];
+        const float send = up ? v[j] : v[j + 16];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool up = lane & 8;
+        const float keep = up ? v[j + 8] : v[j];
+        const float send = up ? v[j] : v[j + 8];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool up = lane & 4;
+        const float keep = up ? v[j + 4] : v[j];
+        const float send = up ? v[j] : v[j + 4];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool up = lane & 2;
+        const float keep = up ? v[j + 2] : v[j];
+        const float send = up ? v[j] : v[j + 2];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const bool up = lane & 1;
+        const float keep = up ? v[1] : v[0];
+        const float send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      if (c0 + lane < N) atomicAdd(P.colsum + c0 + lane, v[0]);
+    }
+    if (row_ok) atomicAdd(P.rowsum + row, racc);
+  }
+};
+
+// Backward InfoNCE epilogue: recomputed cosines -> gradient coefficients of one logit tile,
+//   g[r][c] = E[r][c] * (rinv[r] + cinv[c]) - dcoef * [r == c],
+//   rinv[r] = s*gl/(2B*rowsum[r]),  cinv[c] = s*gl/(2B*colsum[c]),  dcoef = s*gl/B        (gl = d loss)
+// i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g is written as bf16 into an
+// L2-resident block scratch (never the full B x B) that the two gradient GEMMs consume; sum(g * cos) accumulates
+// d loss / d log(s).
+struct EpiGrad {
+  struct Params {
+    __nv_bfloat16* G;
+    long long ldg;
+    const float* rinv;        // [M]
+    const float* cinv;        // [N]
+    const float* scale_ptr;   // device scalar s
+    const float* dcoef_ptr;   // device scalar dcoef
+    float* dlogscale_acc;     // device scalar accumulator: sum g * cos
+    int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
+  };
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                             int q, int lane) {
+    const float s = __ldg(P.scale_ptr);
+    const float sl2 = s * 1.4426950408889634f;
+    const float dcoef = __ldg(P.dcoef_ptr);
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    const int dcol = row + P.diag_offset;
+    const float ri = row_ok ? __ldg(P.rinv + row) : 0.f;
+    __nv_bfloat16* grow = P.G + static_cast<long long>(row) * P.ldg;
+    const bool vec_ok = ((P.ldg & 7) == 0) && ((reinterpret_cast<uintptr_t>(P.G) & 15) == 0);
+    float dacc = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 64; ++ch) {
+      const int cl = half * (BN / 2) + ch * 32;
+      const int c0 = n0 + cl;
+      if (c0 >= N) break;  // warp-uniform
+      float v[32];
+      tmem_ld_32x32b_x32(tacc + cl, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float cosv = v[j];
+        const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
+        const float ci = (c0 + j < N) ? __ldg(P.cinv + c0 + j) : 0.f;
+        float g = e * (ri + ci);
+        if (c0 + j == dcol) g -= dcoef;
+        g = (row_ok && c0 + j < N) ? g : 0.f;
+        dacc = fmaf(g, cosv, dacc);
+        v[j] = g;
+      }
+      if (row_ok) {
+        if (vec_ok && c0 + 32 <= N) {
+          uint4* dst = reinterpret_cast<uint4*>(grow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            dst[j] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < N) grow[c0 + j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+    dacc = warp_sum(dacc);
+    if (lane == 0 && dacc != 0.f) atomicAdd(P.dlogscale_acc, dacc);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const GemmProblem p0, const GemmProblem p1, const typename Epi::Params e0,
+               const typename Epi::Params e1) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: a power of two >= 32
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * S::kBBytes);
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p1.tiles_m > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p0.num_tiles() + p1.num_tiles();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, p0, p1);
+        const GemmProblem& p = tc.prob ? p1 : p0;
+        const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
+        const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
+        const int m0 = tc.m_blk * kBM;
+        const int n0 = tc.n_blk * BN;
+        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kABytes + S::kBBytes);
+          uint8_t* a_dst = sA + stage * S::kABytes;
+          uint8_t* b_dst = sB + stage * S::kBBytes;
+          const int k0 = kb * kBK;
+          if (!p.a_mn) {
+            tma_load_2d(mA, &full_bar[stage], a_dst, k0, m0, kEvictNormal);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBM / 64; ++i)
+              tma_load_2d(mA, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, k0, kEvictNormal);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(mB, &full_bar[stage], b_dst, k0, n0, kEvictNormal);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(mB, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, k0, kEvictNormal);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(t, p0, p1);
+      const GemmProblem& p = tc.prob ? p1 : p0;
+      const int acc_stage = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_bf16(kBM, BN, p.a_mn, p.b_mn);
+      const uint32_t tmem_d = tmem_base + acc_stage * BN;
+      // K-major: 8-row groups are 1024 B apart (SBO); one swizzle span along K, LBO unused.
+      // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN atoms are kBK*128 B apart (LBO).
+      const uint32_t a_lbo = p.a_mn ? kBK * 128 : 0, b_lbo = p.b_mn ? kBK * 128 : 0;
+      const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;
+      const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
+      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == tc.kb_end - 1) umma_commit(&tfull_bar[acc_stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc.kb_begin >= tc.kb_end) {
+        // Degenerate split (no K blocks): nothing was issued; still publish the (stale) stage so the
+        // epilogue does not dead-lock.  Host code never creates such splits; kept as a guard.
+        if (lane == 0) umma_commit(&tfull_bar[acc_stage]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(t, p0, p1);
+      const GemmProblem& p = tc.prob ? p1 : p0;
+      const int acc_stage = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc_stage], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
+      if (tc.kb_begin < tc.kb_end)
+        Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kBM, tc.n_blk * BN, p.M, p.N, half, q, lane);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace mmg

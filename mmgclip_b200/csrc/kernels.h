@@ -1,0 +1,73 @@
+// mmgclip_b200 -- internal launcher declarations shared by the .cu translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mmg {
+
+// thread-local error reporting (c_api.cu)
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// ---- tensor-core (bf16, tcgen05) launchers: tc_kernels.cu ----
+struct TcOperand {
+  const void* ptr;   // bf16
+  long long ld;      // row pitch in elements
+  int mn_major;      // 0: [rows, K]  1: [K, rows]
+};
+
+int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
+                  const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
+
+// Two independent accumulate-GEMMs in one launch (dA and dB of one logit block).
+int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
+                            const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,
+                            cudaStream_t st);
+
+int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
+                   float* rowsum, float* colsum, float* diag, cudaStream_t st);
+
+int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
+                          const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
+                          long long ldg, float* dlogscale_acc, cudaStream_t st);
+
+// ---- SIMT (fp32) launchers: simt_kernels.cu ----
+int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
+              int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
+int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
+int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
+int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
+                    cudaStream_t st);
+int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st);
+int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
+                          long long n, cudaStream_t st);
+int simt_colsum(const float* x, int rows, int cols, float* out, cudaStream_t st);
+int simt_gelu_fwd(const float* x, float* y, long long n, cudaStream_t st);
+int simt_gelu_bwd(const float* dy, const float* x, float* dx, long long n, cudaStream_t st);
+int simt_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                       float* mean, float* rstd, cudaStream_t st);
+int simt_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       int rows, int cols, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+
+// fp32 InfoNCE block helpers operating on an fp32 cosine block S[rb, cb] (pitch lds) in scratch
+int simt_lse_block(float* S, long long lds, int rb, int cb, int row0, int col0, int diag_offset, const float* scale,
+                   float* rowsum, float* colsum, float* diag, cudaStream_t st);
+int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0, int diag_offset, const float* scale,
+                    const float* rinv, const float* cinv, const float* scal, float* dlogscale_acc, cudaStream_t st);
+
+int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
+                      float inv_two_b, float* loss_out, cudaStream_t st);
+int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+                          const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
+                          cudaStream_t st);
+int simt_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
+                       cudaStream_t st);
+int simt_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
+                       float coef, float* dlogits, long long ldd, cudaStream_t st);
+int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                  float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
+                  cudaStream_t st);
+
+}  // namespace mmg

@@ -1,0 +1,777 @@
+// mmgclip_b200 -- fp32 / SIMT kernels.
+//
+//  * the reference-faithful fp32 arithmetic path (MMG_PREC_FP32): FFMA contraction + fp32 block helpers of the
+//    fused InfoNCE, accurate expf/logf, deterministic reductions where it is cheap;
+//  * the bandwidth-bound small kernels both precisions share: casts, row L2-normalise forward/backward, ReLU/dropout
+//    backward, bias gradient, GELU, LayerNorm, loss finalisation, literal cross-entropy on materialised logits;
+//  * zero-shot prompt scoring (fp32 logits, fused softmax / argmax / top-k with a defined tie rule).
+//
+// Warp-level primitives (shuffles) do the row reductions; loads are 16-byte vectorised where alignment allows.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mmg {
+
+#define MMG_LAUNCH_CHECK(what)                         \
+  do {                                                 \
+    cudaError_t e__ = cudaGetLastError();              \
+    if (e__ != cudaSuccess) return check_cuda(e__, what); \
+  } while (0)
+
+// =====================================================================================================
+// fp32 contraction  C[M,N] (op)= alpha * A . B^T (+bias)(ReLU)
+// 64x64 block tile, 16-deep K slab, 256 threads x (4x4) register micro-tile.
+// =====================================================================================================
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
+             float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, const float* __restrict__ bias,
+             int relu, int mode, int k_per_split) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (A_MN) { k = e >> 6; m = e & 63; } else { m = e >> 4; k = e & 15; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = A_MN ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int n, k;
+      if (B_MN) { k = e >> 6; n = e & 63; } else { n = e >> 4; k = e & 15; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = B_MN ? B[(long long)gk * ldb + gn] : B[(long long)gn * ldb + gk];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] * alpha;
+      if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      float* dst = C + (long long)gm * ldc + gn;
+      if (mode == 0) *dst = v;
+      else if (mode == 1) *dst += v;
+      else atomicAdd(dst, v);
+    }
+  }
+}
+
+int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
+              int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > 1 && mode != 2) return set_error(-1, "simt_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
+  if (k_splits > 1 && relu) return set_error(-1, "simt_gemm: ReLU cannot be fused with split-K");
+  int k_per_split = ((K + k_splits - 1) / k_splits + 15) / 16 * 16;
+  if (k_per_split < 16) k_per_split = 16;
+  k_splits = (K + k_per_split - 1) / k_per_split;
+  if (k_splits < 1) k_splits = 1;
+  dim3 grid((N + 63) / 64, (M + 63) / 64, k_splits);
+  if (grid.y > 65535) return set_error(-3, "simt_gemm: M too large for the SIMT grid (%d)", M);
+#define MMG_SGEMM(AM, BM) \
+  sgemm_kernel<AM, BM><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, relu, mode, k_per_split)
+  if (a_mn && b_mn) MMG_SGEMM(true, true);
+  else if (a_mn) MMG_SGEMM(true, false);
+  else if (b_mn) MMG_SGEMM(false, true);
+  else MMG_SGEMM(false, false);
+#undef MMG_SGEMM
+  MMG_LAUNCH_CHECK("sgemm_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// casts
+// =====================================================================================================
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long j = i; j < n4; j += stride) {
+      const float4 v = reinterpret_cast<const float4*>(x)[j];
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(y)[j] = o;
+    }
+    for (long long j = (n4 << 2) + i; j < n; j += stride) y[j] = __float2bfloat16_rn(x[j]);
+  } else {
+    for (long long j = i; j < n; j += stride) y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+static inline int ew_blocks(long long n, int per_thread) {
+  long long b = (n / per_thread + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  cast_bf16_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  MMG_LAUNCH_CHECK("cast_bf16_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// row L2 normalise (one warp per row, float4 loads, shuffle reduction)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__ y, float* __restrict__ inv_norm,
+                  __nv_bfloat16* __restrict__ yb) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* ur = u + (long long)row * D;
+  const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(u) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  float ss = 0.f;
+  if (vec) {
+    for (int i = lane; i < (D >> 2); i += 32) {
+      const float4 v = reinterpret_cast<const float4*>(ur)[i];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) ss += ur[i] * ur[i];
+  }
+  ss = warp_sum(ss);
+  // Reference: x / x.norm(dim=1, keepdim=True) with no epsilon (a zero row gives NaN there and here).
+  const float nrm = sqrtf(ss);
+  const float inv = 1.0f / nrm;
+  if (lane == 0 && inv_norm != nullptr) inv_norm[row] = inv;
+  float* yr = y + (long long)row * D;
+  __nv_bfloat16* ybr = yb ? yb + (long long)row * D : nullptr;
+  if (vec) {
+    for (int i = lane; i < (D >> 2); i += 32) {
+      float4 v = reinterpret_cast<const float4*>(ur)[i];
+      v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm;
+      reinterpret_cast<float4*>(yr)[i] = v;
+      if (ybr) {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        reinterpret_cast<uint2*>(ybr)[i] = o;
+      }
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const float v = ur[i] / nrm;
+      yr[i] = v;
+      if (ybr) ybr[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st) {
+  if (B <= 0) return 0;
+  l2norm_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(u, B, D, y, inv_norm, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  MMG_LAUNCH_CHECK("l2norm_fwd_kernel");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm, int B,
+                  int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* dyr = dy + (long long)row * D;
+  const float* yr = y + (long long)row * D;
+  float dot = 0.f;
+  for (int i = lane; i < D; i += 32) dot = fmaf(dyr[i], yr[i], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  for (int i = lane; i < D; i += 32) {
+    const float v = (dyr[i] - yr[i] * dot) * inv;
+    if (du) du[(long long)row * D + i] = v;
+    if (dub) dub[(long long)row * D + i] = __float2bfloat16_rn(v);
+  }
+}
+
+int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
+                    cudaStream_t st) {
+  if (B <= 0) return 0;
+  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16));
+  MMG_LAUNCH_CHECK("l2norm_bwd_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// MultiLinearHead hidden-layer helpers
+// =====================================================================================================
+__global__ void dropout_apply_kernel(float* __restrict__ y, const uint8_t* __restrict__ mask, float keep_scale,
+                                     long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = mask[i] ? y[i] * keep_scale : 0.f;
+}
+
+int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  dropout_apply_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(y, mask, keep_scale, n);
+  MMG_LAUNCH_CHECK("dropout_apply_kernel");
+  return 0;
+}
+
+// y is the layer output AFTER ReLU and dropout (y > 0 <=> pre-activation > 0 and kept); y == NULL means no ReLU.
+__global__ void relu_dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                        const uint8_t* __restrict__ mask, float keep_scale, float* __restrict__ dz,
+                                        long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float g = (y == nullptr || y[i] > 0.f) ? dy[i] : 0.f;
+    if (mask != nullptr) g = mask[i] ? g * keep_scale : 0.f;
+    dz[i] = g;
+  }
+}
+
+int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
+                          long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  relu_dropout_bwd_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(dy, y, mask, keep_scale, dz, n);
+  MMG_LAUNCH_CHECK("relu_dropout_bwd_kernel");
+  return 0;
+}
+
+// out[c] = sum_r x[r, c].  Block = 32 columns x 8 row groups; fixed-order shared-memory combine (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = ty; r < rows; r += 8) s += x[(long long)r * cols + c];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    out[c] = t;
+  }
+}
+
+int simt_colsum(const float* x, int rows, int cols, float* out, cudaStream_t st) {
+  if (cols <= 0) return 0;
+  colsum_kernel<<<(cols + 31) / 32, 256, 0, st>>>(x, rows, cols, out);
+  MMG_LAUNCH_CHECK("colsum_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// MLPProjectionHead helpers: exact-erf GELU, LayerNorm
+// =====================================================================================================
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    y[i] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
+                                long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
+    dx[i] = dy[i] * (cdf + v * pdf);
+  }
+}
+int simt_gelu_fwd(const float* x, float* y, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gelu_fwd_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(x, y, n);
+  MMG_LAUNCH_CHECK("gelu_fwd_kernel");
+  return 0;
+}
+int simt_gelu_bwd(const float* dy, const float* x, float* dx, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  gelu_bwd_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(dy, x, dx, n);
+  MMG_LAUNCH_CHECK("gelu_bwd_kernel");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     int rows, int cols, float eps, float* __restrict__ y, float* __restrict__ mean,
+                     float* __restrict__ rstd) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * cols;
+  float s = 0.f;
+  for (int i = lane; i < cols; i += 32) s += xr[i];
+  const float mu = warp_sum(s) / cols;
+  float v = 0.f;
+  for (int i = lane; i < cols; i += 32) {
+    const float d = xr[i] - mu;
+    v = fmaf(d, d, v);
+  }
+  const float rs = rsqrtf(warp_sum(v) / cols + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  for (int i = lane; i < cols; i += 32) y[(long long)row * cols + i] = (xr[i] - mu) * rs * gamma[i] + beta[i];
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, int rows, int cols,
+                        float* __restrict__ dx) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * cols;
+  const float* dyr = dy + (long long)row * cols;
+  const float mu = mean[row], rs = rstd[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < cols; i += 32) {
+    const float g = dyr[i] * gamma[i];
+    const float xh = (xr[i] - mu) * rs;
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+  }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+  for (int i = lane; i < cols; i += 32) {
+    const float g = dyr[i] * gamma[i];
+    const float xh = (xr[i] - mu) * rs;
+    dx[(long long)row * cols + i] = (g - s1 - xh * s2) * rs;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_params_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, int rows, int cols, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta) {
+  __shared__ float pg[8][33], pb[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float sg = 0.f, sb = 0.f;
+  if (c < cols)
+    for (int r = ty; r < rows; r += 8) {
+      const float d = dy[(long long)r * cols + c];
+      sg = fmaf(d, (x[(long long)r * cols + c] - mean[r]) * rstd[r], sg);
+      sb += d;
+    }
+  pg[ty][tx] = sg;
+  pb[ty][tx] = sb;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a += pg[i][tx];
+      b += pb[i][tx];
+    }
+    dgamma[c] = a;
+    dbeta[c] = b;
+  }
+}
+
+int simt_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                       float* mean, float* rstd, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, rows, cols, eps, y, mean, rstd);
+  MMG_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return 0;
+}
+int simt_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       int rows, int cols, float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  layernorm_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, dx);
+  MMG_LAUNCH_CHECK("layernorm_bwd_dx_kernel");
+  layernorm_bwd_params_kernel<<<(cols + 31) / 32, 256, 0, st>>>(dy, x, mean, rstd, rows, cols, dgamma, dbeta);
+  MMG_LAUNCH_CHECK("layernorm_bwd_params_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// fp32 InfoNCE block helpers.  S holds cosines of logit block (rows row0.., cols col0..).
+// =====================================================================================================
+// rows: one warp per row -> E = exp(s*cos - s) written back in place, rowsum[row0+r] += sum_c E, diag.
+__global__ void __launch_bounds__(256)
+lse_rows_kernel(float* __restrict__ S, long long lds, int rb, int cb, int row0, int col0, int diag_offset,
+                const float* __restrict__ scale, float* __restrict__ rowsum, float* __restrict__ diag) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rb) return;
+  const float s = *scale;
+  float* Sr = S + (long long)r * lds;
+  const int dcol = row0 + r + diag_offset - col0;  // column inside this block holding the matching pair
+  float acc = 0.f;
+  for (int c = lane; c < cb; c += 32) {
+    const float cosv = Sr[c];
+    if (c == dcol) diag[row0 + r] = s * cosv;
+    const float e = expf(s * cosv - s);
+    Sr[c] = e;
+    acc += e;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) rowsum[row0 + r] += acc;
+}
+
+// columns: block = 32 columns x 8 row groups over the E block; fixed-order combine.
+__global__ void __launch_bounds__(256)
+lse_cols_kernel(const float* __restrict__ E, long long lds, int rb, int cb, int col0, float* __restrict__ colsum) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cb)
+    for (int r = ty; r < rb; r += 8) s += E[(long long)r * lds + c];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cb) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    colsum[col0 + c] += t;
+  }
+}
+
+int simt_lse_block(float* S, long long lds, int rb, int cb, int row0, int col0, int diag_offset, const float* scale,
+                   float* rowsum, float* colsum, float* diag, cudaStream_t st) {
+  lse_rows_kernel<<<(rb + 7) / 8, 256, 0, st>>>(S, lds, rb, cb, row0, col0, diag_offset, scale, rowsum, diag);
+  MMG_LAUNCH_CHECK("lse_rows_kernel");
+  lse_cols_kernel<<<(cb + 31) / 32, 256, 0, st>>>(S, lds, rb, cb, col0, colsum);
+  MMG_LAUNCH_CHECK("lse_cols_kernel");
+  return 0;
+}
+
+// cos -> g in place (see EpiGrad in gemm_tc.cuh for the formula); accumulates sum g*cos.
+__global__ void __launch_bounds__(256)
+grad_block_kernel(float* __restrict__ S, long long lds, int rb, int cb, int row0, int col0, int diag_offset,
+                  const float* __restrict__ scale, const float* __restrict__ rinv, const float* __restrict__ cinv,
+                  const float* __restrict__ scal, float* __restrict__ dlogscale_acc) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float dacc = 0.f;
+  if (r < rb) {
+    const float s = *scale;
+    const float dcoef = scal[0];
+    const float ri = rinv[row0 + r];
+    float* Sr = S + (long long)r * lds;
+    const int dcol = row0 + r + diag_offset - col0;
+    for (int c = lane; c < cb; c += 32) {
+      const float cosv = Sr[c];
+      float g = expf(s * cosv - s) * (ri + cinv[col0 + c]);
+      if (c == dcol) g -= dcoef;
+      Sr[c] = g;
+      dacc = fmaf(g, cosv, dacc);
+    }
+  }
+  dacc = warp_sum(dacc);
+  __shared__ float wsum[8];
+  if (lane == 0) wsum[threadIdx.x >> 5] = dacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += wsum[i];
+    if (t != 0.f) atomicAdd(dlogscale_acc, t);
+  }
+}
+
+int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0, int diag_offset, const float* scale,
+                    const float* rinv, const float* cinv, const float* scal, float* dlogscale_acc, cudaStream_t st) {
+  grad_block_kernel<<<(rb + 7) / 8, 256, 0, st>>>(S, lds, rb, cb, row0, col0, diag_offset, scale, rinv, cinv, scal,
+                                                  dlogscale_acc);
+  MMG_LAUNCH_CHECK("grad_block_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// loss finalisation (single block, fixed-order tree => deterministic)
+// =====================================================================================================
+__global__ void __launch_bounds__(1024)
+infonce_loss_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum, const float* __restrict__ diag,
+                    int n, const float* __restrict__ scale, float inv_two_b, float* __restrict__ loss_out) {
+  __shared__ double part[1024];
+  const float s = *scale;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024)
+    acc += (double)(logf(rowsum[i]) + s - diag[i]) + (double)(logf(colsum[i]) + s - diag[i]);
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (float)(part[0] * (double)inv_two_b);
+}
+
+int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
+                      float inv_two_b, float* loss_out, cudaStream_t st) {
+  infonce_loss_kernel<<<1, 1024, 0, st>>>(rowsum, colsum, diag, n, scale, inv_two_b, loss_out);
+  MMG_LAUNCH_CHECK("infonce_loss_kernel");
+  return 0;
+}
+
+__global__ void infonce_bwd_prep_kernel(const float* __restrict__ rowsum, int rows, const float* __restrict__ colsum,
+                                        int cols, const float* __restrict__ scale, const float* __restrict__ grad_loss,
+                                        float inv_two_b, float* __restrict__ rinv, float* __restrict__ cinv,
+                                        float* __restrict__ scal) {
+  const float coef = (*scale) * (*grad_loss) * inv_two_b;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) rinv[i] = coef / rowsum[i];
+  if (i < cols) cinv[i] = coef / colsum[i];
+  if (i == 0) scal[0] = 2.0f * coef;
+}
+
+int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+                          const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
+                          cudaStream_t st) {
+  const int n = rows > cols ? rows : cols;
+  infonce_bwd_prep_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b,
+                                                           rinv, cinv, scal);
+  MMG_LAUNCH_CHECK("infonce_bwd_prep_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// literal cross-entropy with labels = arange(n) on materialised logits (losses.py:39-43)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+ce_arange_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, float coef, float* __restrict__ lse,
+                     float* __restrict__ loss_out) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float term = 0.f;
+  if (r < n) {
+    const float* lr = logits + (long long)r * ld;
+    float mx = -INFINITY;
+    for (int c = lane; c < m; c += 32) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < m; c += 32) s += expf(lr[c] - mx);
+    s = warp_sum(s);
+    const float l = mx + logf(s);
+    if (lane == 0) {
+      lse[r] = l;
+      term = l - lr[r];
+    }
+  }
+  __shared__ float wsum[8];
+  if (lane == 0) wsum[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += wsum[i];
+    atomicAdd(loss_out, coef * t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_arange_bwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, const float* __restrict__ lse,
+                     const float* __restrict__ grad_loss, float coef, float* __restrict__ dlogits, long long ldd) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float k = coef * (*grad_loss);
+  const float l = lse[r];
+  for (int c = lane; c < m; c += 32) {
+    float p = expf(logits[(long long)r * ld + c] - l);
+    if (c == r) p -= 1.0f;
+    dlogits[(long long)r * ldd + c] = k * p;
+  }
+}
+
+int simt_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
+                       cudaStream_t st) {
+  if (n <= 0) return 0;
+  ce_arange_fwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, coef, lse, loss_out);
+  MMG_LAUNCH_CHECK("ce_arange_fwd_kernel");
+  return 0;
+}
+int simt_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
+                       float coef, float* dlogits, long long ldd, cudaStream_t st) {
+  if (n <= 0) return 0;
+  ce_arange_bwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, lse, grad_loss, coef, dlogits, ldd);
+  MMG_LAUNCH_CHECK("ce_arange_bwd_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// zero-shot prompt scoring: logits = (s*img) . txt^T in fp32, softmax, argmax, top-k
+// Block = 64 image rows; the 64x64 logit tile is accumulated with the same 4x4 FFMA micro-tile as sgemm, parked in
+// shared memory, then one warp per 8 rows finishes softmax / argmax / top-k with shuffles.
+// =====================================================================================================
+__device__ __forceinline__ void warp_argmax(float& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zeroshot_kernel(const float* __restrict__ img, const float* __restrict__ txt, int N, int C, int D,
+                const float* __restrict__ scale, float* __restrict__ logits_out, float* __restrict__ probs_out,
+                long long* __restrict__ argmax_out, int k, long long* __restrict__ topk_idx,
+                float* __restrict__ topk_val) {
+  __shared__ float As[32][64 + 4];
+  __shared__ float Bs[32][64 + 4];
+  __shared__ float Ls[64][64 + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 64;
+  const float s = *scale;
+  const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(txt) & 15) == 0);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += 32) {
+    // 64 rows x 32 k = 512 float4 per operand, 2 per thread
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * 256;
+      const int r = e >> 3, kq = (e & 7) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int gm = m0 + r, gk = k0 + kq;
+      if (vec) {
+        if (gm < N && gk < D) a = *reinterpret_cast<const float4*>(img + (long long)gm * D + gk);
+        if (r < C && gk < D) b = *reinterpret_cast<const float4*>(txt + (long long)r * D + gk);
+      } else {
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 4; ++j) {
+          if (gm < N && gk + j < D) av[j] = img[(long long)gm * D + gk + j];
+          if (r < C && gk + j < D) bv[j] = txt[(long long)r * D + gk + j];
+        }
+        a = make_float4(av[0], av[1], av[2], av[3]);
+        b = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      }
+      // reference order of operations: (logit_scale * image_embeddings) @ text_embeddings.t()
+      As[kq + 0][r] = s * a.x; As[kq + 1][r] = s * a.y; As[kq + 2][r] = s * a.z; As[kq + 3][r] = s * a.w;
+      Bs[kq + 0][r] = b.x; Bs[kq + 1][r] = b.y; Bs[kq + 2][r] = b.z; Bs[kq + 3][r] = b.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ls[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = warp * 8 + rr;
+    const long long gm = (long long)m0 + r;
+    if (gm >= N) break;  // warp-uniform
+    const float v0 = (lane < C) ? Ls[r][lane] : -INFINITY;
+    const float v1 = (lane + 32 < C) ? Ls[r][lane + 32] : -INFINITY;
+    if (logits_out != nullptr) {
+      if (lane < C) logits_out[gm * C + lane] = v0;
+      if (lane + 32 < C) logits_out[gm * C + lane + 32] = v1;
+    }
+    const float mx = warp_max(fmaxf(v0, v1));
+    const float e0 = (lane < C) ? expf(v0 - mx) : 0.f;
+    const float e1 = (lane + 32 < C) ? expf(v1 - mx) : 0.f;
+    const float den = warp_sum(e0 + e1);
+    const float p0 = e0 / den, p1 = e1 / den;
+    if (probs_out != nullptr) {
+      if (lane < C) probs_out[gm * C + lane] = p0;
+      if (lane + 32 < C) probs_out[gm * C + lane + 32] = p1;
+    }
+    if (argmax_out != nullptr) {
+      // the reference takes argmax of the PROBABILITIES (mmgclip_model.py:204,209); ties -> lowest index
+      float bv = (lane < C) ? p0 : -INFINITY;
+      int bi = lane;
+      if (lane + 32 < C && p1 > bv) { bv = p1; bi = lane + 32; }
+      warp_argmax(bv, bi);
+      if (lane == 0) argmax_out[gm] = bi;
+    }
+    if (k > 0 && topk_idx != nullptr) {
+      float w0 = v0, w1 = v1;  // top-k is defined on the logits: value desc, index asc
+      for (int j = 0; j < k; ++j) {
+        float bv = w0;
+        int bi = lane;
+        if (w1 > bv) { bv = w1; bi = lane + 32; }
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+          topk_idx[gm * k + j] = (j < C) ? bi : -1;
+          if (topk_val != nullptr) topk_val[gm * k + j] = bv;
+        }
+        if (bi == lane) w0 = -INFINITY;
+        if (bi == lane + 32) w1 = -INFINITY;
+      }
+    }
+  }
+}
+
+int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                  float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
+                  cudaStream_t st) {
+  if (N <= 0) return 0;
+  zeroshot_kernel<<<(N + 63) / 64, 256, 0, st>>>(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k,
+                                                 topk_idx, topk_val);
+  MMG_LAUNCH_CHECK("zeroshot_kernel");
+  return 0;
+}
+
+}  // namespace mmg

@@ -1,0 +1,189 @@
+// mmgclip_b200 -- host-side launchers of the tcgen05 mainloop (gemm_tc.cuh): TMA tensor-map construction,
+// tile-shape selection, persistent-grid sizing (one CTA per SM).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "gemm_tc.cuh"
+#include "kernels.h"
+
+namespace mmg {
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 row-major matrix [outer, inner] with row pitch `ld` elements; box = [box_outer, 64] (64 bf16 = one 128-byte
+// swizzle span).  Out-of-bounds box elements read as zero, which is what makes ragged edges free in the mainloop.
+static int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(-4, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(-2, "bf16 operand pointer must be 16-byte aligned");
+  if ((ld & 7) != 0) return set_error(-2, "bf16 operand pitch must be a multiple of 8 elements (got %lld)", ld);
+  if (inner <= 0 || outer <= 0) return set_error(-1, "empty operand (%lld x %lld)", outer, inner);
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-4, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+// operand with `rows` along M/N and `K` along the contraction
+static int make_operand_map(CUtensorMap* m, const TcOperand& op, int rows, int K, int tile_rows) {
+  if (!op.mn_major) return make_tmap(m, op.ptr, K, rows, op.ld, tile_rows);  // [rows, K]: box tile_rows x 64(K)
+  return make_tmap(m, op.ptr, rows, K, op.ld, kBK);                          // [K, rows]: box 64(K) x 64(rows)
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn) {
+  GemmProblem p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + kBM - 1) / kBM;
+  p.tiles_n = (N + BN - 1) / BN;
+  const int nkb = (K + kBK - 1) / kBK;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > nkb) k_splits = nkb;
+  // no empty splits: shrink until the last split still owns a K block
+  while (k_splits > 1) {
+    const int per = (nkb + k_splits - 1) / k_splits;
+    if ((k_splits - 1) * per < nkb) break;
+    --k_splits;
+  }
+  p.k_splits = k_splits;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  return p;
+}
+
+static GemmProblem empty_problem() {
+  GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.k_splits = 1;
+  return p;
+}
+
+template <int BN, class Epi>
+static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
+                  const GemmProblem& p0, const GemmProblem& p1, const typename Epi::Params& e0,
+                  const typename Epi::Params& e1, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+    configured = true;
+  }
+  const int total = p0.num_tiles() + p1.num_tiles();
+  if (total <= 0) return 0;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(a0, b0, a1, b1, p0, p1, e0, e1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
+  return 0;
+}
+
+static int pick_bn(int N) { return N > 128 ? 256 : 128; }
+
+int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
+                  const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(-1, "tc_gemm: empty problem %dx%dx%d", M, N, K);
+  if (k_splits > 1 && mode != 2) return set_error(-1, "tc_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
+  if (k_splits > 1 && (relu || bias)) return set_error(-1, "tc_gemm: bias/ReLU cannot be fused with split-K");
+  const int BN = pick_bn(N);
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_operand_map(&ma, A, M, K, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb, B, N, K, BN)) != 0) return rc;
+  GemmProblem p0 = make_problem(M, N, K, BN, k_splits, A.mn_major, B.mn_major);
+  GemmProblem p1 = empty_problem();
+  EpiStoreF32::Params e;
+  e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.mode = mode; e.relu = relu;
+  if (BN == 256) return launch<256, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
+  return launch<128, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
+}
+
+int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
+                            const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,
+                            cudaStream_t st) {
+  if (N0 != N1) return set_error(-1, "tc_gemm_dual: both problems must share N");
+  const int BN = pick_bn(N0);
+  CUtensorMap ma0, mb0, ma1, mb1;
+  int rc;
+  if ((rc = make_operand_map(&ma0, A0, M0, K0, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb0, B0, N0, K0, BN)) != 0) return rc;
+  if ((rc = make_operand_map(&ma1, A1, M1, K1, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb1, B1, N1, K1, BN)) != 0) return rc;
+  GemmProblem p0 = make_problem(M0, N0, K0, BN, 1, A0.mn_major, B0.mn_major);
+  GemmProblem p1 = make_problem(M1, N1, K1, BN, 1, A1.mn_major, B1.mn_major);
+  EpiStoreF32::Params e0, e1;
+  e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.mode = 1; e0.relu = 0;
+  e1 = e0;
+  e1.C = C1; e1.ldc = ldc1;
+  if (BN == 256) return launch<256, EpiStoreF32>(ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
+  return launch<128, EpiStoreF32>(ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
+}
+
+int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
+                   float* rowsum, float* colsum, float* diag, cudaStream_t st) {
+  const int BN = pick_bn(cols);
+  TcOperand A{a_hat, D, 0}, B{b_hat, D, 0};
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_operand_map(&ma, A, rows, D, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb, B, cols, D, BN)) != 0) return rc;
+  GemmProblem p0 = make_problem(rows, cols, D, BN, 1, 0, 0);
+  GemmProblem p1 = empty_problem();
+  EpiLse::Params e;
+  e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
+  if (BN == 256) return launch<256, EpiLse>(ma, mb, ma, mb, p0, p1, e, e, st);
+  return launch<128, EpiLse>(ma, mb, ma, mb, p0, p1, e, e, st);
+}
+
+int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
+                          const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
+                          long long ldg, float* dlogscale_acc, cudaStream_t st) {
+  const int BN = pick_bn(cb);
+  TcOperand A{a_blk, D, 0}, B{b_blk, D, 0};
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_operand_map(&ma, A, rb, D, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb, B, cb, D, BN)) != 0) return rc;
+  GemmProblem p0 = make_problem(rb, cb, D, BN, 1, 0, 0);
+  GemmProblem p1 = empty_problem();
+  EpiGrad::Params e;
+  e.G = reinterpret_cast<__nv_bfloat16*>(G); e.ldg = ldg; e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
+  e.dcoef_ptr = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
+  if (BN == 256) return launch<256, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
+  return launch<128, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
+}
+
+}  // namespace mmg

@@ -1,0 +1,528 @@
+"""Host-side operators of the hot path: torch tensors in, C-ABI calls on the current CUDA stream, torch tensors out.
+
+PyTorch is used for what it is good at here -- device memory, streams and the autograd graph that ties the operators
+to ``loss.backward()`` in the reference's training loop (mmgclip/experiments/ClassifierExperiment.py:109-118).  All
+arithmetic happens in ``libmmgclip_b200.so``; nothing in this file computes on the CPU or through ATen kernels.
+
+Arithmetic follows the reference lines cited in ``include/mmgclip_b200.h``; closed-form gradients are SURVEY.md s3.5.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MMG_ACCUMULATE, MMG_ATOMIC_ADD, MMG_PREC_BF16, MMG_PREC_FP32, MMG_STORE, check
+
+_PREC = {"fp32": MMG_PREC_FP32, "bf16": MMG_PREC_BF16}
+_default_precision = os.environ.get("MMGCLIP_B200_PRECISION", "bf16")
+_NUM_SMS = None
+
+
+def set_default_precision(p: str) -> None:
+    """'bf16' (tcgen05 tensor cores, 2e-3 parity) or 'fp32' (FFMA, 1e-5 parity)."""
+    global _default_precision
+    if p not in _PREC:
+        raise ValueError(f"Invalid precision: {p}")
+    _default_precision = p
+
+
+def get_default_precision() -> str:
+    return _default_precision
+
+
+def _resolve(prec: Optional[str]) -> str:
+    p = prec or _default_precision
+    if p not in _PREC:
+        raise ValueError(f"Invalid precision: {p}")
+    return p
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmgclip_b200 has no CPU fallback: expected CUDA tensors, got a tensor on " + str(t.device))
+
+
+def num_sms() -> int:
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = _lib.device_info()[0]
+    return _NUM_SMS
+
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch per device (the L2-resident gradient-coefficient block lives here)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# raw wrappers
+# ----------------------------------------------------------------------------------------------------------------
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.bfloat16:
+        return x
+    if x.dtype != torch.float32:
+        raise ValueError("cast_bf16 expects float32 input")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().mmg_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream()), "mmg_cast_f32_to_bf16")
+    return y
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
+         out: Optional[torch.Tensor] = None, alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
+         relu: bool = False, mode: int = MMG_STORE, k_splits: int = 1, prec: Optional[str] = None) -> torch.Tensor:
+    """C[M,N] (op)= alpha * A . B^T.  A is [M,K] (or [K,M] if a_mn), B is [N,K] (or [K,N] if b_mn)."""
+    prec = _resolve(prec)
+    _need_cuda(A, B, out, bias)
+    want = torch.bfloat16 if prec == "bf16" else torch.float32
+    if A.dtype != want or B.dtype != want:
+        raise ValueError(f"gemm({prec}) expects {want} operands, got {A.dtype} / {B.dtype}")
+    if A.dim() != 2 or B.dim() != 2 or A.stride(1) != 1 or B.stride(1) != 1:
+        raise ValueError("gemm operands must be 2-D with a contiguous last dimension")
+    exp_a = (K, M) if a_mn else (M, K)
+    exp_b = (K, N) if b_mn else (N, K)
+    if tuple(A.shape) != exp_a or tuple(B.shape) != exp_b:
+        raise ValueError(f"gemm shape mismatch: A {tuple(A.shape)} vs {exp_a}, B {tuple(B.shape)} vs {exp_b}")
+    if out is None:
+        if mode != MMG_STORE:
+            out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+        else:
+            out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if out.dtype != torch.float32 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise ValueError("gemm output must be float32 [M, N] with contiguous rows")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm bias must be contiguous float32 [N]")
+    check(_lib.load().mmg_gemm(_PREC[prec], _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out),
+                               out.stride(0), M, N, K, float(alpha), _p(bias), int(relu), mode, k_splits, _stream()),
+          "mmg_gemm")
+    return out
+
+
+def _split_k_for(M: int, N: int, K: int) -> int:
+    """Split-K factor that fills the SMs for a short-and-wide output (the dW contraction has K = batch)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    nkb = (K + 63) // 64
+    return max(1, min(nkb // 4 if nkb >= 8 else 1, num_sms() // max(tiles, 1)))
+
+
+def l2norm_fwd(u: torch.Tensor, want_bf16: bool) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    _need_cuda(u)
+    u = u.contiguous()
+    B, D = u.shape
+    y = torch.empty_like(u)
+    inv = torch.empty(B, dtype=torch.float32, device=u.device)
+    yb = torch.empty((B, D), dtype=torch.bfloat16, device=u.device) if want_bf16 else None
+    if B > 0:
+        check(_lib.load().mmg_l2norm_fwd(_p(u), B, D, _p(y), _p(inv), _p(yb), _stream()), "mmg_l2norm_fwd")
+    return y, inv, yb
+
+
+def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: bool, want_bf16: bool):
+    _need_cuda(dy, y, inv)
+    dy = dy.contiguous()
+    B, D = y.shape
+    du = torch.empty_like(y) if want_f32 else None
+    dub = torch.empty((B, D), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    if B > 0:
+        check(_lib.load().mmg_l2norm_bwd(_p(dy), _p(y), _p(inv), B, D, _p(du), _p(dub), _stream()), "mmg_l2norm_bwd")
+    return du, dub
+
+
+def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, colsum=None):
+    """Accumulate row/column sums of exp(s*cos - s) for local rows `a` against all columns `b`."""
+    _need_cuda(a, b, scale)
+    rows, D = a.shape
+    cols = b.shape[0]
+    dev = a.device
+    if rowsum is None:
+        rowsum = torch.zeros(rows, dtype=torch.float32, device=dev)
+    if colsum is None:
+        colsum = torch.zeros(cols, dtype=torch.float32, device=dev)
+    diag = torch.empty(rows, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
+    ws = _workspace(dev, nbytes)
+    check(lib.mmg_infonce_fwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum), _p(colsum),
+                              _p(diag), _p(ws), ws.numel(), _stream()), "mmg_infonce_fwd")
+    return rowsum, colsum, diag
+
+
+def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=rowsum.device)
+    check(_lib.load().mmg_infonce_loss(_p(rowsum), _p(colsum_slice), _p(diag), rowsum.numel(), _p(scale),
+                                       float(inv_two_b), _p(out), _stream()), "mmg_infonce_loss")
+    return out
+
+
+def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, prec: str,
+                         block_rows: int = 0, block_cols: int = 0):
+    """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header."""
+    rows, D = a.shape
+    cols = b.shape[0]
+    dev = a.device
+    lib = _lib.load()
+    rinv = torch.empty(rows, dtype=torch.float32, device=dev)
+    cinv = torch.empty(cols, dtype=torch.float32, device=dev)
+    scal = torch.empty(4, dtype=torch.float32, device=dev)
+    gl = grad_loss.reshape(()).to(torch.float32).contiguous()
+    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b), _p(rinv),
+                                   _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
+    dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+    dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
+    dls = torch.zeros((), dtype=torch.float32, device=dev)
+    block_rows = block_rows or int(os.environ.get("MMGCLIP_B200_BLOCK_ROWS", "0"))
+    block_cols = block_cols or int(os.environ.get("MMGCLIP_B200_BLOCK_COLS", "0"))
+    nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
+    if block_rows or block_cols:
+        esz = 2 if prec == "bf16" else 4
+        br = min(rows, block_rows or 4096)
+        bc = (min(cols, block_cols or 4096) + 63) // 64 * 64
+        nbytes = max(nbytes, br * bc * esz + 256)
+    ws = _workspace(dev, nbytes)
+    check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+                              _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
+                              _stream()), "mmg_infonce_bwd")
+    return dA, dB, dls
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd operators
+# ----------------------------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) [* dropout mask]; nn.Linear semantics (projection.py:17,45-59,88-97)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool, mask, keep_scale: float, prec: str):
+        _need_cuda(x, weight, bias, mask)
+        if x.dim() != 2:
+            raise ValueError("projection heads take [B, E] inputs")
+        Bn, E = x.shape
+        D = weight.shape[0]
+        if weight.shape[1] != E:
+            raise ValueError(f"mat1 and mat2 shapes cannot be multiplied ({Bn}x{E} and {weight.shape[1]}x{D})")
+        x = x.contiguous()
+        w = weight.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        if Bn == 0:
+            ctx.empty = True
+            return x.new_zeros((0, D))
+        ctx.empty = False
+        if prec == "bf16":
+            xo, wo = cast_bf16(x), cast_bf16(w)
+        else:
+            xo, wo = x, w
+        y = gemm(xo, wo, Bn, D, E, bias=b, relu=relu, prec=prec)
+        if mask is not None:
+            check(_lib.load().mmg_dropout_apply(_p(y), _p(mask), float(keep_scale), y.numel(), _stream()),
+                  "mmg_dropout_apply")
+        ctx.prec, ctx.relu, ctx.keep_scale = prec, relu, keep_scale
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xo, wo, y if (relu or mask is not None) else None, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.empty:
+            return None, None, None, None, None, None, None
+        xo, wo, y, mask = ctx.saved_tensors
+        prec = ctx.prec
+        Bn, E = xo.shape
+        D = wo.shape[0]
+        dy = dy.contiguous()
+        if ctx.relu or mask is not None:
+            dz = torch.empty_like(dy)
+            yy = y if ctx.relu else None
+            check(_lib.load().mmg_relu_dropout_bwd(_p(dy), _p(yy), _p(mask), float(ctx.keep_scale), _p(dz), dz.numel(),
+                                                   _stream()), "mmg_relu_dropout_bwd")
+        else:
+            dz = dy
+        dzo = cast_bf16(dz) if prec == "bf16" else dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[1]:
+            ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
+            dw = gemm(dzo, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks,
+                      mode=MMG_ATOMIC_ADD if ks > 1 else MMG_STORE)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(D, dtype=torch.float32, device=dy.device)
+            check(_lib.load().mmg_colsum(_p(dz), Bn, D, _p(db), _stream()), "mmg_colsum")
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dzo, wo, Bn, E, D, b_mn=True, prec=prec)
+        return dx, dw, db, None, None, None, None
+
+
+def linear(x, weight, bias=None, relu=False, mask=None, keep_scale=1.0, prec=None):
+    return _LinearFn.apply(x, weight, bias, relu, mask, keep_scale, _resolve(prec))
+
+
+class _L2NormFn(torch.autograd.Function):
+    """x / x.norm(dim=1, keepdim=True)  (mmgclip_model.py:128-129), no epsilon."""
+
+    @staticmethod
+    def forward(ctx, u, want_bf16: bool):
+        y, inv, yb = l2norm_fwd(u, want_bf16)
+        ctx.save_for_backward(y, inv)
+        if yb is None:
+            yb = y.new_empty(0)
+        ctx.mark_non_differentiable(yb)
+        return y, yb
+
+    @staticmethod
+    def backward(ctx, dy, _unused):
+        y, inv = ctx.saved_tensors
+        du, _ = l2norm_bwd(dy, y, inv, True, False)
+        return du, None
+
+
+def l2_normalize(u, prec=None):
+    """Row-normalise; the bf16 operand copy the loss kernel needs is produced in the same pass and attached."""
+    prec = _resolve(prec)
+    y, yb = _L2NormFn.apply(u, prec == "bf16")
+    if prec == "bf16":
+        y._mmg_bf16 = yb
+    return y
+
+
+class _ProjNormFn(torch.autograd.Function):
+    """Bias-free projection + L2 normalise in one operator (LinearProjectionLayer followed by mmgclip_model.py:128).
+
+    Forward: u = x W^T (tensor cores) -> y = u/||u|| (+ bf16 copy).  Backward: du = (dy - y<y,dy>)/||u|| written
+    directly as the bf16 MN-major operand of dW = du^T x (split-K over the batch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, prec: str):
+        _need_cuda(x, weight)
+        Bn, E = x.shape
+        D = weight.shape[0]
+        if weight.shape[1] != E:
+            raise ValueError(f"mat1 and mat2 shapes cannot be multiplied ({Bn}x{E} and {weight.shape[1]}x{D})")
+        x = x.contiguous()
+        w = weight.contiguous()
+        if prec == "bf16":
+            xo, wo = cast_bf16(x), cast_bf16(w)
+        else:
+            xo, wo = x, w
+        u = gemm(xo, wo, Bn, D, E, prec=prec)
+        y, inv, yb = l2norm_fwd(u, prec == "bf16")
+        ctx.prec = prec
+        ctx.save_for_backward(xo, wo, y, inv)
+        if yb is None:
+            yb = y.new_empty(0)
+        ctx.mark_non_differentiable(yb)
+        return y, yb
+
+    @staticmethod
+    def backward(ctx, dy, _unused):
+        xo, wo, y, inv = ctx.saved_tensors
+        prec = ctx.prec
+        Bn, E = xo.shape
+        D = wo.shape[0]
+        need_dx = ctx.needs_input_grad[0]
+        du, dub = l2norm_bwd(dy, y, inv, prec == "fp32", prec == "bf16")
+        dz = dub if prec == "bf16" else du
+        dw = dx = None
+        if ctx.needs_input_grad[1]:
+            ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
+            dw = gemm(dz, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks,
+                      mode=MMG_ATOMIC_ADD if ks > 1 else MMG_STORE)
+        if need_dx:
+            dx = gemm(dz, wo, Bn, E, D, b_mn=True, prec=prec)
+        return dx, dw, None
+
+
+def project_normalize(x, weight, prec=None):
+    prec = _resolve(prec)
+    y, yb = _ProjNormFn.apply(x, weight, prec)
+    if prec == "bf16":
+        y._mmg_bf16 = yb
+    return y
+
+
+def _operand(t: torch.Tensor, prec: str) -> torch.Tensor:
+    """The kernel operand for an embedding matrix: itself (fp32) or its bf16 copy (reused if a producer attached one)."""
+    if prec == "fp32":
+        if t.dtype != torch.float32:
+            raise ValueError("fp32 path expects float32 embeddings")
+        return t.detach().contiguous()
+    if t.dtype == torch.bfloat16:
+        return t.detach().contiguous()
+    cached = getattr(t, "_mmg_bf16", None)
+    if cached is not None and cached.shape == t.shape and cached.device == t.device:
+        return cached
+    return cast_bf16(t.detach())
+
+
+class _InfoNCEFn(torch.autograd.Function):
+    """(CE(L, arange) + CE(L^T, arange)) / 2 with L = s * A B^T, never materialising L (losses.py:28-44, 73-82)."""
+
+    @staticmethod
+    def forward(ctx, a_hat, b_hat, scale, a_op, b_op, prec: str):
+        n, D = a_hat.shape
+        if b_hat.shape != a_hat.shape:
+            raise ValueError(f"paired InfoNCE needs equal shapes, got {tuple(a_hat.shape)} and {tuple(b_hat.shape)}")
+        s = scale.detach().reshape(()).to(device=a_hat.device, dtype=torch.float32).contiguous()
+        rowsum, colsum, diag = infonce_forward_raw(a_op, b_op, s, 0, prec)
+        loss = infonce_loss_raw(rowsum, colsum, diag, s, 0.5 / n)
+        ctx.prec = prec
+        ctx.save_for_backward(a_op, b_op, s, rowsum, colsum)
+        ctx.scale_shape = scale.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        a_op, b_op, s, rowsum, colsum = ctx.saved_tensors
+        n = a_op.shape[0]
+        dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec)
+        dscale = None
+        if ctx.needs_input_grad[2]:
+            dscale = (dls / s).reshape(ctx.scale_shape)  # d loss / d s ; sum g*cos = s * dloss/ds
+        return (dA if ctx.needs_input_grad[0] else None, dB if ctx.needs_input_grad[1] else None, dscale, None, None,
+                None)
+
+
+def info_nce(a_hat: torch.Tensor, b_hat: torch.Tensor, logit_scale: torch.Tensor, prec: Optional[str] = None):
+    """Symmetric InfoNCE of L2-normalised [n, D] embeddings; `logit_scale` is the already-exponentiated scale."""
+    prec = _resolve(prec)
+    _need_cuda(a_hat, b_hat)
+    if not torch.is_tensor(logit_scale):
+        logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_hat.device)
+    return _InfoNCEFn.apply(a_hat, b_hat, logit_scale, _operand(a_hat, prec), _operand(b_hat, prec), prec)
+
+
+class _CEArangeFn(torch.autograd.Function):
+    """coef * sum_r (logsumexp(logits[r]) - logits[r, r]): F.cross_entropy(logits, arange(n)) * n * coef."""
+
+    @staticmethod
+    def forward(ctx, logits, coef: float):
+        _need_cuda(logits)
+        if logits.dim() != 2 or logits.shape[1] < logits.shape[0]:
+            raise ValueError("cross entropy with labels arange(n) needs logits [n, m] with m >= n")
+        lg = logits.detach().to(torch.float32).contiguous()
+        n, m = lg.shape
+        lse = torch.empty(n, dtype=torch.float32, device=lg.device)
+        out = torch.zeros((), dtype=torch.float32, device=lg.device)
+        check(_lib.load().mmg_ce_arange_fwd(_p(lg), lg.stride(0), n, m, float(coef), _p(lse), _p(out), _stream()),
+              "mmg_ce_arange_fwd")
+        ctx.coef = coef
+        ctx.save_for_backward(lg, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        lg, lse = ctx.saved_tensors
+        n, m = lg.shape
+        d = torch.empty_like(lg)
+        gl = grad.reshape(()).to(torch.float32).contiguous()
+        check(_lib.load().mmg_ce_arange_bwd(_p(lg), lg.stride(0), n, m, _p(lse), _p(gl), float(ctx.coef), _p(d),
+                                            d.stride(0), _stream()), "mmg_ce_arange_bwd")
+        return d, None
+
+
+def ce_arange(logits: torch.Tensor, coef: float) -> torch.Tensor:
+    return _CEArangeFn.apply(logits, coef)
+
+
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(_lib.load().mmg_gelu_fwd(_p(x), _p(y), x.numel(), _stream()), "mmg_gelu_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        check(_lib.load().mmg_gelu_bwd(_p(dy), _p(x), _p(dx), x.numel(), _stream()), "mmg_gelu_bwd")
+        return dx
+
+
+def gelu(x):
+    return _GeluFn.apply(x)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float):
+        _need_cuda(x, gamma, beta)
+        x = x.contiguous()
+        rows, cols = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        g, b = gamma.contiguous(), beta.contiguous()
+        check(_lib.load().mmg_layernorm_fwd(_p(x), _p(g), _p(b), rows, cols, float(eps), _p(y), _p(mean), _p(rstd),
+                                            _stream()), "mmg_layernorm_fwd")
+        ctx.save_for_backward(x, g, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, mean, rstd = ctx.saved_tensors
+        rows, cols = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.empty(cols, dtype=torch.float32, device=x.device)
+        db = torch.empty(cols, dtype=torch.float32, device=x.device)
+        check(_lib.load().mmg_layernorm_bwd(_p(dy), _p(x), _p(g), _p(mean), _p(rstd), rows, cols, _p(dx), _p(dg),
+                                            _p(db), _stream()), "mmg_layernorm_bwd")
+        return dx, dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return _LayerNormFn.apply(x, gamma, beta, eps)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# zero-shot scoring (inference only)
+# ----------------------------------------------------------------------------------------------------------------
+def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, logit_scale, k: int = 0,
+                   want_logits: bool = True, want_probs: bool = True):
+    """logits = (s*I) @ T^T, softmax(-1), argmax (ties -> lowest index), top-k (value desc, index asc).
+
+    Returns dict(logits, probs, argmax[int64], topk_idx[int64, k], topk_val).  C <= 64 prompts, k <= 8.
+    (mmgclip_model.py:201-209; evaluator.py:182-188, 282-299, 354-368)"""
+    _need_cuda(image_embeddings, text_embeddings)
+    img = image_embeddings.detach().to(torch.float32).contiguous()
+    txt = text_embeddings.detach().to(torch.float32).contiguous()
+    N, D = img.shape
+    C = txt.shape[0]
+    if txt.shape[1] != D:
+        raise ValueError(f"embedding dims differ: {D} vs {txt.shape[1]}")
+    dev = img.device
+    if torch.is_tensor(logit_scale):
+        s = logit_scale.detach().reshape(()).to(device=dev, dtype=torch.float32).contiguous()
+    else:
+        s = torch.tensor(float(logit_scale), dtype=torch.float32, device=dev)
+    logits = torch.empty((N, C), dtype=torch.float32, device=dev) if want_logits else None
+    probs = torch.empty((N, C), dtype=torch.float32, device=dev) if want_probs else None
+    amax = torch.empty(N, dtype=torch.int64, device=dev)
+    tki = torch.empty((N, k), dtype=torch.int64, device=dev) if k > 0 else None
+    tkv = torch.empty((N, k), dtype=torch.float32, device=dev) if k > 0 else None
+    check(_lib.load().mmg_zeroshot_score(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
+                                         _p(tkv), _stream()), "mmg_zeroshot_score")
+    return {"logits": logits, "probs": probs, "argmax": amax, "topk_idx": tki, "topk_val": tkv}
