@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Headline benchmark: CLIP loss fwd+bwd pairs/sec at global batch 32768 on 1/2/4/8 B200 (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...            # the reference arithmetic on the host CPU (oracle port)
+
+A *step* is one pass of the hot path over one global batch of synthetic encoder features:
+    LinearProjectionLayer heads (768 -> 512, image and text) -> L2 normalise -> exp(logit_scale) -> symmetric InfoNCE
+    (CLIPLoss) forward -> backward down to the head-weight gradients            (reference: mmgclip_model.py:124-136,
+    losses.py:36-44, ClassifierExperiment.py:109-115; optimizer step excluded, as in the metric's definition)
+Rows are sharded across ranks (strong scaling: the global batch is fixed at 32768); text embeddings are all-gathered,
+column sums all-reduced, text-side gradients reduce-scattered, head gradients all-reduced (NCCL over NVLink).
+
+`value`  : inputs already resident in HBM (fp32 features), timed with CUDA events on the launching stream, max over ranks.
+`e2e`    : same call with features in pinned HOST memory: each step's host->device copy (prefetched on a copy stream one
+           step ahead) and a device->host read of the loss are inside the timed region.
+`roofline`: algorithmic FLOPs (6 B^2 D + 4 B (E_i+E_t) D, SURVEY s8d / DESIGN.md) / step time / GPUs vs the measured
+           bf16 tensor peak in MEASURED_PEAKS.json (sustained figure: the kernels are timed inside a long step).
+`cpu_baseline`: the oracle port of the reference step timed on this box's host cores on a bounded sample (rank 0, N=1).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GLOBAL_BATCH = 32768
+E_IMG = E_TXT = 768
+D_PROJ = 512
+METRIC = "CLIP loss fwd+bwd pairs/sec (global batch 32k)"
+
+
+def alg_flops(b, e_i, e_t, d):
+    return 6.0 * b * b * d + 4.0 * b * (e_i + e_t) * d
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm": float(p["hbm_gbs"]), "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference step on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(sample_batch, steps, warmup):
+    import torch
+    from oracle import clip_oracle as oc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    xi, xt = oc.synthetic_features(sample_batch, E_IMG, E_TXT, seed=42)
+    wi, wt = oc.synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
+    xi, xt, wi, wt = (torch.from_numpy(t) for t in (xi, xt, wi, wt))
+    ls = torch.tensor(math.log(1 / 0.07))
+    for _ in range(warmup):
+        oc.torch_train_step(xi, xt, wi, wt, ls)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = oc.torch_train_step(xi, xt, wi, wt, ls)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"pairs_per_s": sample_batch / dt, "ms_per_step": dt * 1e3, "cores": cores, "loss": float(out["loss"]),
+            "threads": torch.get_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = args.cpu_sample_batch
+    r = cpu_reference(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    desc = (f"oracle port (fp32 eager PyTorch on CPU) of the reference step at batch {sample} of {GLOBAL_BATCH}, "
+            f"{r['threads']} threads; cost per pair grows ~linearly with the batch, so the full 32768 batch would be "
+            f"~{GLOBAL_BATCH // sample}x slower per pair")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample_batch=sample),
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": desc},
+        "e2e": {"value": r["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, sample_batch=None):
+    cfg = {"workload": f"mmg-clip hot path: LinearProjectionLayer heads {E_IMG}->{D_PROJ} (image, text) + L2 normalise + "
+                       f"symmetric CLIPLoss fwd+bwd to head-weight grads, global batch {GLOBAL_BATCH}, synthetic "
+                       f"ConvNeXt-like / BERT-like features",
+           "global_batch": GLOBAL_BATCH, "embedding_dim": E_IMG, "projection_dim": D_PROJ,
+           "parallelism": f"row-sharded x{n_gpus} (all-gather text embeddings, all-reduce column sums, reduce-scatter dT)",
+           "l2": "step inputs rotate over >= 256 MB of distinct buffers (larger than the 126 MB L2)"}
+    if sample_batch is not None:
+        cfg["cpu_sample_batch"] = sample_batch
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, reasons, mx, power = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.tmp.read().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # samples under load dominate the upper half
+            out.update({"sm_mhz": sorted(sm)[len(sm) // 2], "sm_mhz_under_load_median": busy[len(busy) // 2],
+                        "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                        "power_w_max": max(power) if power else None})
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from mmgclip_b200 import _lib, ops
+    from mmgclip_b200.distributed import allreduce_gradients, sharded_info_nce
+    from mmgclip_b200.projection import LinearProjectionLayer
+    from oracle import clip_oracle as oc  # only for the synthetic-input recipe and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} processes (one per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mmgclip_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.batch
+    if B % world:
+        raise SystemExit("global batch must divide evenly across ranks")
+    bl = B // world
+    prec = args.precision
+
+    # identical global tensors on every rank, contiguous row shard per rank
+    xi_g, xt_g = oc.synthetic_features(B, E_IMG, E_TXT, seed=42)
+    wi, wt = oc.synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
+    xi_h = torch.from_numpy(xi_g[rank * bl:(rank + 1) * bl].copy())
+    xt_h = torch.from_numpy(xt_g[rank * bl:(rank + 1) * bl].copy())
+    del xi_g, xt_g
+    step_bytes = (xi_h.numel() + xt_h.numel()) * 4
+    n_sets = max(2, -(-(256 << 20) // step_bytes))
+    n_sets = min(n_sets, 16)
+    dev_sets = [(xi_h.to(dev), xt_h.to(dev)) for _ in range(n_sets)]
+    host_sets = [(xi_h.clone().pin_memory(), xt_h.clone().pin_memory()) for _ in range(min(n_sets, 4))]
+
+    head_i = LinearProjectionLayer(E_IMG, D_PROJ, precision=prec).to(dev)
+    head_t = LinearProjectionLayer(E_TXT, D_PROJ, precision=prec).to(dev)
+    with torch.no_grad():
+        head_i.layer.weight.copy_(torch.from_numpy(wi))
+        head_t.layer.weight.copy_(torch.from_numpy(wt))
+    logit_scale = torch.tensor(math.log(1 / 0.07), device=dev).exp()
+    group = None
+
+    def step(xi, xt):
+        head_i.layer.weight.grad = None
+        head_t.layer.weight.grad = None
+        ie = head_i.forward_normalized(xi)
+        te = head_t.forward_normalized(xt)
+        loss = sharded_info_nce(ie, te, logit_scale, group=group, prec=prec)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(head_i, group)
+            allreduce_gradients(head_t, group)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W, K = max(args.warmup, 3), args.steps
+    # ---- device-resident timing ("value") ----
+    for i in range(W):
+        loss = step(*dev_sets[i % n_sets])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.load().mmg_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        loss = step(*dev_sets[i % n_sets])
+    e1.record()
+    barrier()
+    ms_value = max_over_ranks(e0.elapsed_time(e1) / K)
+    launches = _lib.load().mmg_kernel_launch_count() - launches0
+    loss_value = float(loss.item())
+
+    # ---- end-to-end timing: pinned host features -> H2D (prefetched one step ahead) -> step -> loss D2H ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream(dev)
+    stage = [(torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(K + W + 2, dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            hx, ht = host_sets[i % len(host_sets)]
+            stage[s][0].copy_(hx, non_blocking=True)
+            stage[s][1].copy_(ht, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n_steps, base):
+        prefetch(base)
+        for i in range(n_steps):
+            s = (base + i) % 2
+            if i + 1 < n_steps:
+                prefetch(base + i + 1)
+            compute.wait_event(ready[s])
+            l = step(*stage[s])
+            consumed[s].record(compute)
+            loss_host[base + i].copy_(l.detach(), non_blocking=True)
+
+    for s in range(2):
+        consumed[s].record(compute)
+    e2e_loop(W, 0)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    W2 = W + (W % 2)  # keep the double-buffer parity aligned
+    barrier()
+    e2.record()
+    e2e_loop(K, W2)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3) / K)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- per-launch timing of the dominant kernels (informational; outside the timed regions) ----
+    kernels = None
+    if rank == 0 and args.kernel_breakdown:
+        kernels = kernel_breakdown(torch, ops, dev, bl, B, D_PROJ)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    fl = alg_flops(B, E_IMG, E_TXT, D_PROJ)
+    ach = fl / (ms_value * 1e-3) / world / 1e12
+    line = {
+        "metric": METRIC, "value": B / (ms_value * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic", "config": workload_config(world),
+        "loss": loss_value,
+        "clocks": clocks,
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": step_bytes * world, "d2h_bytes_per_step": 4 * world},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                     "frac": ach / peaks["sustained"], "frac_of_burst_peak": ach / peaks["burst"],
+                     "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                     "algorithmic_flops_per_step": fl, "traffic": None,
+                     "kernel": "gemm_tc_kernel (tcgen05 mainloop: projection, logit tiles fwd/recompute, dI/dT, dW)",
+                     "kernels": kernels},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(args.cpu_sample_batch, 3, 1)
+        line["cpu_baseline"] = {
+            "value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+            "sample": f"oracle port of the reference step (fp32 eager PyTorch, {r['threads']} threads) at batch "
+                      f"{args.cpu_sample_batch} of {B}, 3 steps; per-pair cost grows ~linearly with batch"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_breakdown(torch, ops, dev, rows, cols, d):
+    """CUDA-event time of one launch group of each dominant kernel at the bench shape (local rows x global columns)."""
+    gen = torch.Generator(device=dev).manual_seed(7)
+    a = torch.nn.functional.normalize(torch.randn(rows, d, device=dev, generator=gen), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(cols, d, device=dev, generator=gen), dim=1)
+    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    s = torch.tensor(1 / 0.07, device=dev)
+    one = torch.ones((), device=dev)
+
+    def timeit(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    t_f = timeit(lambda: ops.infonce_forward_raw(ab, bb, s, 0, "bf16"))
+    rs, cs, _ = ops.infonce_forward_raw(ab, bb, s, 0, "bf16")
+    t_b = timeit(lambda: ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, 0, "bf16"))
+    f = 2.0 * rows * cols * d
+    return [
+        {"name": "gemm_tc_kernel<EpiLse> (forward logit tiles + row/col sum-exp)", "ms": t_f, "flops": f,
+         "tflops": f / t_f / 1e9},
+        {"name": "gemm_tc_kernel<EpiGrad> + dual gemm_tc_kernel<EpiStoreF32> (recompute, dI, dT), all blocks", "ms": t_b,
+         "flops_algorithmic": 2 * f, "flops_executed": 3 * f, "tflops_algorithmic": 2 * f / t_b / 1e9,
+         "tflops_executed": 3 * f / t_b / 1e9},
+    ]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: the metric's 32768)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-breakdown", action="store_true", default=True)
+    ap.add_argument("--no-kernel-breakdown", dest="kernel_breakdown", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -47,18 +47,20 @@ typedef void* mmg_stream_t; /* cudaStream_t */
 int mmg_version(void);                    /* 10000*major + 100*minor + patch */
 const char* mmg_last_error_string(void);  /* thread-local, never NULL */
 int mmg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+long long mmg_kernel_launch_count(void);   /* kernels launched by this library since load (process-wide) */
 
 /* ---- dense contraction: C[M,N] (op)= alpha * A . B^T (+bias) (ReLU) ------------------------------------- */
 /* Replaces nn.Linear forward / backward: mmgclip/networks/projection.py:17,33 (LinearProjectionLayer),
  * :45-59 (MultiLinearHead), :88-97 (MLPProjectionHead) and their autograd transposes.
  *   A: a_mn == 0 -> row-major [M, K] (lda = row pitch in elements), a_mn == 1 -> row-major [K, M];
  *   B: b_mn == 0 -> row-major [N, K],                               b_mn == 1 -> row-major [K, N];
- *   C: fp32 row-major [M, N]; bias: fp32 [N] or NULL.
+ *   C: fp32 row-major [M, N]; bias: fp32 [N] or NULL; alpha_dev: optional DEVICE scalar multiplied into alpha
+ *   (used for logits = s * A.B^T with s living on the device, mmgclip_model.py:132-136).
  * prec BF16: A, B are bf16 (pitches multiple of 8 elements, 16-byte aligned pointers), tcgen05/TMA kernel.
  * prec FP32: A, B are fp32, SIMT FFMA kernel.  k_splits > 1 requires mode == MMG_ATOMIC_ADD. */
 int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, float* C,
-             long long ldc, int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits,
-             mmg_stream_t stream);
+             long long ldc, int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu,
+             int mode, int k_splits, mmg_stream_t stream);
 
 /* ---- element-wise helpers -------------------------------------------------------------------------------- */
 int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream);
@@ -79,6 +81,7 @@ int mmg_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, f
 int mmg_colsum(const float* x, int rows, int cols, float* out, mmg_stream_t stream);
 
 /* MLPProjectionHead pieces (projection.py:85-101): exact-erf GELU and LayerNorm(eps) over the last dim. */
+int mmg_add(const float* x, const float* y, float* out, long long n, mmg_stream_t stream); /* residual x + y */
 int mmg_gelu_fwd(const float* x, float* y, long long n, mmg_stream_t stream);
 int mmg_gelu_bwd(const float* dy, const float* x, float* dx, long long n, mmg_stream_t stream);
 int mmg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
@@ -106,11 +109,19 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
 int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                      float inv_two_b, float* loss_out, mmg_stream_t stream);
 
-/* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c], scal[0] = dcoef = 2*s*gl*inv_two_b.
- * grad_loss is a DEVICE scalar (upstream gradient of the loss; 1 for a bare loss.backward()). */
+/* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c]; scal[1] = dcoef = 2*s*gl*inv_two_b;
+ * scal[0] = the diagonal coefficient mmg_infonce_bwd itself subtracts: dcoef, or 0 when diag_in_fp32 != 0 and the
+ * caller applies the matching-pair term with mmg_infonce_bwd_diag (what the bf16 path does, see below).  scal has room
+ * for 4 floats.  grad_loss is a DEVICE scalar (upstream gradient of the loss; 1 for a bare loss.backward()). */
 int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                         const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
-                         mmg_stream_t stream);
+                         const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
+                         float* scal, mmg_stream_t stream);
+
+/* Matching-pair term of the gradient applied from the fp32 embeddings (keeps the bf16 operand rounding out of the
+ * dominant term).  b32 and dB point at the `rows` column-side rows paired with the local rows (column diag_offset+r):
+ *   dA[r,:] -= dcoef*b32[r,:],   dB[r,:] -= dcoef*a32[r,:],   dlogscale_acc -= dcoef * sum_r <a32[r], b32[r]>. */
+int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+                         float* dlogscale_acc, mmg_stream_t stream);
 
 /* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
  *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - dcoef*[c == r + diag_offset]      ( = s * dloss/dlogit )
@@ -121,14 +132,16 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
                     float* dlogscale_acc, int block_rows, int block_cols, void* workspace, size_t workspace_bytes,
                     mmg_stream_t stream);
 
-/* ---- literal CLIPLoss on materialised logits (losses.py:28-44) ------------------------------------------- */
-/* logits: fp32 row-major [n, m] (m >= n), labels = arange(n).  lse[n] kept for the backward.
- * loss_out[0] += coef * sum_r (lse[r] - logits[r,r]). */
-int mmg_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
-                      mmg_stream_t stream);
-/* dlogits[r,c] = coef * gl * (exp(logits[r,c] - lse[r]) - [r == c]) */
-int mmg_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
-                      float coef, float* dlogits, long long ldd, mmg_stream_t stream);
+/* ---- literal cross-entropy on materialised logits (losses.py:28-44, 207-212) ----------------------------- */
+/* F.cross_entropy(logits[n, m], labels) pieces; labels: int64 DEVICE array [n] or NULL = arange(n) (needs n <= m).
+ * lse[n] is kept for the backward.   loss_out[0] += coef * sum_r (lse[r] - logits[r, labels[r]]). */
+int mmg_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
+               float* loss_out, mmg_stream_t stream);
+/* dlogits[r,c] = coef * gl * (exp(logits[r,c] - lse[r]) - [c == labels[r]]) */
+int mmg_ce_bwd(const float* logits, long long ld, int n, int m, const long long* labels, const float* lse,
+               const float* grad_loss, float coef, float* dlogits, long long ldd, mmg_stream_t stream);
+/* out[0] = sum_i x[i]*y[i] (deterministic); d logit_scale of materialised logits s*(A.B^T). */
+int mmg_dot_sum(const float* x, const float* y, long long n, float* out, mmg_stream_t stream);
 
 /* ---- zero-shot prompt scoring (mmgclip_model.py:201-209; evaluator.py:182-188,282-299,354-368) ------------- */
 /* logits[n,c] = (s*img[n,:]) . txt[c,:] in fp32 (scale-then-multiply, as the reference's operator precedence does),

@@ -25,14 +25,16 @@ SIGNATURES = {
     "mmg_version": (c_int, []),
     "mmg_last_error_string": (c_char_p, []),
     "mmg_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mmg_kernel_launch_count": (c_longlong, []),
     "mmg_gemm": (c_int, [c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong,
-                         c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+                         c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mmg_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmg_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mmg_dropout_apply": (c_int, [c_void_p, c_void_p, c_float, c_longlong, c_void_p]),
     "mmg_relu_dropout_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_void_p]),
     "mmg_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mmg_add": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_gelu_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
@@ -43,13 +45,16 @@ SIGNATURES = {
     "mmg_infonce_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmg_infonce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]),
-    "mmg_infonce_bwd_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                     c_void_p, c_void_p]),
+    "mmg_infonce_bwd_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "mmg_infonce_bwd_diag": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
     "mmg_infonce_bwd": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "mmg_ce_arange_fwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "mmg_ce_arange_bwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
-                                  c_longlong, c_void_p]),
+    "mmg_ce_fwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmg_ce_bwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                           c_longlong, c_void_p]),
+    "mmg_dot_sum": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     "mmg_zeroshot_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p]),
 }

@@ -5,12 +5,17 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/mmgclip_b200.h"
 #include "kernels.h"
 
 namespace mmg {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -64,6 +69,8 @@ extern "C" {
 
 int mmg_version(void) { return 100; }
 
+long long mmg_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 const char* mmg_last_error_string(void) { return g_err; }
 
 int mmg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -86,8 +93,8 @@ int mmg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, float* C,
-             long long ldc, int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits,
-             mmg_stream_t stream) {
+             long long ldc, int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,
+             int k_splits, mmg_stream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: empty problem %dx%dx%d", M, N, K);
   if (mode < 0 || mode > 2) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: bad store mode %d", mode);
   MMG_REQ(A);
@@ -96,11 +103,11 @@ int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, lo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (prec == MMG_PREC_BF16) {
     TcOperand a{A, lda, a_mn}, b{B, ldb, b_mn};
-    return tc_gemm_store(a, b, C, ldc, M, N, K, alpha, bias, relu, mode, k_splits, st);
+    return tc_gemm_store(a, b, C, ldc, M, N, K, alpha, alpha_dev, bias, relu, mode, k_splits, st);
   }
   if (prec == MMG_PREC_FP32)
     return simt_gemm(static_cast<const float*>(A), lda, a_mn, static_cast<const float*>(B), ldb, b_mn, C, ldc, M, N, K,
-                     alpha, bias, relu, mode, k_splits, st);
+                     alpha, alpha_dev, bias, relu, mode, k_splits, st);
   return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: unknown precision %d", prec);
 }
 
@@ -151,6 +158,14 @@ int mmg_colsum(const float* x, int rows, int cols, float* out, mmg_stream_t stre
   MMG_REQ(x);
   MMG_REQ(out);
   return simt_colsum(x, rows, cols, out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_add(const float* x, const float* y, float* out, long long n, mmg_stream_t stream) {
+  if (n <= 0) return 0;
+  MMG_REQ(x);
+  MMG_REQ(y);
+  MMG_REQ(out);
+  return simt_add(x, y, out, n, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_gelu_fwd(const float* x, float* y, long long n, mmg_stream_t stream) {
@@ -249,7 +264,7 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
     const int rb = rows - r0 < Rb ? rows - r0 : Rb;
     for (int c0 = 0; c0 < cols; c0 += Cb) {
       const int cb = cols - c0 < Cb ? cols - c0 : Cb;
-      MMG_TRY(simt_gemm(a + (long long)r0 * D, D, 0, b + (long long)c0 * D, D, 0, S, lds, rb, cb, D, 1.f, nullptr, 0,
+      MMG_TRY(simt_gemm(a + (long long)r0 * D, D, 0, b + (long long)c0 * D, D, 0, S, lds, rb, cb, D, 1.f, nullptr, nullptr, 0,
                         0, 1, st));
       MMG_TRY(simt_lse_block(S, lds, rb, cb, r0, c0, diag_offset, scale, rowsum, colsum, diag, st));
     }
@@ -269,8 +284,8 @@ int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag
 }
 
 int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                         const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
-                         mmg_stream_t stream) {
+                         const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
+                         float* scal, mmg_stream_t stream) {
   if (rows <= 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep: bad shape");
   MMG_REQ(rowsum);
   MMG_REQ(colsum);
@@ -279,8 +294,20 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
   MMG_REQ(rinv);
   MMG_REQ(cinv);
   MMG_REQ(scal);
-  return simt_infonce_bwd_prep(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b, rinv, cinv, scal,
+  return simt_infonce_bwd_prep(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b, diag_in_fp32, rinv, cinv, scal,
                                static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+                         float* dlogscale_acc, mmg_stream_t stream) {
+  if (rows <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_diag: bad shape");
+  MMG_REQ(a32);
+  MMG_REQ(b32);
+  MMG_REQ(scal);
+  MMG_REQ(dA);
+  MMG_REQ(dB);
+  MMG_REQ(dlogscale_acc);
+  return simt_infonce_bwd_diag(a32, b32, rows, D, scal, dA, dB, dlogscale_acc, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
@@ -329,33 +356,45 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
         const float* a = static_cast<const float*>(a_hat) + (long long)r0 * D;
         const float* b = static_cast<const float*>(b_hat) + (long long)c0 * D;
         float* S = static_cast<float*>(workspace);
-        MMG_TRY(simt_gemm(a, D, 0, b, D, 0, S, ldg, rb, cb, D, 1.f, nullptr, 0, 0, 1, st));
+        MMG_TRY(simt_gemm(a, D, 0, b, D, 0, S, ldg, rb, cb, D, 1.f, nullptr, nullptr, 0, 0, 1, st));
         MMG_TRY(simt_grad_block(S, ldg, rb, cb, 0, 0, doff, scale, rinv + r0, cinv + c0, scal, dlogscale_acc, st));
-        MMG_TRY(simt_gemm(S, ldg, 0, b, D, 1, dA + (long long)r0 * D, D, rb, D, cb, 1.f, nullptr, 0, 1, 1, st));
-        MMG_TRY(simt_gemm(S, ldg, 1, a, D, 1, dB + (long long)c0 * D, D, cb, D, rb, 1.f, nullptr, 0, 1, 1, st));
+        MMG_TRY(simt_gemm(S, ldg, 0, b, D, 1, dA + (long long)r0 * D, D, rb, D, cb, 1.f, nullptr, nullptr, 0, 1, 1, st));
+        MMG_TRY(simt_gemm(S, ldg, 1, a, D, 1, dB + (long long)c0 * D, D, cb, D, rb, 1.f, nullptr, nullptr, 0, 1, 1, st));
       }
     }
   }
   return 0;
 }
 
-int mmg_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
-                      mmg_stream_t stream) {
-  if (n <= 0 || m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_arange_fwd: need 0 < n <= m (got %d, %d)", n, m);
+int mmg_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
+               float* loss_out, mmg_stream_t stream) {
+  if (n <= 0 || m <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_fwd: bad shape %dx%d", n, m);
+  if (labels == nullptr && m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_fwd: arange labels need n <= m (%d, %d)", n, m);
   MMG_REQ(logits);
   MMG_REQ(lse);
   MMG_REQ(loss_out);
-  return simt_ce_arange_fwd(logits, ld, n, m, coef, lse, loss_out, static_cast<cudaStream_t>(stream));
+  return simt_ce_fwd(logits, ld, n, m, labels, coef, lse, loss_out, static_cast<cudaStream_t>(stream));
 }
 
-int mmg_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
-                      float coef, float* dlogits, long long ldd, mmg_stream_t stream) {
-  if (n <= 0 || m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_arange_bwd: need 0 < n <= m (got %d, %d)", n, m);
+int mmg_ce_bwd(const float* logits, long long ld, int n, int m, const long long* labels, const float* lse,
+               const float* grad_loss, float coef, float* dlogits, long long ldd, mmg_stream_t stream) {
+  if (n <= 0 || m <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_bwd: bad shape %dx%d", n, m);
+  if (labels == nullptr && m < n) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_bwd: arange labels need n <= m (%d, %d)", n, m);
   MMG_REQ(logits);
   MMG_REQ(lse);
   MMG_REQ(grad_loss);
   MMG_REQ(dlogits);
-  return simt_ce_arange_bwd(logits, ld, n, m, lse, grad_loss, coef, dlogits, ldd, static_cast<cudaStream_t>(stream));
+  return simt_ce_bwd(logits, ld, n, m, labels, lse, grad_loss, coef, dlogits, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_dot_sum(const float* x, const float* y, long long n, float* out, mmg_stream_t stream) {
+  if (n < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_dot_sum: negative length");
+  MMG_REQ(out);
+  if (n > 0) {
+    MMG_REQ(x);
+    MMG_REQ(y);
+  }
+  return simt_dot_sum(x, y, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,

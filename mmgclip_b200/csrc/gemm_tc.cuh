@@ -78,6 +78,7 @@ struct EpiStoreF32 {
     long long ldc;
     const float* bias;  // per output column, may be null
     float alpha;
+    const float* alpha_ptr;  // optional device scalar multiplied into alpha (e.g. the logit scale)
     int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
     int relu;
   };
@@ -87,6 +88,7 @@ struct EpiStoreF32 {
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;
     const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    const float alpha = P.alpha_ptr ? P.alpha * __ldg(P.alpha_ptr) : P.alpha;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 64; ++ch) {
       const int cl = half * (BN / 2) + ch * 32;
@@ -98,7 +100,7 @@ struct EpiStoreF32 {
       if (row < M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = v[j] * P.alpha;
+          float x = v[j] * alpha;
           if (P.bias != nullptr && c0 + j < N) x += __ldg(P.bias + c0 + j);
           if (P.relu) x = fmaxf(x, 0.f);
           v[j] = x;

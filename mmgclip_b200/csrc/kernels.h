@@ -10,6 +10,8 @@ namespace mmg {
 // thread-local error reporting (c_api.cu)
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+// every kernel launch of the library is counted (mmg_kernel_launch_count)
+void count_launch();
 
 // ---- tensor-core (bf16, tcgen05) launchers: tc_kernels.cu ----
 struct TcOperand {
@@ -19,7 +21,7 @@ struct TcOperand {
 };
 
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
-                  const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
+                  const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
 
 // Two independent accumulate-GEMMs in one launch (dA and dB of one logit block).
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
@@ -35,7 +37,8 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
 
 // ---- SIMT (fp32) launchers: simt_kernels.cu ----
 int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
-              int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
+              int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,
+              int k_splits, cudaStream_t st);
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
 int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
@@ -44,6 +47,7 @@ int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long lon
 int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                           long long n, cudaStream_t st);
 int simt_colsum(const float* x, int rows, int cols, float* out, cudaStream_t st);
+int simt_add(const float* x, const float* y, float* out, long long n, cudaStream_t st);
 int simt_gelu_fwd(const float* x, float* y, long long n, cudaStream_t st);
 int simt_gelu_bwd(const float* dy, const float* x, float* dx, long long n, cudaStream_t st);
 int simt_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
@@ -60,12 +64,15 @@ int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0,
 int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                       float inv_two_b, float* loss_out, cudaStream_t st);
 int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                          const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
-                          cudaStream_t st);
-int simt_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
-                       cudaStream_t st);
-int simt_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
-                       float coef, float* dlogits, long long ldd, cudaStream_t st);
+                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
+                          float* scal, cudaStream_t st);
+int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+                          float* dlogscale_acc, cudaStream_t st);
+int simt_dot_sum(const float* x, const float* y, long long n, float* out, cudaStream_t st);
+int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
+                float* loss_out, cudaStream_t st);
+int simt_ce_bwd(const float* logits, long long ld, int n, int m, const long long* labels, const float* lse,
+                const float* grad_loss, float coef, float* dlogits, long long ldd, cudaStream_t st);
 int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
                   float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
                   cudaStream_t st);

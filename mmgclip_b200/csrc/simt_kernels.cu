@@ -19,6 +19,7 @@ namespace mmg {
   do {                                                 \
     cudaError_t e__ = cudaGetLastError();              \
     if (e__ != cudaSuccess) return check_cuda(e__, what); \
+    count_launch();                                    \
   } while (0)
 
 // =====================================================================================================
@@ -28,8 +29,10 @@ namespace mmg {
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
-             float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, const float* __restrict__ bias,
-             int relu, int mode, int k_per_split) {
+             float* __restrict__ C, long long ldc, int M, int N, int K, float alpha_host,
+             const float* __restrict__ alpha_dev, const float* __restrict__ bias, int relu, int mode,
+             int k_per_split) {
+  const float alpha = alpha_dev ? alpha_host * (*alpha_dev) : alpha_host;
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x;
@@ -98,7 +101,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
 }
 
 int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
-              int M, int N, int K, float alpha, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
+              int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,
+              int k_splits, cudaStream_t st) {
   if (k_splits < 1) k_splits = 1;
   if (k_splits > 1 && mode != 2) return set_error(-1, "simt_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
   if (k_splits > 1 && relu) return set_error(-1, "simt_gemm: ReLU cannot be fused with split-K");
@@ -109,7 +113,8 @@ int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long
   dim3 grid((N + 63) / 64, (M + 63) / 64, k_splits);
   if (grid.y > 65535) return set_error(-3, "simt_gemm: M too large for the SIMT grid (%d)", M);
 #define MMG_SGEMM(AM, BM) \
-  sgemm_kernel<AM, BM><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, relu, mode, k_per_split)
+  sgemm_kernel<AM, BM><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, alpha_dev, bias, relu, \
+                                             mode, k_per_split)
   if (a_mn && b_mn) MMG_SGEMM(true, true);
   else if (a_mn) MMG_SGEMM(true, false);
   else if (b_mn) MMG_SGEMM(false, true);
@@ -320,6 +325,17 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __res
     const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
     dx[i] = dy[i] * (cdf + v * pdf);
   }
+}
+__global__ void add_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                           long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] + y[i];
+}
+int simt_add(const float* x, const float* y, float* out, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  add_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(x, y, out, n);
+  MMG_LAUNCH_CHECK("add_kernel");
+  return 0;
 }
 int simt_gelu_fwd(const float* x, float* y, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
@@ -554,31 +570,35 @@ int simt_infonce_loss(const float* rowsum, const float* colsum, const float* dia
 
 __global__ void infonce_bwd_prep_kernel(const float* __restrict__ rowsum, int rows, const float* __restrict__ colsum,
                                         int cols, const float* __restrict__ scale, const float* __restrict__ grad_loss,
-                                        float inv_two_b, float* __restrict__ rinv, float* __restrict__ cinv,
-                                        float* __restrict__ scal) {
+                                        float inv_two_b, int diag_in_fp32, float* __restrict__ rinv,
+                                        float* __restrict__ cinv, float* __restrict__ scal) {
   const float coef = (*scale) * (*grad_loss) * inv_two_b;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows) rinv[i] = coef / rowsum[i];
   if (i < cols) cinv[i] = coef / colsum[i];
-  if (i == 0) scal[0] = 2.0f * coef;
+  if (i == 0) {
+    scal[0] = diag_in_fp32 ? 0.f : 2.0f * coef;  // what the block kernels subtract on the diagonal
+    scal[1] = 2.0f * coef;                       // dcoef = s*gl/B
+  }
 }
 
 int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                          const float* grad_loss, float inv_two_b, float* rinv, float* cinv, float* scal,
-                          cudaStream_t st) {
+                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
+                          float* scal, cudaStream_t st) {
   const int n = rows > cols ? rows : cols;
   infonce_bwd_prep_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b,
-                                                           rinv, cinv, scal);
+                                                           diag_in_fp32, rinv, cinv, scal);
   MMG_LAUNCH_CHECK("infonce_bwd_prep_kernel");
   return 0;
 }
 
 // =====================================================================================================
-// literal cross-entropy with labels = arange(n) on materialised logits (losses.py:39-43)
+// literal cross-entropy on materialised logits: F.cross_entropy(logits, labels), labels == NULL -> arange(n)
+// (losses.py:39-43; AveragedMedicalCLIPLoss passes cluster labels, losses.py:207-212)
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-ce_arange_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, float coef, float* __restrict__ lse,
-                     float* __restrict__ loss_out) {
+ce_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, const long long* __restrict__ labels,
+              float coef, float* __restrict__ lse, float* __restrict__ loss_out) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   float term = 0.f;
@@ -593,7 +613,8 @@ ce_arange_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int 
     const float l = mx + logf(s);
     if (lane == 0) {
       lse[r] = l;
-      term = l - lr[r];
+      const long long lab = labels ? labels[r] : r;
+      term = l - lr[lab];
     }
   }
   __shared__ float wsum[8];
@@ -608,32 +629,104 @@ ce_arange_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int 
 }
 
 __global__ void __launch_bounds__(256)
-ce_arange_bwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, const float* __restrict__ lse,
-                     const float* __restrict__ grad_loss, float coef, float* __restrict__ dlogits, long long ldd) {
+ce_bwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, const long long* __restrict__ labels,
+              const float* __restrict__ lse, const float* __restrict__ grad_loss, float coef,
+              float* __restrict__ dlogits, long long ldd) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n) return;
   const float k = coef * (*grad_loss);
   const float l = lse[r];
+  const long long lab = labels ? labels[r] : r;
   for (int c = lane; c < m; c += 32) {
     float p = expf(logits[(long long)r * ld + c] - l);
-    if (c == r) p -= 1.0f;
+    if (c == lab) p -= 1.0f;
     dlogits[(long long)r * ldd + c] = k * p;
   }
 }
 
-int simt_ce_arange_fwd(const float* logits, long long ld, int n, int m, float coef, float* lse, float* loss_out,
-                       cudaStream_t st) {
+int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
+                float* loss_out, cudaStream_t st) {
   if (n <= 0) return 0;
-  ce_arange_fwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, coef, lse, loss_out);
-  MMG_LAUNCH_CHECK("ce_arange_fwd_kernel");
+  ce_fwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, labels, coef, lse, loss_out);
+  MMG_LAUNCH_CHECK("ce_fwd_kernel");
   return 0;
 }
-int simt_ce_arange_bwd(const float* logits, long long ld, int n, int m, const float* lse, const float* grad_loss,
-                       float coef, float* dlogits, long long ldd, cudaStream_t st) {
+int simt_ce_bwd(const float* logits, long long ld, int n, int m, const long long* labels, const float* lse,
+                const float* grad_loss, float coef, float* dlogits, long long ldd, cudaStream_t st) {
   if (n <= 0) return 0;
-  ce_arange_bwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, lse, grad_loss, coef, dlogits, ldd);
-  MMG_LAUNCH_CHECK("ce_arange_bwd_kernel");
+  ce_bwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(logits, ld, n, m, labels, lse, grad_loss, coef, dlogits, ldd);
+  MMG_LAUNCH_CHECK("ce_bwd_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// InfoNCE backward, matching-pair term in fp32.
+// The -dcoef*[r == c'] part of g carries almost all of the gradient's magnitude; multiplying it by a bf16-rounded
+// embedding would put the full 2^-9 operand rounding error straight into dA/dB.  The bf16 path therefore leaves it
+// out of the tensor-core contraction (scal[0] = 0) and applies it here from the fp32 embeddings:
+//   dA[r,:] -= dcoef * b32m[r,:]    dBm[r,:] -= dcoef * a32[r,:]    dlogscale -= dcoef * sum_r <a32[r], b32m[r]>
+// where b32m / dBm are the rows of the column side that are paired with the local rows.
+// One warp per pair; block-level fixed-order sum of the cosines, one atomic per block.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__ b32, int rows, int D,
+                        const float* __restrict__ scal, float* __restrict__ dA, float* __restrict__ dB,
+                        float* __restrict__ dlogscale_acc) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const float dcoef = scal[1];
+  float dot = 0.f;
+  if (r < rows) {
+    const float* ar = a32 + (long long)r * D;
+    const float* br = b32 + (long long)r * D;
+    float* dar = dA + (long long)r * D;
+    float* dbr = dB + (long long)r * D;
+    for (int i = lane; i < D; i += 32) {
+      const float av = ar[i], bv = br[i];
+      dot = fmaf(av, bv, dot);
+      dar[i] -= dcoef * bv;
+      dbr[i] -= dcoef * av;
+    }
+  }
+  dot = warp_sum(dot);
+  __shared__ float wsum[8];
+  if (lane == 0) wsum[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += wsum[i];
+    atomicAdd(dlogscale_acc, -dcoef * t);
+  }
+}
+
+int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+                          float* dlogscale_acc, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, scal, dA, dB, dlogscale_acc);
+  MMG_LAUNCH_CHECK("infonce_bwd_diag_kernel");
+  return 0;
+}
+
+// out[0] = sum_i x[i]*y[i]  (single block, fixed order => deterministic); used for d logit_scale of materialised logits
+__global__ void __launch_bounds__(1024)
+dot_sum_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ out) {
+  __shared__ double part[1024];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) acc += (double)x[i] * (double)y[i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)part[0];
+}
+
+int simt_dot_sum(const float* x, const float* y, long long n, float* out, cudaStream_t st) {
+  dot_sum_kernel<<<1, 1024, 0, st>>>(x, y, n, out);
+  MMG_LAUNCH_CHECK("dot_sum_kernel");
   return 0;
 }
 

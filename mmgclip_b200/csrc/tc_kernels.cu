@@ -108,13 +108,14 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(a0, b0, a1, b1, p0, p1, e0, e1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
+  count_launch();
   return 0;
 }
 
 static int pick_bn(int N) { return N > 128 ? 256 : 128; }
 
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
-                  const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
+                  const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(-1, "tc_gemm: empty problem %dx%dx%d", M, N, K);
   if (k_splits > 1 && mode != 2) return set_error(-1, "tc_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
   if (k_splits > 1 && (relu || bias)) return set_error(-1, "tc_gemm: bias/ReLU cannot be fused with split-K");
@@ -126,7 +127,7 @@ int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ld
   GemmProblem p0 = make_problem(M, N, K, BN, k_splits, A.mn_major, B.mn_major);
   GemmProblem p1 = empty_problem();
   EpiStoreF32::Params e;
-  e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.mode = mode; e.relu = relu;
+  e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
   if (BN == 256) return launch<256, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
   return launch<128, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
 }
@@ -145,7 +146,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   GemmProblem p0 = make_problem(M0, N0, K0, BN, 1, A0.mn_major, B0.mn_major);
   GemmProblem p1 = make_problem(M1, N1, K1, BN, 1, A1.mn_major, B1.mn_major);
   EpiStoreF32::Params e0, e1;
-  e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.mode = 1; e0.relu = 0;
+  e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
   if (BN == 256) return launch<256, EpiStoreF32>(ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);

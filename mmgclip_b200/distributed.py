@@ -1,0 +1,127 @@
+"""Row-sharded symmetric InfoNCE across the GPUs of one NVSwitch domain (the reference has no
+multi-GPU code at all).  One process per GPU, ``torch.distributed`` (NCCL over NVLink 5) for the exchange steps:
+
+    rank r owns rows [r*Bl, (r+1)*Bl) of both modalities
+    1. all-gather the column-side embeddings T (bf16 on the tensor-core path)          -> T_all [B, D]
+    2. fused forward on local rows x all columns: rowsum (complete), colsum (partial)  -> all-reduce colsum [B]
+    3. loss partial over own rows / own columns                                        -> all-reduce scalar
+    4. backward: dI_local complete, dT partial for ALL columns                         -> reduce-scatter to owners
+    5. d logit_scale partial                                                           -> all-reduce scalar
+
+Only the column side is gathered: with the fixed softmax shift m = s (|cos| <= 1) partial column sums add directly,
+so no running-max exchange is needed.  Head-weight gradients are summed with :func:`allreduce_gradients`.
+The collectives are abstracted behind ``torch.distributed`` so the same code runs under ``gloo`` on CPU tensors in
+the host-logic tests (tests/test_dist_gloo.py) with the kernels replaced by the oracle -- the product path always
+uses the CUDA kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _reduce_scatter_sum(out: torch.Tensor, full: torch.Tensor, group) -> None:
+    """out = this rank's slice of sum_over_ranks(full).  NCCL: one reduce-scatter; gloo (CPU host-logic tests) has no
+    reduce-scatter, so all-reduce and slice."""
+    if dist.get_backend(group) == "gloo":
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+        n = out.shape[0]
+        r = dist.get_rank(group)
+        out.copy_(full[r * n:(r + 1) * n])
+    else:
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=group)
+
+
+class _Kernels:
+    """The four local compute steps the sharded loss is made of (swappable for the gloo host-logic tests)."""
+
+    @staticmethod
+    def operand(t, prec):
+        return ops._operand(t, prec)
+
+    @staticmethod
+    def forward(a_op, b_all_op, scale, diag_offset, prec):
+        return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec)
+
+    @staticmethod
+    def loss(rowsum, colsum_slice, diag, scale, inv_two_b):
+        return ops.infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b)
+
+    @staticmethod
+    def backward(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec, a32, b32_paired):
+        return ops.infonce_backward_raw(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec,
+                                        a32=a32, b32=b32_paired)
+
+
+class _ShardedInfoNCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a_local, b_local, scale, group, prec, kernels):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        bl, D = a_local.shape
+        if b_local.shape != a_local.shape:
+            raise ValueError("each rank must hold the same number of rows of both modalities")
+        B = bl * world
+        s = scale.detach().reshape(()).to(device=a_local.device, dtype=torch.float32).contiguous()
+        a_op = kernels.operand(a_local, prec)
+        b_op = kernels.operand(b_local, prec)
+        b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
+        dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
+        off = rank * bl
+        rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec)
+        dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+        loss = kernels.loss(rowsum, colsum[off:off + bl], diag, s, 0.5 / B)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
+        ctx.scale_shape = scale.shape
+        ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach())
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        a_op, b_all, s, rowsum, colsum, a32, b32_local = ctx.saved_tensors
+        group, prec, kernels = ctx.group, ctx.prec, ctx.kernels
+        bl, D = a_op.shape
+        # fp32 embeddings for the matching-pair term: the columns paired with this rank's rows are its own b rows
+        if not (prec == "bf16" and a32.dtype == torch.float32):
+            a32 = b32_local = None
+        dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
+                                           b32_local)
+        dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)
+        _reduce_scatter_sum(dB, dB_all, group)
+        dscale = None
+        if ctx.needs_input_grad[2]:
+            dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
+            dscale = (dls / s).reshape(ctx.scale_shape)
+        return dA, dB, dscale, None, None, None
+
+
+def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, group=None, prec: Optional[str] = None,
+                     _kernels=_Kernels) -> torch.Tensor:
+    """Global symmetric InfoNCE for a batch sharded by rows; every rank gets the same (global mean) loss and, on
+    backward, the exact gradient of that global loss with respect to ITS rows (no 1/world rescaling is needed)."""
+    prec = ops._resolve(prec)
+    if not torch.is_tensor(logit_scale):
+        logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_local.device)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ops.info_nce(a_local, b_local, logit_scale, prec=prec)
+    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels)
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
+    """Sum parameter gradients across ranks: with the global loss above each rank's head gradient covers its own rows."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()

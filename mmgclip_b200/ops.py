@@ -90,7 +90,8 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
-         out: Optional[torch.Tensor] = None, alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
+         bias: Optional[torch.Tensor] = None,
          relu: bool = False, mode: int = MMG_STORE, k_splits: int = 1, prec: Optional[str] = None) -> torch.Tensor:
     """C[M,N] (op)= alpha * A . B^T.  A is [M,K] (or [K,M] if a_mn), B is [N,K] (or [K,N] if b_mn)."""
     prec = _resolve(prec)
@@ -114,7 +115,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm bias must be contiguous float32 [N]")
     check(_lib.load().mmg_gemm(_PREC[prec], _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out),
-                               out.stride(0), M, N, K, float(alpha), _p(bias), int(relu), mode, k_splits, _stream()),
+                               out.stride(0), M, N, K, float(alpha), _p(alpha_dev), _p(bias), int(relu), mode, k_splits,
+                               _stream()),
           "mmg_gemm")
     return out
 
@@ -176,8 +178,12 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
 
 
 def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, prec: str,
-                         block_rows: int = 0, block_cols: int = 0):
-    """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header."""
+                         block_rows: int = 0, block_cols: int = 0, a32=None, b32=None):
+    """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header.
+
+    When the fp32 embeddings (a32 [rows,D]; b32 [rows,D] = the column-side rows paired with the local rows) are supplied
+    to the bf16 path, the matching-pair term of the
+    gradient is applied from them in fp32 (mmg_infonce_bwd_diag) instead of through the bf16 contraction."""
     rows, D = a.shape
     cols = b.shape[0]
     dev = a.device
@@ -186,8 +192,9 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     cinv = torch.empty(cols, dtype=torch.float32, device=dev)
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
-    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b), _p(rinv),
-                                   _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
+    diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None
+    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+                                   int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
     dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
     dls = torch.zeros((), dtype=torch.float32, device=dev)
@@ -203,6 +210,10 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
                               _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
                               _stream()), "mmg_infonce_bwd")
+    if diag_fp32:
+        dBm = dB[diag_offset:diag_offset + rows]
+        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(scal), _p(dA), _p(dBm), _p(dls), _stream()),
+              "mmg_infonce_bwd_diag")
     return dA, dB, dls
 
 
@@ -384,15 +395,26 @@ class _InfoNCEFn(torch.autograd.Function):
         rowsum, colsum, diag = infonce_forward_raw(a_op, b_op, s, 0, prec)
         loss = infonce_loss_raw(rowsum, colsum, diag, s, 0.5 / n)
         ctx.prec = prec
-        ctx.save_for_backward(a_op, b_op, s, rowsum, colsum)
+        # fp32 embeddings (when that is what the caller holds) serve the matching-pair term of the backward
+        keep32 = prec == "bf16" and a_hat.dtype == torch.float32 and b_hat.dtype == torch.float32
+        ctx.keep32 = keep32
+        if keep32:
+            ctx.save_for_backward(a_op, b_op, s, rowsum, colsum, a_hat.detach().contiguous(), b_hat.detach().contiguous())
+        else:
+            ctx.save_for_backward(a_op, b_op, s, rowsum, colsum)
         ctx.scale_shape = scale.shape
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        a_op, b_op, s, rowsum, colsum = ctx.saved_tensors
+        if ctx.keep32:
+            a_op, b_op, s, rowsum, colsum, a32, b32 = ctx.saved_tensors
+        else:
+            a_op, b_op, s, rowsum, colsum = ctx.saved_tensors
+            a32 = b32 = None
         n = a_op.shape[0]
-        dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec)
+        dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec,
+                                           a32=a32, b32=b32)
         dscale = None
         if ctx.needs_input_grad[2]:
             dscale = (dls / s).reshape(ctx.scale_shape)  # d loss / d s ; sum g*cos = s * dloss/ds
@@ -409,37 +431,102 @@ def info_nce(a_hat: torch.Tensor, b_hat: torch.Tensor, logit_scale: torch.Tensor
     return _InfoNCEFn.apply(a_hat, b_hat, logit_scale, _operand(a_hat, prec), _operand(b_hat, prec), prec)
 
 
-class _CEArangeFn(torch.autograd.Function):
-    """coef * sum_r (logsumexp(logits[r]) - logits[r, r]): F.cross_entropy(logits, arange(n)) * n * coef."""
+class _CEFn(torch.autograd.Function):
+    """coef * sum_r (logsumexp(logits[r]) - logits[r, labels[r]]); labels None = arange(n)."""
 
     @staticmethod
-    def forward(ctx, logits, coef: float):
-        _need_cuda(logits)
-        if logits.dim() != 2 or logits.shape[1] < logits.shape[0]:
+    def forward(ctx, logits, labels, coef: float):
+        _need_cuda(logits, labels)
+        if logits.dim() != 2:
+            raise ValueError("cross entropy expects logits [n, m]")
+        if labels is None and logits.shape[1] < logits.shape[0]:
             raise ValueError("cross entropy with labels arange(n) needs logits [n, m] with m >= n")
         lg = logits.detach().to(torch.float32).contiguous()
         n, m = lg.shape
+        lab = None
+        if labels is not None:
+            lab = labels.detach().to(device=lg.device, dtype=torch.int64).contiguous()
+            if lab.numel() != n:
+                raise ValueError(f"Expected input batch_size ({n}) to match target batch_size ({lab.numel()}).")
         lse = torch.empty(n, dtype=torch.float32, device=lg.device)
         out = torch.zeros((), dtype=torch.float32, device=lg.device)
-        check(_lib.load().mmg_ce_arange_fwd(_p(lg), lg.stride(0), n, m, float(coef), _p(lse), _p(out), _stream()),
-              "mmg_ce_arange_fwd")
+        check(_lib.load().mmg_ce_fwd(_p(lg), lg.stride(0), n, m, _p(lab), float(coef), _p(lse), _p(out), _stream()),
+              "mmg_ce_fwd")
         ctx.coef = coef
-        ctx.save_for_backward(lg, lse)
+        ctx.has_labels = lab is not None
+        if lab is not None:
+            ctx.save_for_backward(lg, lse, lab)
+        else:
+            ctx.save_for_backward(lg, lse)
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        lg, lse = ctx.saved_tensors
+        if ctx.has_labels:
+            lg, lse, lab = ctx.saved_tensors
+        else:
+            lg, lse = ctx.saved_tensors
+            lab = None
         n, m = lg.shape
         d = torch.empty_like(lg)
         gl = grad.reshape(()).to(torch.float32).contiguous()
-        check(_lib.load().mmg_ce_arange_bwd(_p(lg), lg.stride(0), n, m, _p(lse), _p(gl), float(ctx.coef), _p(d),
-                                            d.stride(0), _stream()), "mmg_ce_arange_bwd")
-        return d, None
+        check(_lib.load().mmg_ce_bwd(_p(lg), lg.stride(0), n, m, _p(lab), _p(lse), _p(gl), float(ctx.coef), _p(d),
+                                     d.stride(0), _stream()), "mmg_ce_bwd")
+        return d, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.cross_entropy(logits, labels) with mean reduction; labels None = arange(n)."""
+    return _CEFn.apply(logits, labels, 1.0 / logits.shape[0])
 
 
 def ce_arange(logits: torch.Tensor, coef: float) -> torch.Tensor:
-    return _CEArangeFn.apply(logits, coef)
+    return _CEFn.apply(logits, None, coef)
+
+
+class _LogitsFn(torch.autograd.Function):
+    """L = (s * A) @ B^T materialised (mmgclip_model.py:135-136) -- the n != m / evaluation / small-n case."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale, prec: str):
+        _need_cuda(a, b)
+        n, D = a.shape
+        m = b.shape[0]
+        if b.shape[1] != D:
+            raise ValueError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{D} and {b.shape[1]}x{m})")
+        s = scale.detach().reshape(()).to(device=a.device, dtype=torch.float32).contiguous()
+        ao, bo = _operand(a, prec), _operand(b, prec)
+        logits = gemm(ao, bo, n, m, D, alpha_dev=s, prec=prec)  # s applied in the contraction's epilogue
+        ctx.prec = prec
+        ctx.scale_shape = scale.shape
+        ctx.save_for_backward(ao, bo, s, logits)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dL):
+        ao, bo, s, logits = ctx.saved_tensors
+        prec = ctx.prec
+        n, D = ao.shape
+        m = bo.shape[0]
+        dL = dL.contiguous()
+        dLo = cast_bf16(dL) if prec == "bf16" else dL
+        dA = dB = dS = None
+        if ctx.needs_input_grad[0]:
+            dA = gemm(dLo, bo, n, D, m, b_mn=True, alpha_dev=s, prec=prec)
+        if ctx.needs_input_grad[1]:
+            dB = gemm(dLo, ao, m, D, n, a_mn=True, b_mn=True, alpha_dev=s, prec=prec)
+        if ctx.needs_input_grad[2]:
+            out = torch.empty((), dtype=torch.float32, device=dL.device)
+            check(_lib.load().mmg_dot_sum(_p(dL), _p(logits), dL.numel(), _p(out), _stream()), "mmg_dot_sum")
+            dS = (out / s).reshape(ctx.scale_shape)  # sum dL*logits = s * sum dL*cos; 0-d glue only
+        return dA, dB, dS, None
+
+
+def similarity_logits(a_hat, b_hat, logit_scale, prec: Optional[str] = None) -> torch.Tensor:
+    prec = _resolve(prec)
+    if not torch.is_tensor(logit_scale):
+        logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_hat.device)
+    return _LogitsFn.apply(a_hat, b_hat, logit_scale, prec)
 
 
 class _GeluFn(torch.autograd.Function):
@@ -463,6 +550,26 @@ class _GeluFn(torch.autograd.Function):
 
 def gelu(x):
     return _GeluFn.apply(x)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        _need_cuda(x, y)
+        if x.shape != y.shape:
+            raise ValueError("residual_add expects equal shapes")
+        x, y = x.contiguous(), y.contiguous()
+        out = torch.empty_like(x)
+        check(_lib.load().mmg_add(_p(x), _p(y), _p(out), x.numel(), _stream()), "mmg_add")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def residual_add(x, y):
+    return _AddFn.apply(x, y)
 
 
 class _LayerNormFn(torch.autograd.Function):

@@ -1,0 +1,237 @@
+"""GPU parity: the CUDA path (through the Python boundary -> C ABI) against the golden vectors frozen from the
+reference's own source files and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path 1e-5 relative, bf16 path 2e-3 relative; labels/indices bit-exact.
+"Relative" is max-abs error over the max-abs of the reference tensor (loss: relative to the loss value)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import fro_err, rel_err
+from oracle import clip_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-3}
+
+
+def cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.fixture(scope="module")
+def mm():
+    from mmgclip_b200 import losses, model, ops, projection
+    return type("M", (), {"ops": ops, "losses": losses, "projection": projection, "model": model})
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_linear_heads_clip_loss_vs_reference_fixture(mm, golden, prec):
+    g = golden("clip_linear_small")
+    P = mm.projection
+    hi = P.LinearProjectionLayer(96, 64, precision=prec).cuda()
+    ht = P.LinearProjectionLayer(80, 64, precision=prec).cuda()
+    hi.load_state_dict({"layer.weight": cuda(g["w_image"])})
+    ht.load_state_dict({"layer.weight": cuda(g["w_text"])})
+    ls = torch.tensor(float(g["logit_scale_log"]), device="cuda", requires_grad=True)
+    ie = hi.forward_normalized(cuda(g["xi"]))
+    te = ht.forward_normalized(cuda(g["xt"]))
+    ie.retain_grad(); te.retain_grad()
+    loss, labels = mm.losses.CLIPLoss(precision=prec)(image_embeddings=ie, text_embeddings=te, logit_scale=ls.exp(),
+                                                      logits_per_image=None, logits_per_text=None)
+    loss.backward()
+    tol = TOL[prec]
+    assert labels.dtype == torch.int64 and labels.is_cuda and labels.tolist() == g["labels"].tolist()
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < tol
+    assert rel_err(ie.detach().cpu(), g["image_embeddings"]) < max(tol, 2e-6) * (2 if prec == "bf16" else 1)
+    assert rel_err(ie.grad.cpu(), g["d_image_embeddings"]) < tol
+    assert rel_err(te.grad.cpu(), g["d_text_embeddings"]) < tol
+    assert rel_err(hi.layer.weight.grad.cpu(), g["dw_image"]) < tol * (3 if prec == "bf16" else 1)
+    assert rel_err(ht.layer.weight.grad.cpu(), g["dw_text"]) < tol * (3 if prec == "bf16" else 1)
+    assert fro_err(hi.layer.weight.grad.cpu(), g["dw_image"]) < tol
+    assert abs(ls.grad.item() - float(g["dlogit_scale_log"])) < tol * max(1.0, abs(float(g["dlogit_scale_log"])))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_cfg1_shape_b32_768_512(mm, golden, prec):
+    """BASELINE config 1: batch 32, 768-d features, projection 512 (train_prompt_clf shape)."""
+    g = golden("clip_cfg1_b32_768_512")
+    xi, xt = oc.synthetic_features(32, 768, 768, seed=int(g["seed_inputs"]))
+    wi, wt = oc.synthetic_head_weights(512, 768, 768, seed=int(g["seed_weights"]))
+    P = mm.projection
+    hi, ht = P.LinearProjectionLayer(768, 512, precision=prec).cuda(), P.LinearProjectionLayer(768, 512, precision=prec).cuda()
+    hi.load_state_dict({"layer.weight": cuda(wi)})
+    ht.load_state_dict({"layer.weight": cuda(wt)})
+    ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
+    ie, te = hi.forward_normalized(cuda(xi)), ht.forward_normalized(cuda(xt))
+    loss, _ = mm.losses.CLIPLoss(precision=prec)(image_embeddings=ie, text_embeddings=te, logit_scale=ls.exp())
+    loss.backward()
+    tol = TOL[prec]
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < tol
+    gi = hi.layer.weight.grad.cpu().numpy()
+    gt = ht.layer.weight.grad.cpu().numpy()
+    assert abs(np.linalg.norm(gi.astype(np.float64)) / float(g["dw_image_fro"]) - 1) < tol
+    assert abs(np.linalg.norm(gt.astype(np.float64)) / float(g["dw_text_fro"]) - 1) < tol
+    scale = np.abs(gi).max()
+    assert np.abs(gi[:32, :32] - g["dw_image_block"]).max() / scale < tol * (3 if prec == "bf16" else 1)
+    assert abs(ls.grad.item() - float(g["dlogit_scale_log"])) < tol * max(1.0, abs(float(g["dlogit_scale_log"])))
+
+
+def _load_head(head, g, tag):
+    head.load_state_dict({k[len(f"p_{tag}."):]: cuda(v) for k, v in g.items() if k.startswith(f"p_{tag}.")})
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["multilinear", "mlp"])
+def test_deep_heads_vs_reference_fixture(mm, golden, prec, kind):
+    g = golden(f"clip_{kind}_small")
+    P = mm.projection
+    if kind == "multilinear":
+        dims = g["dims"].tolist()
+        hi, ht = P.MultiLinearHead(48, dims, dropout=0.5, precision=prec), P.MultiLinearHead(40, dims, dropout=0.5, precision=prec)
+    else:
+        hi, ht = P.MLPProjectionHead(48, 32, dropout=0.5, precision=prec), P.MLPProjectionHead(40, 32, dropout=0.5, precision=prec)
+    hi, ht = hi.cuda().eval(), ht.cuda().eval()
+    _load_head(hi, g, "i"); _load_head(ht, g, "t")
+    ie = mm.ops.l2_normalize(hi(cuda(g["xi"])), prec=prec)
+    te = mm.ops.l2_normalize(ht(cuda(g["xt"])), prec=prec)
+    s = torch.tensor(math.log(1 / 0.07), device="cuda").exp()
+    loss, _ = mm.losses.CLIPLoss(precision=prec)(image_embeddings=ie, text_embeddings=te, logit_scale=s)
+    loss.backward()
+    tol = TOL[prec]
+    # hidden ReLU units whose pre-activation is within rounding of zero may flip under bf16; embeddings stay within 3*tol
+    assert rel_err(ie.detach().cpu(), g["image_embeddings"]) < 3 * tol
+    assert rel_err(te.detach().cpu(), g["text_embeddings"]) < 3 * tol
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < (tol if prec == "fp32" else 5 * tol)
+    for tag, head in (("i", hi), ("t", ht)):
+        for k, p in head.named_parameters():
+            ref = g[f"g_{tag}.{k}"]
+            err = fro_err(p.grad.cpu(), ref)
+            assert err < (2e-5 if prec == "fp32" else 2e-2), (k, err)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mmgclip_loss_vs_reference_fixture(mm, golden, prec):
+    g = golden("mmgclip_loss_small")
+    ie, te, te2 = (cuda(g[k]).requires_grad_() for k in ("image_embeddings", "text_embeddings", "text_embeddings2"))
+    s = cuda(g["logit_scale"]).requires_grad_()
+    loss, labels = mm.losses.MMGCLIPLoss(t2t_weight=0.5, precision=prec)(
+        image_embeddings=ie, text_embeddings=te, text_embeddings2=te2, logit_scale=s, logits_per_image=None)
+    loss.backward()
+    tol = TOL[prec]
+    assert labels.tolist() == list(range(20))
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < tol
+    assert rel_err(ie.grad.cpu(), g["d_image_embeddings"]) < tol
+    assert rel_err(te.grad.cpu(), g["d_text_embeddings"]) < tol
+    assert rel_err(te2.grad.cpu(), g["d_text_embeddings2"]) < tol
+    assert abs(s.grad.item() - float(g["d_logit_scale"])) < tol * max(1.0, abs(float(g["d_logit_scale"])))
+
+
+def test_literal_logit_signature_known_answers(mm, golden):
+    """CLIPLoss(logits_per_image, logits_per_text) exactly as the reference is called; KAT 2.1586060524."""
+    k = golden("reference_kats")
+    lg = cuda(k["logits8"]).requires_grad_()
+    loss, labels = mm.losses.CLIPLoss()(lg, lg.t().contiguous())
+    assert abs(loss.item() - 2.1586060524) < 2e-6
+    assert labels.tolist() == list(range(8)) and labels.is_cuda
+    loss.backward()
+    ref = torch.from_numpy(k["logits8"]).requires_grad_()
+    l_ref, _ = oc.torch_clip_loss(ref, ref.t())
+    l_ref.backward()
+    assert rel_err(lg.grad.cpu(), ref.grad) < 1e-5
+    # AveragedMedicalCLIPLoss: notebook KAT (averaged CE 1.2048) and a full forward frozen from the reference
+    am = mm.losses.AveragedMedicalCLIPLoss()
+    avg = am._average_logits(cuda(k["logits8"]), k["notebook_labels"].tolist())
+    assert rel_err(avg.cpu(), k["notebook_avg_logits"]) < 1e-6
+    ce = mm.ops.cross_entropy(avg, cuda(k["notebook_labels"]))
+    assert abs(ce.item() - 1.2048) < 5e-5
+    loss_am, lab = mm.losses.AveragedMedicalCLIPLoss(0.65)(
+        cuda(k["am_image_embeddings"]), cuda(k["am_text_embeddings"]), cuda(k["am_logit_scale"]),
+        cuda(k["am_logits_per_image"]), cuda(k["am_logits_per_text"]))
+    assert lab.tolist() == k["am_labels"].tolist()
+    assert abs(loss_am.item() - float(k["am_loss"])) < 1e-5 * float(k["am_loss"])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n,d", [(1, 64), (7, 40), (129, 256), (1000, 512), (4096, 512)])
+def test_infonce_vs_closed_form_ragged_sizes(mm, prec, n, d):
+    """Empty-ish / ragged / multi-tile batches against the float64 closed form (seeded inputs)."""
+    rng = np.random.RandomState(n * 31 + d)
+    a = rng.standard_normal((n, d)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = rng.standard_normal((n, d)) + 0.7 * a; b /= np.linalg.norm(b, axis=1, keepdims=True)
+    s32 = float(np.float32(1 / 0.07))
+    ref = oc.closed_form_info_nce(a, b, s32)
+    at, bt = cuda(a.astype(np.float32)).requires_grad_(), cuda(b.astype(np.float32)).requires_grad_()
+    st = torch.tensor(s32, device="cuda", requires_grad=True)
+    loss = mm.ops.info_nce(at, bt, st, prec=prec)
+    (2.0 * loss).backward()  # non-unit upstream gradient
+    tol = TOL[prec]
+    assert abs(loss.item() - ref["loss"]) <= tol * max(ref["loss"], 1.0)
+    assert rel_err(at.grad.cpu(), 2.0 * ref["da"], floor=1e-3) < tol   # n = 1: the exact gradient is zero
+    assert rel_err(bt.grad.cpu(), 2.0 * ref["db"], floor=1e-3) < tol
+    assert abs(st.grad.item() - 2.0 * ref["ds"]) < tol * max(1e-3, abs(2.0 * ref["ds"]), 1e-2)
+
+
+def test_zero_row_gives_nan_like_the_reference(mm):
+    """Quirk Q3: no epsilon in the normalisation -- an all-zero projected row is NaN there and here."""
+    u = torch.randn(4, 32, device="cuda")
+    u[2] = 0
+    y = mm.ops.l2_normalize(u, prec="fp32")
+    assert torch.isnan(y[2]).all() and torch.isfinite(y[[0, 1, 3]]).all()
+
+
+def test_bf16_full_size_properties(mm):
+    """BASELINE config 2 size (B = 4096, D = 512) and a 5-block ragged size: size-independent properties.
+
+    (1) a<->b swap symmetry, (2) invariance to the gradient block shape, (3) row-sharded evaluation (two 'ranks' on one
+    GPU through the raw offsets API) == unsharded, (4) sampled rows against float64, (5) no O(B^2) allocation."""
+    ops = mm.ops
+    for n in (4096, 9000):
+        d = 512
+        gen = torch.Generator(device="cuda").manual_seed(n)
+        a = torch.nn.functional.normalize(torch.randn(n, d, device="cuda", generator=gen), dim=1)
+        b = torch.nn.functional.normalize(torch.randn(n, d, device="cuda", generator=gen) + 0.5 * a, dim=1)
+        s = torch.tensor(float(np.float32(1 / 0.07)), device="cuda")
+        ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        rs, cs, dg = ops.infonce_forward_raw(ab, bb, s, 0, "bf16")
+        loss = ops.infonce_loss_raw(rs, cs, dg, s, 0.5 / n)
+        one = torch.ones((), device="cuda")
+        dA, dB, dls = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / n, 0, "bf16", a32=a, b32=b)
+        peak = torch.cuda.max_memory_allocated() - base
+        assert peak < 2 * 4096 * 4096 * 2 + 64 * n * d, peak     # block scratch + O(B*D); B*B*4 would be 64-324 MB more
+        # (1) swap symmetry
+        rs2, cs2, dg2 = ops.infonce_forward_raw(bb, ab, s, 0, "bf16")
+        loss2 = ops.infonce_loss_raw(rs2, cs2, dg2, s, 0.5 / n)
+        assert abs(loss.item() - loss2.item()) < 1e-5 * loss.item()
+        assert rel_err(rs.cpu(), cs2.cpu()) < 1e-5 and rel_err(cs.cpu(), rs2.cpu()) < 1e-5
+        # (2) block-shape invariance of the backward
+        dA2, dB2, dls2 = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / n, 0, "bf16", 1024, 2048, a32=a, b32=b)
+        assert rel_err(dA2.cpu(), dA.cpu()) < 2e-4 and rel_err(dB2.cpu(), dB.cpu()) < 2e-4
+        assert abs(dls2.item() - dls.item()) < 1e-3 * abs(dls.item()) + 1e-6
+        # (3) two row shards with offsets, partial sums added
+        h = n // 2
+        rsa, csa, dga = ops.infonce_forward_raw(ab[:h], bb, s, 0, "bf16")
+        rsb, csb, dgb = ops.infonce_forward_raw(ab[h:], bb, s, h, "bf16", colsum=csa)
+        assert rel_err(torch.cat([rsa, rsb]).cpu(), rs.cpu()) < 1e-5
+        assert rel_err(csb.cpu(), cs.cpu()) < 1e-5
+        assert rel_err(torch.cat([dga, dgb]).cpu(), dg.cpu()) < 1e-6
+        dAb, dBb, _ = ops.infonce_backward_raw(ab[h:], bb, s, rs[h:], cs, one, 0.5 / n, h, "bf16", a32=a[h:], b32=b[h:])
+        assert rel_err(dAb.cpu(), dA[h:].cpu()) < 2e-4
+        # (4) 48 sampled rows against float64 on the host (operands as the kernel sees them: bf16-rounded)
+        idx = np.random.RandomState(0).choice(n, 48, replace=False)
+        a64, b64 = ab.double().cpu().numpy(), bb.double().cpu().numpy()
+        sv = float(s.item())
+        cos = a64[idx] @ b64.T
+        e = np.exp(sv * cos - sv)
+        assert rel_err(rs.cpu().numpy()[idx], e.sum(1)) < 2e-4
+        assert rel_err(dg.cpu().numpy()[idx], sv * cos[np.arange(48), idx]) < 1e-5
+        cs64 = cs.double().cpu().numpy()
+        coef = sv * 0.5 / n
+        g = e * (coef / e.sum(1)[:, None] + coef / cs64[None, :])
+        g[np.arange(48), idx] -= 2 * coef
+        ref_da = g @ b.double().cpu().numpy()
+        assert rel_err(dA.cpu().numpy()[idx], ref_da) < 2e-3
