@@ -57,20 +57,25 @@ long long mmg_kernel_launch_count(void);   /* kernels launched by this library s
  *   C: fp32 row-major [M, N]; bias: fp32 [N] or NULL; alpha_dev: optional DEVICE scalar multiplied into alpha
  *   (used for logits = s * A.B^T with s living on the device, mmgclip_model.py:132-136).
  * prec BF16: A, B are bf16 (pitches multiple of 8 elements, 16-byte aligned pointers), tcgen05/TMA kernel.
- * prec FP32: A, B are fp32, SIMT FFMA kernel.  k_splits > 1 requires mode == MMG_ATOMIC_ADD. */
+ * prec FP32: A, B are fp32, SIMT FFMA kernel.  k_splits > 1 requires mode == MMG_ATOMIC_ADD.
+ * With MMG_ACCUMULATE the result is act(C_old + alpha*A.B^T + bias), i.e. bias/ReLU belong on the LAST pass. */
 int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, float* C,
              long long ldc, int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu,
              int mode, int k_splits, mmg_stream_t stream);
 
 /* ---- element-wise helpers -------------------------------------------------------------------------------- */
 int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream);
+/* hi = bf16(x), lo = bf16(x - hi): operands of the three-pass "bf16x3" contraction A_hi.B_hi + A_hi.B_lo + A_lo.B_hi that
+ * keeps the projection heads fp32-faithful (~2^-17 per operand) on the bf16 tensor pipe. */
+int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, long long n, mmg_stream_t stream);
 
 /* Row-wise L2 normalisation y = u / ||u||_2, no epsilon (mmgclip/networks/mmgclip_model.py:128-129,163;
  * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_bf16 (nullable) receives a bf16 copy. */
 int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream);
-/* du = (dy - y * <y, dy>) * inv_norm   (autograd of the line above).  du_bf16 nullable. */
+/* du = (dy - y * <y, dy>) * inv_norm   (autograd of the line above).  Outputs (each nullable, at least one): du fp32,
+ * du_bf16 = bf16(du), du_bf16_lo = bf16(du - du_bf16) for the bf16x3 weight-gradient contraction. */
 int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                   mmg_stream_t stream);
+                   void* du_bf16_lo, mmg_stream_t stream);
 
 /* Hidden-layer pieces of MultiLinearHead (projection.py:54-61): ReLU/inverted-dropout backward and bias gradient.
  *   dz[i] = dy[i] * (y ? y[i] > 0 : 1) * (mask ? mask[i] * keep_scale : 1)      db[n] = sum_rows dz[:, n]

@@ -98,31 +98,47 @@ struct EpiStoreF32 {
       tmem_ld_32x32b_x32(tacc + cl, v);
       tmem_ld_wait();
       if (row < M) {
+        const bool vec = vec_ok && c0 + 32 <= N;
+        // C = act(C_old + alpha*acc + bias): accumulate first, then bias / activation (multi-pass contractions)
+        if (P.mode == 1) {
+          if (vec) {
+            const float4* src = reinterpret_cast<const float4*>(crow + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j] * alpha;
-          if (P.bias != nullptr && c0 + j < N) x += __ldg(P.bias + c0 + j);
-          if (P.relu) x = fmaxf(x, 0.f);
-          v[j] = x;
+            for (int j = 0; j < 8; ++j) {
+              const float4 old = src[j];
+              v[4 * j] = fmaf(v[4 * j], alpha, old.x);
+              v[4 * j + 1] = fmaf(v[4 * j + 1], alpha, old.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], alpha, old.z);
+              v[4 * j + 3] = fmaf(v[4 * j + 3], alpha, old.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < N) v[j] = fmaf(v[j], alpha, crow[c0 + j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= alpha;
         }
-        if (vec_ok && c0 + 32 <= N && P.mode != 2) {
+        if (P.bias != nullptr || P.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j];
+            if (P.bias != nullptr && c0 + j < N) x += __ldg(P.bias + c0 + j);
+            if (P.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+          }
+        }
+        if (vec && P.mode != 2) {
           float4* dst = reinterpret_cast<float4*>(crow + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (P.mode == 1) {
-              const float4 old = dst[j];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            dst[j] = o;
-          }
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (c0 + j < N) {
-              if (P.mode == 0) crow[c0 + j] = v[j];
-              else if (P.mode == 1) crow[c0 + j] += v[j];
-              else atomicAdd(crow + c0 + j, v[j]);
+              if (P.mode == 2) atomicAdd(crow + c0 + j, v[j]);
+              else crow[c0 + j] = v[j];
             }
           }
         }

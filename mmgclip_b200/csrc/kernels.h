@@ -40,9 +40,10 @@ int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long
               int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,
               int k_splits, cudaStream_t st);
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
+int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st);
 int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                    cudaStream_t st);
+                    void* du_bf16_lo, cudaStream_t st);
 int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st);
 int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                           long long n, cudaStream_t st);

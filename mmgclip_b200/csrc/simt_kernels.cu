@@ -89,13 +89,13 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
+      float* dst = C + (long long)gm * ldc + gn;
       float v = acc[i][j] * alpha;
+      if (mode == 1) v += *dst;  // accumulate first, then bias / activation: C = act(C + alpha*acc + bias)
       if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
       if (relu) v = fmaxf(v, 0.f);
-      float* dst = C + (long long)gm * ldc + gn;
-      if (mode == 0) *dst = v;
-      else if (mode == 1) *dst += v;
-      else atomicAdd(dst, v);
+      if (mode == 2) atomicAdd(dst, v);
+      else *dst = v;
     }
   }
 }
@@ -146,11 +146,32 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
   }
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits survive, so the three-product contraction
+// A_hi.B_hi + A_hi.B_lo + A_lo.B_hi on the bf16 tensor pipe is accurate to ~2^-17 per operand ("bf16x3").
+__global__ void cast_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 static inline int ew_blocks(long long n, int per_thread) {
   long long b = (n / per_thread + 255) / 256;
   if (b < 1) b = 1;
   if (b > 148 * 16) b = 148 * 16;
   return (int)b;
+}
+
+int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  cast_split_kernel<<<ew_blocks(n, 2), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                     reinterpret_cast<__nv_bfloat16*>(lo), n);
+  MMG_LAUNCH_CHECK("cast_split_kernel");
+  return 0;
 }
 
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st) {
@@ -218,7 +239,7 @@ int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, voi
 
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm, int B,
-                  int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub) {
+                  int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub, __nv_bfloat16* __restrict__ dul) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -231,14 +252,19 @@ l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
   for (int i = lane; i < D; i += 32) {
     const float v = (dyr[i] - yr[i] * dot) * inv;
     if (du) du[(long long)row * D + i] = v;
-    if (dub) dub[(long long)row * D + i] = __float2bfloat16_rn(v);
+    if (dub) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      dub[(long long)row * D + i] = h;
+      if (dul) dul[(long long)row * D + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
 }
 
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                    cudaStream_t st) {
+                    void* du_bf16_lo, cudaStream_t st) {
   if (B <= 0) return 0;
-  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16));
+  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16),
+                                                 reinterpret_cast<__nv_bfloat16*>(du_bf16_lo));
   MMG_LAUNCH_CHECK("l2norm_bwd_kernel");
   return 0;
 }

@@ -89,6 +89,78 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_bf16_split(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(hi, lo) bf16 pair with hi + lo ~= x to 16 mantissa bits (operands of the bf16x3 head contractions)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        raise ValueError("cast_bf16_split expects float32 input")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().mmg_cast_f32_to_bf16_split(_p(x), _p(hi), _p(lo), x.numel(), _stream()),
+          "mmg_cast_f32_to_bf16_split")
+    return hi, lo
+
+
+# Projection heads on the bf16 tensor pipe use three passes (hi.hi + hi.lo + lo.hi) by default: they are a few percent
+# of the step's FLOPs at large batch, and it keeps embeddings and head-weight gradients fp32-faithful (~1e-5) instead of
+# carrying the 2^-9 bf16 operand rounding into every downstream quantity.  MMGCLIP_B200_SPLIT_HEADS=0 = single pass.
+_split_heads = os.environ.get("MMGCLIP_B200_SPLIT_HEADS", "1") != "0"
+
+
+def set_split_heads(flag: bool) -> None:
+    global _split_heads
+    _split_heads = bool(flag)
+
+
+class _Operand:
+    """A contraction operand for a given precision: fp32 tensor, bf16 tensor, or a (hi, lo) bf16 pair."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def of(x: torch.Tensor, prec: str) -> "_Operand":
+        if prec == "fp32":
+            return _Operand(x.contiguous())
+        if _split_heads:
+            return _Operand(*cast_bf16_split(x))
+        return _Operand(cast_bf16(x))
+
+    def tensors(self):
+        return (self.hi,) if self.lo is None else (self.hi, self.lo)
+
+    @staticmethod
+    def from_tensors(ts):
+        return _Operand(*ts)
+
+
+def gemm_heads(A: "_Operand", B: "_Operand", M: int, N: int, K: int, *, a_mn=False, b_mn=False, bias=None, relu=False,
+               k_splits: int = 1, prec: str = "bf16") -> torch.Tensor:
+    """alpha=1 contraction of head operands; split operands run hi.hi + hi.lo + lo.hi, bias/ReLU on the last pass."""
+    passes = [(A.hi, B.hi)]
+    if A.lo is not None or B.lo is not None:
+        if B.lo is not None:
+            passes.append((A.hi, B.lo))
+        if A.lo is not None:
+            passes.append((A.lo, B.hi))
+    if k_splits > 1:
+        out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
+        for (a, b) in passes:
+            gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_ATOMIC_ADD, k_splits=k_splits, prec=prec)
+        if bias is not None or relu:
+            raise ValueError("bias/ReLU cannot be combined with split-K")
+        return out
+    out = None
+    for i, (a, b) in enumerate(passes):
+        last = i == len(passes) - 1
+        out = gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_STORE if i == 0 else MMG_ACCUMULATE,
+                   bias=bias if last else None, relu=relu and last, prec=prec)
+    return out
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          out: Optional[torch.Tensor] = None, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None,
@@ -140,14 +212,19 @@ def l2norm_fwd(u: torch.Tensor, want_bf16: bool) -> Tuple[torch.Tensor, torch.Te
     return y, inv, yb
 
 
-def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: bool, want_bf16: bool):
+def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: bool, want_bf16: bool,
+               want_lo: bool = False):
     _need_cuda(dy, y, inv)
     dy = dy.contiguous()
     B, D = y.shape
     du = torch.empty_like(y) if want_f32 else None
     dub = torch.empty((B, D), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    dul = torch.empty((B, D), dtype=torch.bfloat16, device=y.device) if (want_bf16 and want_lo) else None
     if B > 0:
-        check(_lib.load().mmg_l2norm_bwd(_p(dy), _p(y), _p(inv), B, D, _p(du), _p(dub), _stream()), "mmg_l2norm_bwd")
+        check(_lib.load().mmg_l2norm_bwd(_p(dy), _p(y), _p(inv), B, D, _p(du), _p(dub), _p(dul), _stream()),
+              "mmg_l2norm_bwd")
+    if want_lo:
+        return du, dub, dul
     return du, dub
 
 
@@ -239,27 +316,28 @@ class _LinearFn(torch.autograd.Function):
             ctx.empty = True
             return x.new_zeros((0, D))
         ctx.empty = False
-        if prec == "bf16":
-            xo, wo = cast_bf16(x), cast_bf16(w)
-        else:
-            xo, wo = x, w
-        y = gemm(xo, wo, Bn, D, E, bias=b, relu=relu, prec=prec)
+        xo, wo = _Operand.of(x, prec), _Operand.of(w, prec)
+        y = gemm_heads(xo, wo, Bn, D, E, bias=b, relu=relu, prec=prec)
         if mask is not None:
             check(_lib.load().mmg_dropout_apply(_p(y), _p(mask), float(keep_scale), y.numel(), _stream()),
                   "mmg_dropout_apply")
         ctx.prec, ctx.relu, ctx.keep_scale = prec, relu, keep_scale
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(xo, wo, y if (relu or mask is not None) else None, mask)
+        ctx.nx, ctx.nw = len(xo.tensors()), len(wo.tensors())
+        ctx.shape = (Bn, E, D)
+        ctx.save_for_backward(*xo.tensors(), *wo.tensors(), y if (relu or mask is not None) else None, mask)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         if ctx.empty:
             return None, None, None, None, None, None, None
-        xo, wo, y, mask = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        xo = _Operand.from_tensors(saved[:ctx.nx])
+        wo = _Operand.from_tensors(saved[ctx.nx:ctx.nx + ctx.nw])
+        y, mask = saved[ctx.nx + ctx.nw], saved[ctx.nx + ctx.nw + 1]
         prec = ctx.prec
-        Bn, E = xo.shape
-        D = wo.shape[0]
+        Bn, E, D = ctx.shape
         dy = dy.contiguous()
         if ctx.relu or mask is not None:
             dz = torch.empty_like(dy)
@@ -268,17 +346,16 @@ class _LinearFn(torch.autograd.Function):
                                                    _stream()), "mmg_relu_dropout_bwd")
         else:
             dz = dy
-        dzo = cast_bf16(dz) if prec == "bf16" else dz
+        dzo = _Operand.of(dz, prec)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
             ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
-            dw = gemm(dzo, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks,
-                      mode=MMG_ATOMIC_ADD if ks > 1 else MMG_STORE)
+            dw = gemm_heads(dzo, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(D, dtype=torch.float32, device=dy.device)
             check(_lib.load().mmg_colsum(_p(dz), Bn, D, _p(db), _stream()), "mmg_colsum")
         if ctx.needs_input_grad[0]:
-            dx = gemm(dzo, wo, Bn, E, D, b_mn=True, prec=prec)
+            dx = gemm_heads(dzo, wo, Bn, E, D, b_mn=True, prec=prec)
         return dx, dw, db, None, None, None, None
 
 
@@ -329,14 +406,13 @@ class _ProjNormFn(torch.autograd.Function):
             raise ValueError(f"mat1 and mat2 shapes cannot be multiplied ({Bn}x{E} and {weight.shape[1]}x{D})")
         x = x.contiguous()
         w = weight.contiguous()
-        if prec == "bf16":
-            xo, wo = cast_bf16(x), cast_bf16(w)
-        else:
-            xo, wo = x, w
-        u = gemm(xo, wo, Bn, D, E, prec=prec)
+        xo, wo = _Operand.of(x, prec), _Operand.of(w, prec)
+        u = gemm_heads(xo, wo, Bn, D, E, prec=prec)
         y, inv, yb = l2norm_fwd(u, prec == "bf16")
         ctx.prec = prec
-        ctx.save_for_backward(xo, wo, y, inv)
+        ctx.nx, ctx.nw = len(xo.tensors()), len(wo.tensors())
+        ctx.shape = (Bn, E, D)
+        ctx.save_for_backward(*xo.tensors(), *wo.tensors(), y, inv)
         if yb is None:
             yb = y.new_empty(0)
         ctx.mark_non_differentiable(yb)
@@ -344,20 +420,25 @@ class _ProjNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _unused):
-        xo, wo, y, inv = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        xo = _Operand.from_tensors(saved[:ctx.nx])
+        wo = _Operand.from_tensors(saved[ctx.nx:ctx.nx + ctx.nw])
+        y, inv = saved[ctx.nx + ctx.nw], saved[ctx.nx + ctx.nw + 1]
         prec = ctx.prec
-        Bn, E = xo.shape
-        D = wo.shape[0]
+        Bn, E, D = ctx.shape
         need_dx = ctx.needs_input_grad[0]
-        du, dub = l2norm_bwd(dy, y, inv, prec == "fp32", prec == "bf16")
-        dz = dub if prec == "bf16" else du
+        if prec == "bf16":
+            split = xo.lo is not None
+            res = l2norm_bwd(dy, y, inv, False, True, want_lo=split)
+            dz = _Operand(res[1], res[2] if split else None)
+        else:
+            dz = _Operand(l2norm_bwd(dy, y, inv, True, False)[0])
         dw = dx = None
         if ctx.needs_input_grad[1]:
             ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
-            dw = gemm(dz, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks,
-                      mode=MMG_ATOMIC_ADD if ks > 1 else MMG_STORE)
+            dw = gemm_heads(dz, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if need_dx:
-            dx = gemm(dz, wo, Bn, E, D, b_mn=True, prec=prec)
+            dx = gemm_heads(dz, wo, Bn, E, D, b_mn=True, prec=prec)
         return dx, dw, None
 
 

@@ -218,7 +218,90 @@ def sec_perf():
     print(f"  perf torch.matmul bf16 8192^3: {t:.3f} ms ({2.0 * M * N * K / t / 1e9:.1f} TFLOP/s)")
 
 
+def sec_bf16_err():
+    """max-abs and Frobenius relative errors of the bf16 path vs float64 closed form, for tolerance setting."""
+    import numpy as np
+    from oracle import clip_oracle as oc
+    from mmgclip_b200.projection import LinearProjectionLayer
+
+    def fro(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+    def mx(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return np.abs(a - b).max() / np.abs(b).max()
+
+    for (n, e, d) in [(32, 96, 64), (32, 768, 512), (256, 768, 512), (2048, 768, 512), (8192, 768, 512)]:
+        xi, xt = oc.synthetic_features(n, e, e, seed=n)
+        wi, wt = oc.synthetic_head_weights(d, e, e, seed=n + 1)
+        ref = oc.closed_form_train_step(xi, xt, wi, wt, math.log(1 / 0.07))
+        hi, ht = LinearProjectionLayer(e, d, precision="bf16").cuda(), LinearProjectionLayer(e, d, precision="bf16").cuda()
+        with torch.no_grad():
+            hi.layer.weight.copy_(torch.from_numpy(wi)); ht.layer.weight.copy_(torch.from_numpy(wt))
+        ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
+        ie = hi.forward_normalized(torch.from_numpy(xi).cuda()); te = ht.forward_normalized(torch.from_numpy(xt).cuda())
+        ie.retain_grad(); te.retain_grad()
+        loss = ops.info_nce(ie, te, ls.exp(), prec="bf16")
+        loss.backward()
+        print(f"  bf16 n={n} e={e} d={d}: loss_rel={abs(loss.item() - ref['loss']) / ref['loss']:.2e} "
+              f"emb max={mx(ie.detach().cpu(), ref['image_embeddings']):.2e} "
+              f"dA max={mx(ie.grad.cpu(), ref['da']):.2e} fro={fro(ie.grad.cpu(), ref['da']):.2e} "
+              f"dB max={mx(te.grad.cpu(), ref['db']):.2e} fro={fro(te.grad.cpu(), ref['db']):.2e} "
+              f"dWi max={mx(hi.layer.weight.grad.cpu(), ref['dw_image']):.2e} fro={fro(hi.layer.weight.grad.cpu(), ref['dw_image']):.2e} "
+              f"dWt max={mx(ht.layer.weight.grad.cpu(), ref['dw_text']):.2e} fro={fro(ht.layer.weight.grad.cpu(), ref['dw_text']):.2e} "
+              f"dls={abs(ls.grad.item() - ref['dlogit_scale_log']) / max(1, abs(ref['dlogit_scale_log'])):.2e}")
+
+
+def sec_blocks():
+    def timeit(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    n, D = 32768, 512
+    g = torch.Generator(device="cpu").manual_seed(6)
+    a = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(dev)
+    b = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(dev)
+    ab, bb = a.bfloat16(), b.bfloat16()
+    s = torch.tensor(1 / 0.07, device=dev)
+    rs, cs, dg = ops.infonce_forward_raw(ab, bb, s, 0, "bf16")
+    gl = torch.ones((), device=dev)
+    fl = 2.0 * n * n * D
+    for (br, bc) in ((4096, 4096), (8192, 4096), (8192, 8192), (16384, 4096), (16384, 8192), (32768, 4096), (4736, 4736)):
+        t_b = timeit(lambda: ops.infonce_backward_raw(ab, bb, s, rs, cs, gl, 0.5 / n, 0, "bf16", br, bc))
+        import time as _t
+        t0 = _t.perf_counter()
+        ops.infonce_backward_raw(ab, bb, s, rs, cs, gl, 0.5 / n, 0, "bf16", br, bc)
+        host = (_t.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        print(f"    bwd block {br}x{bc}: {t_b:.3f} ms ({3 * fl / t_b / 1e9:.1f} TFLOP/s executed) host-side enqueue {host:.3f} ms")
+
+
+def sec_one_bwd():
+    """one forward + one backward at n=32768 (for the ncu launch list)"""
+    n, D = 32768, 512
+    g = torch.Generator(device="cpu").manual_seed(6)
+    a = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(dev)
+    b = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(dev)
+    ab, bb = a.bfloat16(), b.bfloat16()
+    s = torch.tensor(1 / 0.07, device=dev)
+    rs, cs, dg = ops.infonce_forward_raw(ab, bb, s, 0, "bf16")
+    gl = torch.ones((), device=dev)
+    ops.infonce_backward_raw(ab, bb, s, rs, cs, gl, 0.5 / n, 0, "bf16")
+    torch.cuda.synchronize()
+
+
 SECTIONS = {
+    "bf16_err": sec_bf16_err,
+    "blocks": sec_blocks,
+    "one_bwd": sec_one_bwd,
     "gemm_fp32": sec_gemm_fp32,
     "small": sec_small,
     "infonce_fp32": lambda: sec_infonce("fp32", ((8, 64), (32, 512), (200, 256), (1024, 512), (2500, 512))),
