@@ -114,22 +114,26 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
 int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                      float inv_two_b, float* loss_out, mmg_stream_t stream);
 
-/* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c]; scal[1] = dcoef = 2*s*gl*inv_two_b;
- * scal[0] = the diagonal coefficient mmg_infonce_bwd itself subtracts: dcoef, or 0 when diag_in_fp32 != 0 and the
- * caller applies the matching-pair term with mmg_infonce_bwd_diag (what the bf16 path does, see below).  scal has room
- * for 4 floats.  grad_loss is a DEVICE scalar (upstream gradient of the loss; 1 for a bare loss.backward()). */
+/* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c]; scal (4 floats): [1] = dcoef =
+ * 2*s*gl*inv_two_b; [0] = the diagonal coefficient mmg_infonce_bwd itself subtracts (dcoef, or 0 when diag_in_fp32);
+ * [2] = diag_in_fp32 flag: mmg_infonce_bwd then ZEROES the matching-pair element of g and the caller applies it with
+ * mmg_infonce_bwd_diag (what the bf16 path does).  grad_loss is a DEVICE scalar (1 for a bare loss.backward()). */
 int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                          float* scal, mmg_stream_t stream);
 
-/* Matching-pair term of the gradient applied from the fp32 embeddings (keeps the bf16 operand rounding out of the
- * dominant term).  b32 and dB point at the `rows` column-side rows paired with the local rows (column diag_offset+r):
- *   dA[r,:] -= dcoef*b32[r,:],   dB[r,:] -= dcoef*a32[r,:],   dlogscale_acc -= dcoef * sum_r <a32[r], b32[r]>. */
-int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+/* Matching-pair element of the gradient applied from the fp32 embeddings (keeps the bf16 operand rounding out of the
+ * dominant, heavily cancelling term).  b32, dB and cinv_paired point at the `rows` column-side entries paired with the
+ * local rows (column diag_offset + r); diag is the forward's diag[] (the pair's logit):
+ *   g = exp(diag[r] - s)*(rinv[r] + cinv_paired[r]) - dcoef
+ *   dA[r,:] += g*b32[r,:],   dB[r,:] += g*a32[r,:],   dlogscale_acc += g * diag[r]/s. */
+int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
+                         const float* rinv, const float* cinv_paired, const float* scal, float* dA, float* dB,
                          float* dlogscale_acc, mmg_stream_t stream);
 
 /* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
- *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - dcoef*[c == r + diag_offset]      ( = s * dloss/dlogit )
+ *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - scal[0]*[c == r + diag_offset]    ( = s * dloss/dlogit; the
+ *         matching-pair element is zeroed instead when scal[2] != 0, see mmg_infonce_bwd_diag )
  * dA, dB, dlogscale_acc are fp32 and must be zero-filled (or hold a running sum) by the caller.
  * Works block by block (block_rows x block_cols, 0 = library default) through `workspace`. */
 int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,

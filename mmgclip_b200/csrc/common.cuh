@@ -176,6 +176,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
       : "memory");
 }
 
+// 16 TMEM lanes x 32 fp32 columns in the mma-fragment layout: thread l holds rows {l/4, l/4 + 8} (relative to the lane
+// field of taddr) and, for each 8-column group g = 0..3, columns 8g + 2*(l%4) + {0,1}:
+//     v[4g + 2h + e] = D[row l/4 + 8h][col 8g + 2*(l%4) + e]
+// Four rows x eight columns per thread after two loads, so column sums need 7 shuffles per 32x32 block instead of 31.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------

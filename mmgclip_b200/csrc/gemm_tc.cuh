@@ -40,7 +40,7 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kBarBytes = 1024;
+  static constexpr int kBarBytes = 4096;  // mbarriers + TMEM slot (first 512 B) and 2 x 1 KB of epilogue scratch
   static constexpr int kTotal = kStages * (kABytes + kBBytes) + kBarBytes + 1024 /* alignment slack */;
 };
 
@@ -82,9 +82,11 @@ struct EpiStoreF32 {
     int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
     int relu;
   };
+  static constexpr int kSmemFloats = 0;
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane) {
+                                             int q, int lane, int ewarp, float* smem) {
+    (void)ewarp; (void)smem;
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;
     const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
@@ -151,6 +153,10 @@ struct EpiStoreF32 {
 // (|cos| <= 1 => logits in [-s, s]) E = exp(s*cos - s) feeds the row sums AND the column sums with a single exp per
 // logit, and partial sums from different tiles / GPUs simply add.  Nothing of the tile is written to memory except
 //   rowsum[r] += sum_c E      colsum[c] += sum_r E      diag[r] = s * cos[r][r]
+// The tile is read in the 16x256b fragment layout (4 rows x 8 columns of every 32x32 block per thread): row sums
+// accumulate in registers for the whole tile, column sums are pre-reduced over the thread's 4 rows and finished with a
+// 3-stage / 7-shuffle transposing butterfly.  Interior tiles take a mask-free path; the diagonal is looked at only in
+// tiles that contain it.
 struct EpiLse {
   struct Params {
     float* rowsum;            // [M]   (atomic accumulate; zero-initialised by the caller)
@@ -159,82 +165,112 @@ struct EpiLse {
     const float* scale_ptr;   // device scalar s = exp(logit_scale)
     int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
   };
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane) {
-    const float s = __ldg(P.scale_ptr);
-    const float sl2 = s * 1.4426950408889634f;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
-    const int dcol = row + P.diag_offset;
-    float racc = 0.f;
+  static constexpr int kSmemFloats = 0;
+
+  template <int BN, bool kMasked, bool kDiag>
+  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                              int q, int lane, float s, float sl2) {
+    const int lr = lane >> 2;          // row within an 8-row group
+    const int lc = (lane & 3) * 2;     // first of this thread's two columns within an 8-column group
+    const int rbase = m0 + q * 32 + lr;  // rows rbase + 8*i, i = 0..3
+    float racc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int ch = 0; ch < BN / 64; ++ch) {
       const int cl = half * (BN / 2) + ch * 32;
       const int c0 = n0 + cl;
-      if (c0 >= N) break;  // warp-uniform
-      float v[32];
-      tmem_ld_32x32b_x32(tacc + cl, v);
+      if (kMasked && c0 >= N) break;  // warp-uniform
+      float va[16], vb[16];
+      tmem_ld_16x256b_x4(tacc + cl, va);                  // lanes 32q + 0..15  -> rows i = 0, 1
+      tmem_ld_16x256b_x4(tacc + (16u << 16) + cl, vb);    // lanes 32q + 16..31 -> rows i = 2, 3
       tmem_ld_wait();
-      if (row_ok && dcol >= c0 && dcol < c0 + 32) {
+      float cp[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j == dcol) P.diag[row] = v[j] * s;
-      }
+      for (int g = 0; g < 4; ++g) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = ex2_approx(fmaf(v[j], sl2, -sl2));
-        v[j] = (row_ok && c0 + j < N) ? e : 0.f;
-        racc += v[j];
-      }
-      // Column sums over this warp's 32 rows: transposing butterfly, 31 shuffles for 32 columns.
-      // After the last step lane j holds sum over lanes of v[j].
+        for (int e = 0; e < 2; ++e) {
+          const int col = c0 + 8 * g + lc + e;
+          float x[4] = {va[4 * g + e], va[4 * g + 2 + e], vb[4 * g + e], vb[4 * g + 2 + e]};
+          float csum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const bool up = lane & 16;
-        const float keep = up ? v[j + 16] : v[j];
-        const float send = up ? v[j] : v[j + 16];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          for (int i = 0; i < 4; ++i) {
+            if (kDiag) {
+              const int row = rbase + 8 * i;
+              if (row + P.diag_offset == col && (!kMasked || row < M)) P.diag[row] = x[i] * s;
+            }
+            float ev = ex2_approx(fmaf(x[i], sl2, -sl2));
+            if (kMasked) ev = (rbase + 8 * i < M && col < N) ? ev : 0.f;
+            racc[i] += ev;
+            csum += ev;
+          }
+          cp[2 * g + e] = csum;
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool up = lane & 8;
-        const float keep = up ? v[j + 8] : v[j];
-        const float send = up ? v[j] : v[j + 8];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
+      // transposing butterfly over the 8 lanes that share lane%4: afterwards this lane holds the full 32-row sum of
+      // column 8*g' + lc + e' with g' = 2*bit4 + bit3, e' = bit2 of the lane index
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool up = lane & 4;
-        const float keep = up ? v[j + 4] : v[j];
-        const float send = up ? v[j] : v[j + 4];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        const bool up = lane & 16;
+        const float keep = up ? cp[j + 4] : cp[j];
+        const float send = up ? cp[j] : cp[j + 4];
+        cp[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const bool up = lane & 2;
-        const float keep = up ? v[j + 2] : v[j];
-        const float send = up ? v[j] : v[j + 2];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        const bool up = lane & 8;
+        const float keep = up ? cp[j + 2] : cp[j];
+        const float send = up ? cp[j] : cp[j + 2];
+        cp[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
       }
       {
-        const bool up = lane & 1;
-        const float keep = up ? v[1] : v[0];
-        const float send = up ? v[0] : v[1];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        const bool up = lane & 4;
+        const float keep = up ? cp[1] : cp[0];
+        const float send = up ? cp[0] : cp[1];
+        cp[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
-      if (c0 + lane < N) atomicAdd(P.colsum + c0 + lane, v[0]);
+      const int mycol = c0 + 8 * (2 * ((lane >> 4) & 1) + ((lane >> 3) & 1)) + lc + ((lane >> 2) & 1);
+      if (!kMasked || mycol < N) atomicAdd(P.colsum + mycol, cp[0]);
     }
-    if (row_ok) atomicAdd(P.rowsum + row, racc);
+    // row sums: 4 values per thread, 4 lanes (same lane/4) share the rows -> 3-shuffle transposing butterfly
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool up = lane & 2;
+      const float keep = up ? racc[i + 2] : racc[i];
+      const float send = up ? racc[i] : racc[i + 2];
+      racc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+      const bool up = lane & 1;
+      const float keep = up ? racc[1] : racc[0];
+      const float send = up ? racc[0] : racc[1];
+      racc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const int myrow = rbase + 8 * (lane & 3);
+    if (!kMasked || myrow < M) atomicAdd(P.rowsum + myrow, racc[0]);
+  }
+
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                             int q, int lane, int ewarp, float* smem) {
+    (void)ewarp; (void)smem;
+    const float s = __ldg(P.scale_ptr);
+    const float sl2 = s * 1.4426950408889634f;
+    const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
+    // does this tile contain matching pairs?  columns of rows [m0, m0+128) are [m0+off, m0+off+128)
+    const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
+    if (interior && !has_diag) tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
+    else if (interior) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
+    else tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
   }
 };
 
 // Backward InfoNCE epilogue: recomputed cosines -> gradient coefficients of one logit tile,
-//   g[r][c] = E[r][c] * (rinv[r] + cinv[c]) - dcoef * [r == c],
+//   g[r][c] = E[r][c] * (rinv[r] + cinv[c])           off the diagonal,
+//   g[r][r'] = 0 (zero_diag: the matching pair is applied in fp32 by mmg_infonce_bwd_diag) or  E*(..) - dcoef,
 //   rinv[r] = s*gl/(2B*rowsum[r]),  cinv[c] = s*gl/(2B*colsum[c]),  dcoef = s*gl/B        (gl = d loss)
-// i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g is written as bf16 into an
-// L2-resident block scratch (never the full B x B) that the two gradient GEMMs consume; sum(g * cos) accumulates
-// d loss / d log(s).
+// i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g is written as bf16 into a
+// block scratch (never the full B x B) that the two gradient GEMMs consume; sum(g * cos) accumulates d loss / d log(s).
+// One accumulator row per thread (32x32b layout: 64 contiguous bytes of g per row and chunk); the column terms cinv of
+// the tile are staged once in shared memory and read back as broadcast 16-byte loads.
 struct EpiGrad {
   struct Params {
     __nv_bfloat16* G;
@@ -242,20 +278,25 @@ struct EpiGrad {
     const float* rinv;        // [M]
     const float* cinv;        // [N]
     const float* scale_ptr;   // device scalar s
-    const float* dcoef_ptr;   // device scalar dcoef
+    const float* scal;        // device scalars: [0] diagonal coefficient subtracted here, [2] != 0 -> zero the diagonal
     float* dlogscale_acc;     // device scalar accumulator: sum g * cos
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
   };
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane) {
-    const float s = __ldg(P.scale_ptr);
-    const float sl2 = s * 1.4426950408889634f;
-    const float dcoef = __ldg(P.dcoef_ptr);
+  static constexpr int kSmemFloats = 256;  // per accumulator stage: cinv of the tile's columns
+
+  template <int BN, bool kMasked, bool kDiag>
+  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                              int q, int lane, const float* cs, float sl2) {
     const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
+    const bool row_ok = !kMasked || row < M;
     const int dcol = row + P.diag_offset;
     const float ri = row_ok ? __ldg(P.rinv + row) : 0.f;
+    float dcoef = 0.f;
+    bool zero_diag = false;
+    if (kDiag) {
+      dcoef = __ldg(P.scal);
+      zero_diag = __ldg(P.scal + 2) != 0.f;
+    }
     __nv_bfloat16* grow = P.G + static_cast<long long>(row) * P.ldg;
     const bool vec_ok = ((P.ldg & 7) == 0) && ((reinterpret_cast<uintptr_t>(P.G) & 15) == 0);
     float dacc = 0.f;
@@ -263,23 +304,28 @@ struct EpiGrad {
     for (int ch = 0; ch < BN / 64; ++ch) {
       const int cl = half * (BN / 2) + ch * 32;
       const int c0 = n0 + cl;
-      if (c0 >= N) break;  // warp-uniform
+      if (kMasked && c0 >= N) break;  // warp-uniform
       float v[32];
       tmem_ld_32x32b_x32(tacc + cl, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float cosv = v[j];
-        const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
-        const float ci = (c0 + j < N) ? __ldg(P.cinv + c0 + j) : 0.f;
-        float g = e * (ri + ci);
-        if (c0 + j == dcol) g -= dcoef;
-        g = (row_ok && c0 + j < N) ? g : 0.f;
-        dacc = fmaf(g, cosv, dacc);
-        v[j] = g;
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + cl + 4 * j4);  // broadcast LDS.128
+        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * j4 + jj;
+          const float cosv = v[j];
+          const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
+          float g = e * (ri + cv[jj]);
+          if (kDiag && c0 + j == dcol) g = zero_diag ? 0.f : g - dcoef;
+          if (kMasked) g = (row_ok && c0 + j < N) ? g : 0.f;
+          dacc = fmaf(g, cosv, dacc);
+          v[j] = g;
+        }
       }
       if (row_ok) {
-        if (vec_ok && c0 + 32 <= N) {
+        if (vec_ok && (!kMasked || c0 + 32 <= N)) {
           uint4* dst = reinterpret_cast<uint4*>(grow + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -299,6 +345,22 @@ struct EpiGrad {
     }
     dacc = warp_sum(dacc);
     if (lane == 0 && dacc != 0.f) atomicAdd(P.dlogscale_acc, dacc);
+  }
+
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                             int q, int lane, int ewarp, float* smem) {
+    // stage the column terms of this tile (zero beyond N) -- all epilogue warps, then a named barrier
+    const int t = ewarp * 32 + lane;
+    if (t < BN) smem[t] = (n0 + t < N) ? __ldg(P.cinv + n0 + t) : 0.f;
+    named_bar_sync(1, kEpiWarps * 32);
+    const float s = __ldg(P.scale_ptr);
+    const float sl2 = s * 1.4426950408889634f;
+    const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
+    const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
+    if (interior && !has_diag) tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
+    else if (interior) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
+    else tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
   }
 };
 
@@ -325,6 +387,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // epilogue scratch: 2 accumulator stages x 256 floats, after the barriers (inside the 4 KB tail reserved in GemmSmem)
+  float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -450,7 +514,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       if (tc.kb_begin < tc.kb_end)
-        Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kBM, tc.n_blk * BN, p.M, p.N, half, q, lane);
+        Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kBM, tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4,
+                              epi_smem + acc_stage * 256);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);

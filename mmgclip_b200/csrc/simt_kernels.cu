@@ -605,6 +605,8 @@ __global__ void infonce_bwd_prep_kernel(const float* __restrict__ rowsum, int ro
   if (i == 0) {
     scal[0] = diag_in_fp32 ? 0.f : 2.0f * coef;  // what the block kernels subtract on the diagonal
     scal[1] = 2.0f * coef;                       // dcoef = s*gl/B
+    scal[2] = diag_in_fp32 ? 1.f : 0.f;          // block kernels zero the diagonal element of g
+    scal[3] = 0.f;
   }
 }
 
@@ -687,50 +689,58 @@ int simt_ce_bwd(const float* logits, long long ld, int n, int m, const long long
 }
 
 // =====================================================================================================
-// InfoNCE backward, matching-pair term in fp32.
-// The -dcoef*[r == c'] part of g carries almost all of the gradient's magnitude; multiplying it by a bf16-rounded
-// embedding would put the full 2^-9 operand rounding error straight into dA/dB.  The bf16 path therefore leaves it
-// out of the tensor-core contraction (scal[0] = 0) and applies it here from the fp32 embeddings:
-//   dA[r,:] -= dcoef * b32m[r,:]    dBm[r,:] -= dcoef * a32[r,:]    dlogscale -= dcoef * sum_r <a32[r], b32m[r]>
-// where b32m / dBm are the rows of the column side that are paired with the local rows.
-// One warp per pair; block-level fixed-order sum of the cosines, one atomic per block.
+// InfoNCE backward, matching-pair (diagonal) element in fp32.
+// g[r, r'] = E*(rinv + cinv) - dcoef carries almost all of the gradient's magnitude and cancels heavily against the
+// off-diagonal sum; multiplying it by a bf16-rounded embedding would put the full 2^-9 operand rounding error straight
+// into dA/dB.  The bf16 path therefore zeroes that element in the tensor-core contraction (scal[2] != 0) and applies
+// it here from the fp32 embeddings:
+//   g = exp(diag[r] - s) * (rinv[r] + cinvm[r]) - dcoef
+//   dA[r,:] += g * b32m[r,:]    dBm[r,:] += g * a32[r,:]    dlogscale += g * diag[r] / s
+// where b32m / dBm / cinvm are the column-side rows paired with the local rows.  One warp per pair; block-level
+// fixed-order sum, one atomic per block.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__ b32, int rows, int D,
+                        const float* __restrict__ diag, const float* __restrict__ scale,
+                        const float* __restrict__ rinv, const float* __restrict__ cinvm,
                         const float* __restrict__ scal, float* __restrict__ dA, float* __restrict__ dB,
                         float* __restrict__ dlogscale_acc) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const float s = *scale;
   const float dcoef = scal[1];
-  float dot = 0.f;
+  float contrib = 0.f;
   if (r < rows) {
+    const float lg = diag[r];
+    const float g = expf(lg - s) * (rinv[r] + cinvm[r]) - dcoef;
     const float* ar = a32 + (long long)r * D;
     const float* br = b32 + (long long)r * D;
     float* dar = dA + (long long)r * D;
     float* dbr = dB + (long long)r * D;
     for (int i = lane; i < D; i += 32) {
       const float av = ar[i], bv = br[i];
-      dot = fmaf(av, bv, dot);
-      dar[i] -= dcoef * bv;
-      dbr[i] -= dcoef * av;
+      dar[i] = fmaf(g, bv, dar[i]);
+      dbr[i] = fmaf(g, av, dbr[i]);
     }
+    contrib = g * (lg / s);
   }
-  dot = warp_sum(dot);
   __shared__ float wsum[8];
-  if (lane == 0) wsum[threadIdx.x >> 5] = dot;
+  if (lane == 0) wsum[threadIdx.x >> 5] = contrib;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += wsum[i];
-    atomicAdd(dlogscale_acc, -dcoef * t);
+    atomicAdd(dlogscale_acc, t);
   }
 }
 
-int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* scal, float* dA, float* dB,
+int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
+                          const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
                           float* dlogscale_acc, cudaStream_t st) {
   if (rows <= 0) return 0;
-  infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, scal, dA, dB, dlogscale_acc);
+  infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, diag, scale, rinv, cinvm, scal, dA, dB,
+                                                          dlogscale_acc);
   MMG_LAUNCH_CHECK("infonce_bwd_diag_kernel");
   return 0;
 }

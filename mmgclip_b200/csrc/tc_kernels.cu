@@ -182,7 +182,7 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   GemmProblem p1 = empty_problem();
   EpiGrad::Params e;
   e.G = reinterpret_cast<__nv_bfloat16*>(G); e.ldg = ldg; e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
-  e.dcoef_ptr = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
+  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
   if (BN == 256) return launch<256, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
   return launch<128, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
 }

