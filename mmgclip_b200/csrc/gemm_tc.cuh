@@ -29,17 +29,20 @@ constexpr int kGemmThreads = 32 * (4 + kEpiWarps);
 
 struct GemmProblem {
   int M, N, K;           // logical extents (ragged edges are zero-filled by TMA and masked in the epilogue)
-  int tiles_m, tiles_n;  // ceil(M/128), ceil(N/BN)
+  int tiles_m, tiles_n;  // ceil(M/(128*kCG)), ceil(N/BN)
   int k_splits;          // >= 1; each split handles a contiguous range of 64-wide K blocks
   int a_mn, b_mn;        // 0 = K-major operand, 1 = MN-major operand
   __host__ __device__ int num_tiles() const { return tiles_m * tiles_n * k_splits; }
 };
 
-template <int BN>
+// kCG = 1: one CTA owns a 128 x BN tile.  kCG = 2: a CTA pair (cta_group::2) owns a 256 x BN tile -- each CTA stages
+// its own 128 A rows and HALF of the B rows, which halves the B-operand shared-memory / L2 traffic per FLOP.
+template <int BN, int kCG>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBRows = BN / kCG;
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStages = 192 * 1024 / (kABytes + kBBytes);  // 4 (48 KB) or 6 (32 KB)
   static constexpr int kBarBytes = 4096;  // mbarriers + TMEM slot (first 512 B) and 2 x 1 KB of epilogue scratch
   static constexpr int kTotal = kStages * (kABytes + kBBytes) + kBarBytes + 1024 /* alignment slack */;
 };
@@ -367,32 +370,38 @@ struct EpiGrad {
 // ---------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int BN, class Epi>
+template <int BN, class Epi, int kCG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const GemmProblem p0, const GemmProblem p1, const typename Epi::Params e0,
                const typename Epi::Params e1) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, kCG>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: a power of two >= 32
+  constexpr int kTileM = kBM * kCG;       // rows of one (pair) tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * S::kBBytes);
-  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's copy is the live one)
+  uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA          (multicast to both CTAs)
+  uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue     (multicast to both CTAs)
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA     (leader's copy is the live one)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   // epilogue scratch: 2 accumulator stages x 256 floats, after the barriers (inside the 4 KB tail reserved in GemmSmem)
   float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile_first = blockIdx.x / kCG;
+  const int tile_step = gridDim.x / kCG;
 
+  if (kCG == 2) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
@@ -403,109 +412,133 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kCG);   // one arrival per producer of the pair
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], kEpiWarps * kCG);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if (kCG == 2) tmem_alloc_cg2(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all();
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p0.num_tiles() + p1.num_tiles();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         const TileCoord tc = decode_tile(t, p0, p1);
         const GemmProblem& p = tc.prob ? p1 : p0;
         const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
         const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
-        const int m0 = tc.m_blk * kBM;
-        const int n0 = tc.n_blk * BN;
+        const int m0 = tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM;       // this CTA's A rows
+        const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * S::kBRows;     // this CTA's share of the B rows
         for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], S::kABytes + S::kBBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], kCG * (S::kABytes + S::kBBytes));
+          else mbar_arrive_cluster(&full_bar[stage], 0);
           uint8_t* a_dst = sA + stage * S::kABytes;
           uint8_t* b_dst = sB + stage * S::kBBytes;
           const int k0 = kb * kBK;
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (kCG == 2) tma_load_2d_cg2(m, &full_bar[stage], dst, c0, c1, kEvictNormal);
+            else tma_load_2d(m, &full_bar[stage], dst, c0, c1, kEvictNormal);
+          };
           if (!p.a_mn) {
-            tma_load_2d(mA, &full_bar[stage], a_dst, k0, m0, kEvictNormal);
+            load(mA, a_dst, k0, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < kBM / 64; ++i)
-              tma_load_2d(mA, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, k0, kEvictNormal);
+            for (int i = 0; i < kBM / 64; ++i) load(mA, a_dst + i * (kBK * 128), m0 + i * 64, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(mB, &full_bar[stage], b_dst, k0, n0, kEvictNormal);
+            load(mB, b_dst, k0, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(mB, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, k0, kEvictNormal);
+            for (int i = 0; i < S::kBRows / 64; ++i) load(mB, b_dst + i * (kBK * 128), n0 + i * 64, k0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(t, p0, p1);
-      const GemmProblem& p = tc.prob ? p1 : p0;
-      const int acc_stage = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
-      tcgen05_fence_after();
-      const uint32_t idesc = make_idesc_bf16(kBM, BN, p.a_mn, p.b_mn);
-      const uint32_t tmem_d = tmem_base + acc_stage * BN;
-      // K-major: 8-row groups are 1024 B apart (SBO); one swizzle span along K, LBO unused.
-      // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN atoms are kBK*128 B apart (LBO).
-      const uint32_t a_lbo = p.a_mn ? kBK * 128 : 0, b_lbo = p.b_mn ? kBK * 128 : 0;
-      const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;
-      const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
-      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = tile_first; t < total_tiles; t += tile_step, ++it) {
+        const TileCoord tc = decode_tile(t, p0, p1);
+        const GemmProblem& p = tc.prob ? p1 : p0;
+        const int acc_stage = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
+        const uint32_t idesc = make_idesc_bf16(kTileM, BN, p.a_mn, p.b_mn);
+        const uint32_t tmem_d = tmem_base + acc_stage * BN;
+        // K-major: 8-row groups are 1024 B apart (SBO); one swizzle span along K, LBO unused.
+        // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN atoms are kBK*128 B apart (LBO).
+        const uint32_t a_lbo = p.a_mn ? kBK * 128 : 0, b_lbo = p.b_mn ? kBK * 128 : 0;
+        const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;
+        const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
+        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
+            const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+              const uint64_t db = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+              const uint32_t acc = (kb > tc.kb_begin || k > 0) ? 1u : 0u;
+              if (kCG == 2) umma_bf16_ss_cg2(tmem_d, da, db, idesc, acc);
+              else umma_bf16_ss(tmem_d, da, db, idesc, acc);
+            }
+            if (kCG == 2) {
+              umma_commit_cg2(&empty_bar[stage]);
+              if (kb == tc.kb_end - 1) umma_commit_cg2(&tfull_bar[acc_stage]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == tc.kb_end - 1) umma_commit(&tfull_bar[acc_stage]);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == tc.kb_end - 1) umma_commit(&tfull_bar[acc_stage]);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (tc.kb_begin >= tc.kb_end) {
+          // Degenerate split (no K blocks): nothing was issued; still publish the (stale) stage so the
+          // epilogue does not dead-lock.  Host code never creates such splits; kept as a guard.
+          if (lane == 0) {
+            if (kCG == 2) umma_commit_cg2(&tfull_bar[acc_stage]);
+            else umma_commit(&tfull_bar[acc_stage]);
+          }
+          __syncwarp();
+        }
       }
-      if (tc.kb_begin >= tc.kb_end) {
-        // Degenerate split (no K blocks): nothing was issued; still publish the (stale) stage so the
-        // epilogue does not dead-lock.  Host code never creates such splits; kept as a guard.
-        if (lane == 0) umma_commit(&tfull_bar[acc_stage]);
-        __syncwarp();
+      if (kCG == 2 && it > 0) {
+        // all epilogue arrivals (also the peer's remote ones) must have landed before the leader's barriers die
+        const int last = it - 1;
+        mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (both CTAs: 128 accumulator rows each) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = tile_first; t < total_tiles; t += tile_step, ++it) {
       const TileCoord tc = decode_tile(t, p0, p1);
       const GemmProblem& p = tc.prob ? p1 : p0;
       const int acc_stage = it & 1;
@@ -514,19 +547,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       if (tc.kb_begin < tc.kb_end)
-        Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kBM, tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4,
-                              epi_smem + acc_stage * 256);
+        Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
+                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + acc_stage * 256);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[acc_stage]);
+        else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCG == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

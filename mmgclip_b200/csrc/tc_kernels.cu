@@ -2,6 +2,7 @@
 // tile-shape selection, persistent-grid sizing (one CTA per SM).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -65,10 +66,10 @@ static int sm_count() {
   return n;
 }
 
-static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn) {
+static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn, int cg) {
   GemmProblem p;
   p.M = M; p.N = N; p.K = K;
-  p.tiles_m = (M + kBM - 1) / kBM;
+  p.tiles_m = (M + kBM * cg - 1) / (kBM * cg);
   p.tiles_n = (N + BN - 1) / BN;
   const int nkb = (K + kBK - 1) / kBK;
   if (k_splits < 1) k_splits = 1;
@@ -91,100 +92,133 @@ static GemmProblem empty_problem() {
   return p;
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, int kCG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
                   const GemmProblem& p0, const GemmProblem& p1, const typename Epi::Params& e0,
                   const typename Epi::Params& e1, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, Epi>;
+  auto kern = gemm_tc_kernel<BN, Epi, kCG>;
+  using S = GemmSmem<BN, kCG>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
     configured = true;
   }
   const int total = p0.num_tiles() + p1.num_tiles();
   if (total <= 0) return 0;
-  const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(a0, b0, a1, b1, p0, p1, e0, e1);
-  cudaError_t e = cudaGetLastError();
+  const int groups = sm_count() / kCG;  // CTAs (or CTA pairs) that can be resident: one per SM
+  const int grid = (total < groups ? total : groups) * kCG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, p0, p1, e0, e1);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
   count_launch();
   return 0;
 }
 
-static int pick_bn(int N) { return N > 128 ? 256 : 128; }
+// Tile shape: 256-row CTA pairs (cta_group::2) when both extents fill them, else single-CTA 128 x {256,128} tiles.
+// MMG_TC_PAIR=0 in the environment forces single-CTA tiles (debugging / A-B measurements).
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMG_TC_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+struct TileCfg { int BN, cg; };
+static TileCfg pick_tile(int M, int N) {
+  TileCfg c;
+  c.BN = N > 128 ? 256 : 128;
+  c.cg = (pair_enabled() && c.BN == 256 && M > 128) ? 2 : 1;
+  return c;
+}
+
+#define MMG_DISPATCH(EPI, cfg, ...)                                              \
+  do {                                                                           \
+    if ((cfg).BN == 256 && (cfg).cg == 2) return launch<256, EPI, 2>(__VA_ARGS__); \
+    if ((cfg).BN == 256) return launch<256, EPI, 1>(__VA_ARGS__);                \
+    return launch<128, EPI, 1>(__VA_ARGS__);                                     \
+  } while (0)
 
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
                   const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(-1, "tc_gemm: empty problem %dx%dx%d", M, N, K);
   if (k_splits > 1 && mode != 2) return set_error(-1, "tc_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
   if (k_splits > 1 && (relu || bias)) return set_error(-1, "tc_gemm: bias/ReLU cannot be fused with split-K");
-  const int BN = pick_bn(N);
+  const TileCfg tcfg = pick_tile(M, N);
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_operand_map(&ma, A, M, K, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb, B, N, K, BN)) != 0) return rc;
-  GemmProblem p0 = make_problem(M, N, K, BN, k_splits, A.mn_major, B.mn_major);
+  if ((rc = make_operand_map(&mb, B, N, K, tcfg.BN / tcfg.cg)) != 0) return rc;
+  GemmProblem p0 = make_problem(M, N, K, tcfg.BN, k_splits, A.mn_major, B.mn_major, tcfg.cg);
   GemmProblem p1 = empty_problem();
   EpiStoreF32::Params e;
   e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
-  if (BN == 256) return launch<256, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
-  return launch<128, EpiStoreF32>(ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
 }
 
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
                             const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,
                             cudaStream_t st) {
   if (N0 != N1) return set_error(-1, "tc_gemm_dual: both problems must share N");
-  const int BN = pick_bn(N0);
+  const TileCfg tcfg = pick_tile(M0 < M1 ? M0 : M1, N0);
   CUtensorMap ma0, mb0, ma1, mb1;
   int rc;
   if ((rc = make_operand_map(&ma0, A0, M0, K0, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb0, B0, N0, K0, BN)) != 0) return rc;
+  if ((rc = make_operand_map(&mb0, B0, N0, K0, tcfg.BN / tcfg.cg)) != 0) return rc;
   if ((rc = make_operand_map(&ma1, A1, M1, K1, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb1, B1, N1, K1, BN)) != 0) return rc;
-  GemmProblem p0 = make_problem(M0, N0, K0, BN, 1, A0.mn_major, B0.mn_major);
-  GemmProblem p1 = make_problem(M1, N1, K1, BN, 1, A1.mn_major, B1.mn_major);
+  if ((rc = make_operand_map(&mb1, B1, N1, K1, tcfg.BN / tcfg.cg)) != 0) return rc;
+  GemmProblem p0 = make_problem(M0, N0, K0, tcfg.BN, 1, A0.mn_major, B0.mn_major, tcfg.cg);
+  GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, 1, A1.mn_major, B1.mn_major, tcfg.cg);
   EpiStoreF32::Params e0, e1;
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
-  if (BN == 256) return launch<256, EpiStoreF32>(ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
-  return launch<128, EpiStoreF32>(ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
                    float* rowsum, float* colsum, float* diag, cudaStream_t st) {
-  const int BN = pick_bn(cols);
+  const TileCfg tcfg = pick_tile(rows, cols);
   TcOperand A{a_hat, D, 0}, B{b_hat, D, 0};
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_operand_map(&ma, A, rows, D, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb, B, cols, D, BN)) != 0) return rc;
-  GemmProblem p0 = make_problem(rows, cols, D, BN, 1, 0, 0);
+  if ((rc = make_operand_map(&mb, B, cols, D, tcfg.BN / tcfg.cg)) != 0) return rc;
+  GemmProblem p0 = make_problem(rows, cols, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
   EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
-  if (BN == 256) return launch<256, EpiLse>(ma, mb, ma, mb, p0, p1, e, e, st);
-  return launch<128, EpiLse>(ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
 }
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
                           const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
                           long long ldg, float* dlogscale_acc, cudaStream_t st) {
-  const int BN = pick_bn(cb);
+  const TileCfg tcfg = pick_tile(rb, cb);
   TcOperand A{a_blk, D, 0}, B{b_blk, D, 0};
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_operand_map(&ma, A, rb, D, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb, B, cb, D, BN)) != 0) return rc;
-  GemmProblem p0 = make_problem(rb, cb, D, BN, 1, 0, 0);
+  if ((rc = make_operand_map(&mb, B, cb, D, tcfg.BN / tcfg.cg)) != 0) return rc;
+  GemmProblem p0 = make_problem(rb, cb, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
   EpiGrad::Params e;
   e.G = reinterpret_cast<__nv_bfloat16*>(G); e.ldg = ldg; e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
   e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
-  if (BN == 256) return launch<256, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
-  return launch<128, EpiGrad>(ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
 }
 
 }  // namespace mmg
