@@ -435,18 +435,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = tile_first; t < total_tiles; t += tile_step) {
-        const TileCoord tc = decode_tile(t, p0, p1);
-        const GemmProblem& p = tc.prob ? p1 : p0;
-        const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
-        const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
-        const int m0 = tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM;       // this CTA's A rows
-        const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * S::kBRows;     // this CTA's share of the B rows
-        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The warp stays converged; one elected lane arms the barrier and issues the bulk-tensor copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
+      const TileCoord tc = decode_tile(t, p0, p1);
+      const GemmProblem& p = tc.prob ? p1 : p0;
+      const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
+      const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
+      const int m0 = tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM;       // this CTA's A rows
+      const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * S::kBRows;     // this CTA's share of the B rows
+      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], kCG * (S::kABytes + S::kBBytes));
           else mbar_arrive_cluster(&full_bar[stage], 0);
           uint8_t* a_dst = sA + stage * S::kABytes;
@@ -468,8 +469,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < S::kBRows / 64; ++i) load(mB, b_dst + i * (kBK * 128), n0 + i * 64, k0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -495,7 +497,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
             const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
 #pragma unroll
@@ -520,7 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (tc.kb_begin >= tc.kb_end) {
           // Degenerate split (no K blocks): nothing was issued; still publish the (stale) stage so the
           // epilogue does not dead-lock.  Host code never creates such splits; kept as a guard.
-          if (lane == 0) {
+          if (elect_one_sync()) {
             if (kCG == 2) umma_commit_cg2(&tfull_bar[acc_stage]);
             else umma_commit(&tfull_bar[acc_stage]);
           }
