@@ -37,14 +37,15 @@ struct GemmProblem {
 
 // kCG = 1: one CTA owns a 128 x BN tile.  kCG = 2: a CTA pair (cta_group::2) owns a 256 x BN tile -- each CTA stages
 // its own 128 A rows and HALF of the B rows, which halves the B-operand shared-memory / L2 traffic per FLOP.
-template <int BN, int kCG>
+template <int BN, int kCG, int kStagingBytes = 0>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBRows = BN / kCG;
   static constexpr int kBBytes = kBRows * kBK * 2;
-  static constexpr int kStages = 192 * 1024 / (kABytes + kBBytes);  // 4 (48 KB) or 6 (32 KB)
+  // operand ring: whatever is left of ~192 KB after the epilogue's output staging tile (TMA-store epilogues)
+  static constexpr int kStages = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
   static constexpr int kBarBytes = 4096;  // mbarriers + TMEM slot (first 512 B) and 2 x 1 KB of epilogue scratch
-  static constexpr int kTotal = kStages * (kABytes + kBBytes) + kBarBytes + 1024 /* alignment slack */;
+  static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kBarBytes + 1024 /* alignment slack */;
 };
 
 struct TileCoord {
@@ -85,11 +86,13 @@ struct EpiStoreF32 {
     int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
     int relu;
   };
-  static constexpr int kSmemFloats = 0;
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
+  static __device__ __forceinline__ void finish(int, int) {}
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane, int ewarp, float* smem) {
-    (void)ewarp; (void)smem;
+                                             int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
+                                             uint8_t* staging) {
+    (void)ewarp; (void)smem; (void)cmap; (void)staging;
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;
     const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
@@ -168,7 +171,8 @@ struct EpiLse {
     const float* scale_ptr;   // device scalar s = exp(logit_scale)
     int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
   };
-  static constexpr int kSmemFloats = 0;
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
+  static __device__ __forceinline__ void finish(int, int) {}
 
   template <int BN, bool kMasked, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
@@ -253,8 +257,9 @@ struct EpiLse {
 
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane, int ewarp, float* smem) {
-    (void)ewarp; (void)smem;
+                                             int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
+                                             uint8_t* staging) {
+    (void)ewarp; (void)smem; (void)cmap; (void)staging;
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
@@ -270,14 +275,14 @@ struct EpiLse {
 //   g[r][c] = E[r][c] * (rinv[r] + cinv[c])           off the diagonal,
 //   g[r][r'] = 0 (zero_diag: the matching pair is applied in fp32 by mmg_infonce_bwd_diag) or  E*(..) - dcoef,
 //   rinv[r] = s*gl/(2B*rowsum[r]),  cinv[c] = s*gl/(2B*colsum[c]),  dcoef = s*gl/B        (gl = d loss)
-// i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g is written as bf16 into a
+// i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g goes out as bf16 into a
 // block scratch (never the full B x B) that the two gradient GEMMs consume; sum(g * cos) accumulates d loss / d log(s).
-// One accumulator row per thread (32x32b layout: 64 contiguous bytes of g per row and chunk); the column terms cinv of
-// the tile are staged once in shared memory and read back as broadcast 16-byte loads.
+// One accumulator row per thread (32x32b layout).  The column terms cinv of the tile are staged once in shared memory
+// (broadcast 16-byte loads).  The bf16 tile is assembled in a 128B-swizzled shared-memory staging buffer and written
+// with TMA bulk-tensor stores: full 128-byte lines, no LSU traffic, ragged edges clipped by the hardware.  No masking
+// is needed anywhere: out-of-range operand rows are zero-filled, so cos = 0 there and g*cos contributes nothing.
 struct EpiGrad {
   struct Params {
-    __nv_bfloat16* G;
-    long long ldg;
     const float* rinv;        // [M]
     const float* cinv;        // [N]
     const float* scale_ptr;   // device scalar s
@@ -285,29 +290,29 @@ struct EpiGrad {
     float* dlogscale_acc;     // device scalar accumulator: sum g * cos
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
   };
-  static constexpr int kSmemFloats = 256;  // per accumulator stage: cinv of the tile's columns
+  // staging: BN/64 boxes of [128 rows x 128 bytes] (64 bf16 columns each)
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kBM * BN * 2; }
 
-  template <int BN, bool kMasked, bool kDiag>
-  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                              int q, int lane, const float* cs, float sl2) {
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = !kMasked || row < M;
+  template <int BN, bool kDiag>
+  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int half, int q,
+                                              int lane, const float* cs, float sl2, uint8_t* staging) {
+    const int rl = q * 32 + lane;  // row inside the tile
+    const int row = m0 + rl;
     const int dcol = row + P.diag_offset;
-    const float ri = row_ok ? __ldg(P.rinv + row) : 0.f;
+    const float ri = (row < M) ? __ldg(P.rinv + row) : 0.f;
     float dcoef = 0.f;
     bool zero_diag = false;
     if (kDiag) {
       dcoef = __ldg(P.scal);
       zero_diag = __ldg(P.scal + 2) != 0.f;
     }
-    __nv_bfloat16* grow = P.G + static_cast<long long>(row) * P.ldg;
-    const bool vec_ok = ((P.ldg & 7) == 0) && ((reinterpret_cast<uintptr_t>(P.G) & 15) == 0);
+    const uint32_t row_off = static_cast<uint32_t>(rl) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(rl & 7);
     float dacc = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 64; ++ch) {
       const int cl = half * (BN / 2) + ch * 32;
       const int c0 = n0 + cl;
-      if (kMasked && c0 >= N) break;  // warp-uniform
       float v[32];
       tmem_ld_32x32b_x32(tacc + cl, v);
       tmem_ld_wait();
@@ -322,28 +327,21 @@ struct EpiGrad {
           const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
           float g = e * (ri + cv[jj]);
           if (kDiag && c0 + j == dcol) g = zero_diag ? 0.f : g - dcoef;
-          if (kMasked) g = (row_ok && c0 + j < N) ? g : 0.f;
           dacc = fmaf(g, cosv, dacc);
           v[j] = g;
         }
       }
-      if (row_ok) {
-        if (vec_ok && (!kMasked || c0 + 32 <= N)) {
-          uint4* dst = reinterpret_cast<uint4*>(grow + c0);
+      // 32 columns = 64 bytes = four 16-byte chunks of this row inside box cl/64; chunk c lives at (c ^ (row & 7))
+      uint8_t* box = staging + (cl >> 6) * (kBM * 128) + row_off;
+      const uint32_t cbase = static_cast<uint32_t>((cl & 63) >> 3);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            dst[j] = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < N) grow[c0 + j] = __float2bfloat16_rn(v[j]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(box + (((cbase + j) ^ sw) << 4)) = o;
       }
     }
     dacc = warp_sum(dacc);
@@ -352,18 +350,31 @@ struct EpiGrad {
 
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                             int q, int lane, int ewarp, float* smem) {
-    // stage the column terms of this tile (zero beyond N) -- all epilogue warps, then a named barrier
+                                             int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
+                                             uint8_t* staging) {
     const int t = ewarp * 32 + lane;
+    // (1) the previous tile's bulk stores must have drained the staging buffer; stage this tile's column terms
+    if (t == 0) tma_store_wait_read();
     if (t < BN) smem[t] = (n0 + t < N) ? __ldg(P.cinv + n0 + t) : 0.f;
     named_bar_sync(1, kEpiWarps * 32);
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
-    const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
     const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
-    if (interior && !has_diag) tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
-    else if (interior) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
-    else tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2);
+    if (has_diag) tile<BN, true>(P, tacc, m0, n0, M, half, q, lane, smem, sl2, staging);
+    else tile<BN, false>(P, tacc, m0, n0, M, half, q, lane, smem, sl2, staging);
+    // (2) make the generic-proxy writes visible to the async proxy, then one thread stores the tile
+    fence_proxy_async_smem();
+    named_bar_sync(2, kEpiWarps * 32);
+    if (t == 0) {
+#pragma unroll
+      for (int b = 0; b < BN / 64; ++b)
+        if (n0 + 64 * b < N) tma_store_2d(cmap, staging + b * (kBM * 128), n0 + 64 * b, m0);
+      tma_store_commit();
+    }
+  }
+
+  static __device__ __forceinline__ void finish(int ewarp, int lane) {
+    if (ewarp == 0 && lane == 0) tma_store_wait_all();
   }
 };
 
@@ -374,9 +385,10 @@ template <int BN, class Epi, int kCG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
                const GemmProblem p0, const GemmProblem p1, const typename Epi::Params e0,
                const typename Epi::Params e1) {
-  using S = GemmSmem<BN, kCG>;
+  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: a power of two >= 32
   constexpr int kTileM = kBM * kCG;       // rows of one (pair) tile
@@ -385,7 +397,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStages * S::kBBytes);
+  uint8_t* staging = sB + kStages * S::kBBytes;  // epilogue output tile (TMA-store epilogues), 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Epi::template staging_bytes<BN>());
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's copy is the live one)
   uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA          (multicast to both CTAs)
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue     (multicast to both CTAs)
@@ -550,7 +563,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       if (tc.kb_begin < tc.kb_end)
         Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
-                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + acc_stage * 256);
+                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + acc_stage * 256,
+                              tc.prob ? &tmC1 : &tmC0, staging);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -558,6 +572,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
       }
     }
+    Epi::finish(warp - 4, lane);
   }
 
   tcgen05_fence_before();

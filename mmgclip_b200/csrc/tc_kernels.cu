@@ -94,10 +94,10 @@ static GemmProblem empty_problem() {
 
 template <int BN, class Epi, int kCG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
-                  const GemmProblem& p0, const GemmProblem& p1, const typename Epi::Params& e0,
-                  const typename Epi::Params& e1, cudaStream_t st) {
+                  const CUtensorMap& c0, const CUtensorMap& c1, const GemmProblem& p0, const GemmProblem& p1,
+                  const typename Epi::Params& e0, const typename Epi::Params& e1, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, Epi, kCG>;
-  using S = GemmSmem<BN, kCG>;
+  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -121,7 +121,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, p0, p1, e0, e1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, c0, c1, p0, p1, e0, e1);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
   count_launch();
   return 0;
@@ -166,7 +166,7 @@ int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ld
   GemmProblem p1 = empty_problem();
   EpiStoreF32::Params e;
   e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
 
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
@@ -186,7 +186,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, p0, p1, e0, e1, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, ma0, ma0, p0, p1, e0, e1, st);
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
@@ -201,7 +201,7 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
   GemmProblem p1 = empty_problem();
   EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
-  MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
@@ -215,10 +215,13 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   if ((rc = make_operand_map(&mb, B, cb, D, tcfg.BN / tcfg.cg)) != 0) return rc;
   GemmProblem p0 = make_problem(rb, cb, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
+  // output tile map: g block [rb, cb] bf16 (pitch ldg), box = 128 rows x 64 columns, 128-byte swizzle
+  CUtensorMap mc;
+  if ((rc = make_tmap(&mc, G, cb, rb, ldg, kBM)) != 0) return rc;
   EpiGrad::Params e;
-  e.G = reinterpret_cast<__nv_bfloat16*>(G); e.ldg = ldg; e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
+  e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
   e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
-  MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
 }
 
 }  // namespace mmg
