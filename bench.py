@@ -110,53 +110,78 @@ def workload_config(n_gpus, sample_batch=None):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and clock-event (throttle) reasons of one GPU from a background thread through NVML
+    while the timed regions run (the recipe's nvidia-smi query, without the process start-up latency)."""
 
-    def __init__(self, gpu_index):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
+    def __init__(self, gpu_index, period_s=0.005):
+        import threading
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.ok = False
+        self._stop = threading.Event()
+        self._active = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self.ok = False
+        self.period = period_s
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        if self.ok:
+            self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    self.samples.append((mhz, pw))
+                    r = int(get_reasons(self.h))
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(self.period)
+
+    def begin(self):
+        self._active.set()
+
+    def end(self):
+        self._active.clear()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        self.tmp.flush()
-        self.tmp.seek(0)
-        sm, reasons, mx, power = [], set(), None, []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.tmp.read().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.tmp.name)
-        except OSError:
-            pass
-        if sm:
-            busy = sorted(sm)[len(sm) // 2:]  # samples under load dominate the upper half
-            out.update({"sm_mhz": sorted(sm)[len(sm) // 2], "sm_mhz_under_load_median": busy[len(busy) // 2],
-                        "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                        "power_w_max": max(power) if power else None})
+        self._stop.set()
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.samples:
+            mhz = sorted(m for m, _ in self.samples)
+            out["sm_mhz"] = mhz[len(mhz) // 2]
+            out["sm_mhz_min"] = mhz[0]
+            out["power_w_max"] = max(p for _, p in self.samples)
+            out["how"] = "NVML polled every 5 ms from a thread during both timed regions (median)"
         return out
 
 
@@ -242,6 +267,8 @@ def run_gpu(args):
         loss = step(*dev_sets[i % n_sets])
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.begin()
     launches0 = _lib.load().mmg_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -251,6 +278,8 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_value = max_over_ranks(e0.elapsed_time(e1) / K)
+    if sampler is not None:
+        sampler.end()
     launches = _lib.load().mmg_kernel_launch_count() - launches0
     loss_value = float(loss.item())
 
@@ -289,10 +318,14 @@ def run_gpu(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     W2 = W + (W % 2)  # keep the double-buffer parity aligned
     barrier()
+    if sampler is not None:
+        sampler.begin()
     e2.record()
     e2e_loop(K, W2)
     e3.record()
     barrier()
+    if sampler is not None:
+        sampler.end()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / K)
     clocks = sampler.stop() if sampler is not None else None
 
@@ -375,8 +408,8 @@ def kernel_breakdown(torch, ops, dev, rows, cols, d):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: the metric's 32768)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

@@ -138,6 +138,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// Pull a box into L2 ahead of the copy that will land it in shared memory (hides DRAM latency for operands that are
+// streamed from HBM, e.g. the 128 MiB gradient-coefficient block, without spending shared memory on deeper rings).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async group); out-of-bounds parts of the box are clipped by the hardware.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c_inner, int c_outer) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -50,6 +50,16 @@ struct GemmSmem {
 
 struct TileCoord {
   int prob, m_blk, n_blk, kb_begin, kb_end;
+  int atomic;  // this tile is a K-slice of an output tile shared with other CTAs: accumulate with red.add
+};
+
+// Tail balancing ("stream-K lite").  With T output tiles on G CTA groups the last round is only (T mod G)/G full.
+// Tiles of that last round are cut into `rem_split` K-slices each, spread over all groups and accumulated with atomics,
+// so the tail costs ~(T mod G)/G of a round instead of a whole one.  Only used for accumulate-mode launches.
+struct TailSplit {
+  int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
+  int rem_split;   // >= 1
+  int prefetch_kb; // L2 prefetch distance of the TMA producer in 64-wide K blocks (0 = off)
 };
 
 __device__ __forceinline__ TileCoord decode_tile(int t, const GemmProblem& p0, const GemmProblem& p1) {
@@ -67,6 +77,22 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const GemmProblem& p0, c
   const int per = (nkb + p.k_splits - 1) / p.k_splits;
   c.kb_begin = split * per;
   c.kb_end = min(nkb, c.kb_begin + per);
+  c.atomic = 0;
+  return c;
+}
+
+__device__ __forceinline__ TileCoord decode_virtual(int t, const GemmProblem& p0, const GemmProblem& p1,
+                                                    const TailSplit& ts) {
+  if (ts.rem_split <= 1 || t < ts.full_tiles) return decode_tile(t, p0, p1);
+  const int r = t - ts.full_tiles;
+  const int base = ts.full_tiles + r / ts.rem_split;
+  const int part = r - (r / ts.rem_split) * ts.rem_split;
+  TileCoord c = decode_tile(base, p0, p1);
+  const int nkb = c.kb_end - c.kb_begin;
+  const int per = (nkb + ts.rem_split - 1) / ts.rem_split;
+  c.kb_begin = c.kb_begin + part * per;
+  c.kb_end = min(c.kb_end, c.kb_begin + per);
+  c.atomic = 1;
   return c;
 }
 
@@ -91,8 +117,9 @@ struct EpiStoreF32 {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging) {
+                                             uint8_t* staging, int force_atomic) {
     (void)ewarp; (void)smem; (void)cmap; (void)staging;
+    const int mode = force_atomic ? 2 : P.mode;
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;
     const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
@@ -108,7 +135,7 @@ struct EpiStoreF32 {
       if (row < M) {
         const bool vec = vec_ok && c0 + 32 <= N;
         // C = act(C_old + alpha*acc + bias): accumulate first, then bias / activation (multi-pass contractions)
-        if (P.mode == 1) {
+        if (mode == 1) {
           if (vec) {
             const float4* src = reinterpret_cast<const float4*>(crow + c0);
 #pragma unroll
@@ -137,7 +164,7 @@ struct EpiStoreF32 {
             v[j] = x;
           }
         }
-        if (vec && P.mode != 2) {
+        if (vec && mode != 2) {
           float4* dst = reinterpret_cast<float4*>(crow + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -145,7 +172,7 @@ struct EpiStoreF32 {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (c0 + j < N) {
-              if (P.mode == 2) atomicAdd(crow + c0 + j, v[j]);
+              if (mode == 2) atomicAdd(crow + c0 + j, v[j]);
               else crow[c0 + j] = v[j];
             }
           }
@@ -258,8 +285,8 @@ struct EpiLse {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging) {
-    (void)ewarp; (void)smem; (void)cmap; (void)staging;
+                                             uint8_t* staging, int force_atomic) {
+    (void)ewarp; (void)smem; (void)cmap; (void)staging; (void)force_atomic;
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
@@ -351,7 +378,8 @@ struct EpiGrad {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging) {
+                                             uint8_t* staging, int force_atomic) {
+    (void)force_atomic;
     const int t = ewarp * 32 + lane;
     // (1) the previous tile's bulk stores must have drained the staging buffer; stage this tile's column terms
     if (t == 0) tma_store_wait_read();
@@ -386,7 +414,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
-               const GemmProblem p0, const GemmProblem p1, const typename Epi::Params e0,
+               const GemmProblem p0, const GemmProblem p1, const TailSplit tail, const typename Epi::Params e0,
                const typename Epi::Params e1) {
   using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
   constexpr int kStages = S::kStages;
@@ -444,7 +472,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p0.num_tiles() + p1.num_tiles();
+  const int real_tiles = p0.num_tiles() + p1.num_tiles();
+  const int total_tiles = tail.rem_split > 1 ? tail.full_tiles + (real_tiles - tail.full_tiles) * tail.rem_split
+                                             : real_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
@@ -452,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int t = tile_first; t < total_tiles; t += tile_step) {
-      const TileCoord tc = decode_tile(t, p0, p1);
+      const TileCoord tc = decode_virtual(t, p0, p1, tail);
       const GemmProblem& p = tc.prob ? p1 : p0;
       const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
       const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
@@ -482,6 +512,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < S::kBRows / 64; ++i) load(mB, b_dst + i * (kBK * 128), n0 + i * 64, k0);
           }
+          // long K loops stream at least one operand from HBM: pull the boxes kPrefetchKb blocks ahead into L2
+          if (tail.prefetch_kb > 0 && kb + tail.prefetch_kb < tc.kb_end) {
+            const int kp = k0 + tail.prefetch_kb * kBK;
+            if (!p.a_mn) {
+              tma_prefetch_l2_2d(mA, kp, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBM / 64; ++i) tma_prefetch_l2_2d(mA, m0 + i * 64, kp);
+            }
+            if (!p.b_mn) {
+              tma_prefetch_l2_2d(mB, kp, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < S::kBRows / 64; ++i) tma_prefetch_l2_2d(mB, n0 + i * 64, kp);
+            }
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -494,7 +540,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0;
       int it = 0;
       for (int t = tile_first; t < total_tiles; t += tile_step, ++it) {
-        const TileCoord tc = decode_tile(t, p0, p1);
+        const TileCoord tc = decode_virtual(t, p0, p1, tail);
         const GemmProblem& p = tc.prob ? p1 : p0;
         const int acc_stage = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -554,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     int it = 0;
     for (int t = tile_first; t < total_tiles; t += tile_step, ++it) {
-      const TileCoord tc = decode_tile(t, p0, p1);
+      const TileCoord tc = decode_virtual(t, p0, p1, tail);
       const GemmProblem& p = tc.prob ? p1 : p0;
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -564,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (tc.kb_begin < tc.kb_end)
         Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
                               tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + acc_stage * 256,
-                              tc.prob ? &tmC1 : &tmC0, staging);
+                              tc.prob ? &tmC1 : &tmC0, staging, tc.atomic);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {

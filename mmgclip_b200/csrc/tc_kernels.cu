@@ -92,10 +92,14 @@ static GemmProblem empty_problem() {
   return p;
 }
 
+static bool tail_balance_enabled();
+static int prefetch_distance();
+
 template <int BN, class Epi, int kCG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
                   const CUtensorMap& c0, const CUtensorMap& c1, const GemmProblem& p0, const GemmProblem& p1,
-                  const typename Epi::Params& e0, const typename Epi::Params& e1, cudaStream_t st) {
+                  const typename Epi::Params& e0, const typename Epi::Params& e1, cudaStream_t st,
+                  bool balance_tail = false) {
   auto kern = gemm_tc_kernel<BN, Epi, kCG>;
   using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
   static bool configured = false;  // per instantiation
@@ -107,7 +111,32 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   const int total = p0.num_tiles() + p1.num_tiles();
   if (total <= 0) return 0;
   const int groups = sm_count() / kCG;  // CTAs (or CTA pairs) that can be resident: one per SM
-  const int grid = (total < groups ? total : groups) * kCG;
+  // tail balancing: cut the tiles of an under-filled last round into K-slices (see TailSplit in gemm_tc.cuh)
+  TailSplit tail;
+  tail.full_tiles = total;
+  tail.rem_split = 1;
+  tail.prefetch_kb = prefetch_distance();
+  if (balance_tail && tail_balance_enabled() && total > groups && total % groups != 0 && p0.k_splits == 1 &&
+      p1.k_splits <= 1) {
+    const int rem = total % groups;
+    int nkb = (p0.K + kBK - 1) / kBK;
+    if (p1.num_tiles() > 0) { const int n1 = (p1.K + kBK - 1) / kBK; nkb = n1 < nkb ? n1 : nkb; }
+    int best_s = 1;
+    double best = 1.0;  // cost of the tail in units of a full round
+    for (int sdiv = 2; sdiv <= 8; ++sdiv) {
+      if (nkb / sdiv < 8) break;                                   // keep slices at least 8 K-blocks long
+      if (((nkb + sdiv - 1) / sdiv) * (sdiv - 1) >= nkb) continue;  // would create an empty slice
+      const int rounds = (rem * sdiv + groups - 1) / groups;
+      const double cost = (double)rounds / sdiv + 0.02 * sdiv;     // small penalty per extra slice (atomics, ramp)
+      if (cost < best - 1e-9) { best = cost; best_s = sdiv; }
+    }
+    if (best_s > 1) {
+      tail.full_tiles = total - rem;
+      tail.rem_split = best_s;
+    }
+  }
+  const int virt = tail.full_tiles + (total - tail.full_tiles) * tail.rem_split;
+  const int grid = (virt < groups ? virt : groups) * kCG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -121,7 +150,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, c0, c1, p0, p1, e0, e1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, c0, c1, p0, p1, tail, e0, e1);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
   count_launch();
   return 0;
@@ -136,6 +165,23 @@ static bool pair_enabled() {
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+static bool tail_balance_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMG_TC_TAIL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static int prefetch_distance() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMG_TC_PREFETCH");
+    v = e != nullptr ? atoi(e) : 12;
+    if (v < 0) v = 0;
+  }
+  return v;
 }
 struct TileCfg { int BN, cg; };
 static TileCfg pick_tile(int M, int N) {
@@ -186,7 +232,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, ma0, ma0, p0, p1, e0, e1, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, ma0, ma0, p0, p1, e0, e1, st, true);
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
