@@ -111,14 +111,67 @@ struct EpiStoreF32 {
     const float* alpha_ptr;  // optional device scalar multiplied into alpha (e.g. the logit scale)
     int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
     int relu;
+    int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
   };
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
-  static __device__ __forceinline__ void finish(int, int) {}
+  // two column-half groups x one [128 rows x 32 fp32] box each
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 2 * kBM * 128; }
+
+  static __device__ __forceinline__ void finish(int ewarp, int lane) {
+    if ((ewarp & 3) == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  // TMA path: the tile leaves through a 128B-swizzled staging box per 32 columns and a bulk-tensor store
+  // (C = v) or reduce-add (C += v, performed at L2 -- also what makes split-K safe).  Full 128-byte lines, no LSU
+  // traffic, ragged edges clipped by the hardware.
+  template <int BN>
+  static __device__ __forceinline__ void run_tma(const Params& P, uint32_t tacc, int m0, int n0, int N, int half, int q,
+                                                 int lane, const CUtensorMap* cmap, uint8_t* staging) {
+    const float alpha = P.alpha_ptr ? P.alpha * __ldg(P.alpha_ptr) : P.alpha;
+    uint8_t* box = staging + half * (kBM * 128);
+    const int rl = q * 32 + lane;
+    uint8_t* rowp = box + rl * 128;
+    const uint32_t sw = static_cast<uint32_t>(rl & 7);
+    const bool issuer = (q == 0 && lane == 0);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 64; ++ch) {
+      const int cl = half * (BN / 2) + ch * 32;
+      const int c0 = n0 + cl;
+      if (c0 >= N) break;  // uniform across the 4 warps of this column half
+      float v[32];
+      tmem_ld_32x32b_x32(tacc + cl, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = v[j] * alpha;
+        if (P.bias != nullptr && c0 + j < N) x += __ldg(P.bias + c0 + j);
+        if (P.relu) x = fmaxf(x, 0.f);
+        v[j] = x;
+      }
+      if (issuer) tma_store_wait_read();  // the previous box of this group has left shared memory
+      named_bar_sync(3 + half, 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(j) ^ sw) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(3 + half, 128);
+      if (issuer) {
+        if (P.mode == 0) tma_store_2d(cmap, box, c0, m0);
+        else tma_reduce_add_2d(cmap, box, c0, m0);
+        tma_store_commit();
+      }
+    }
+  }
+
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
                                              uint8_t* staging, int force_atomic) {
-    (void)ewarp; (void)smem; (void)cmap; (void)staging;
+    (void)ewarp; (void)smem;
+    if (P.use_tma) {
+      run_tma<BN>(P, tacc, m0, n0, N, half, q, lane, cmap, staging);
+      return;
+    }
     const int mode = force_atomic ? 2 : P.mode;
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;

@@ -49,6 +49,29 @@ static int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long
   return 0;
 }
 
+// fp32 row-major output matrix [rows, cols] with pitch ld: box = [128 rows x 32 columns] (32 fp32 = 128 bytes)
+static int make_out_tmap_f32(CUtensorMap* m, const float* ptr, long long cols, long long rows, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(-4, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)kBM};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-4, "cuTensorMapEncodeTiled (fp32 output) failed (CUresult %d)", (int)r);
+  return 0;
+}
+static bool out_tma_ok(const float* C, long long ldc) {
+  static int en = -1;
+  if (en < 0) {
+    const char* e = getenv("MMG_TC_TMA_OUT");
+    en = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return en == 1 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc & 3) == 0;
+}
+
 // operand with `rows` along M/N and `K` along the contraction
 static int make_operand_map(CUtensorMap* m, const TcOperand& op, int rows, int K, int tile_rows) {
   if (!op.mn_major) return make_tmap(m, op.ptr, K, rows, op.ld, tile_rows);  // [rows, K]: box tile_rows x 64(K)
@@ -170,7 +193,7 @@ static bool tail_balance_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MMG_TC_TAIL");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower (scalar atomics in the tail): opt-in
   }
   return v == 1;
 }
@@ -178,7 +201,7 @@ static int prefetch_distance() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MMG_TC_PREFETCH");
-    v = e != nullptr ? atoi(e) : 12;
+    v = e != nullptr ? atoi(e) : 0;  // measured slower than no prefetch on B200: opt-in
     if (v < 0) v = 0;
   }
   return v;
@@ -212,7 +235,11 @@ int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ld
   GemmProblem p1 = empty_problem();
   EpiStoreF32::Params e;
   e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
+  // act(C_old + v) cannot be expressed as a reduction: accumulate + bias/ReLU keeps the direct read-modify-write path
+  e.use_tma = out_tma_ok(C, ldc) && !(mode != 0 && (relu || bias != nullptr));
+  CUtensorMap mc = ma;
+  if (e.use_tma && (rc = make_out_tmap_f32(&mc, C, N, M, ldc)) != 0) return rc;
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
 }
 
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
@@ -230,9 +257,15 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, 1, A1.mn_major, B1.mn_major, tcfg.cg);
   EpiStoreF32::Params e0, e1;
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
+  e0.use_tma = out_tma_ok(C0, ldc0) && out_tma_ok(C1, ldc1);
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, ma0, ma0, p0, p1, e0, e1, st, true);
+  CUtensorMap mc0 = ma0, mc1 = ma0;
+  if (e0.use_tma) {
+    if ((rc = make_out_tmap_f32(&mc0, C0, N0, M0, ldc0)) != 0) return rc;
+    if ((rc = make_out_tmap_f32(&mc1, C1, N1, M1, ldc1)) != 0) return rc;
+  }
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma0, mb0, ma1, mb1, mc0, mc1, p0, p1, e0, e1, st, true);
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
