@@ -44,7 +44,7 @@ struct GemmSmem {
   static constexpr int kBBytes = kBRows * kBK * 2;
   // operand ring: whatever is left of ~192 KB after the epilogue's output staging tile (TMA-store epilogues)
   static constexpr int kStages = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
-  static constexpr int kBarBytes = 4096;  // mbarriers + TMEM slot (first 512 B) and 2 x 1 KB of epilogue scratch
+  static constexpr int kBarBytes = 5120;  // mbarriers + TMEM slot (first 512 B) and 8 x 512 B of per-warp epilogue scratch
   static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kBarBytes + 1024 /* alignment slack */;
 };
 
@@ -113,30 +113,27 @@ struct EpiStoreF32 {
     int relu;
     int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
   };
-  // two column-half groups x one [128 rows x 32 fp32] box each
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 2 * kBM * 128; }
+  // one [32 rows x 32 fp32] (4 KB, 128B-swizzled) staging box per epilogue warp
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kEpiWarps * 4096; }
 
-  static __device__ __forceinline__ void finish(int ewarp, int lane) {
-    if ((ewarp & 3) == 0 && lane == 0) tma_store_wait_all();
+  static __device__ __forceinline__ void finish(int, int lane) {
+    if (lane == 0) tma_store_wait_all();
   }
 
-  // TMA path: the tile leaves through a 128B-swizzled staging box per 32 columns and a bulk-tensor store
-  // (C = v) or reduce-add (C += v, performed at L2 -- also what makes split-K safe).  Full 128-byte lines, no LSU
-  // traffic, ragged edges clipped by the hardware.
+  // TMA path: every warp stages its own 32 x 32 block of the tile and ships it with a bulk-tensor store (C = v) or
+  // reduce-add (C += v, performed at L2 -- also what makes split-K safe).  Warp-local: no CTA-level barriers; full
+  // 128-byte lines, no LSU traffic to global memory, ragged edges clipped by the hardware.
   template <int BN>
   static __device__ __forceinline__ void run_tma(const Params& P, uint32_t tacc, int m0, int n0, int N, int half, int q,
-                                                 int lane, const CUtensorMap* cmap, uint8_t* staging) {
+                                                 int lane, const CUtensorMap* cmap, uint8_t* box) {
     const float alpha = P.alpha_ptr ? P.alpha * __ldg(P.alpha_ptr) : P.alpha;
-    uint8_t* box = staging + half * (kBM * 128);
-    const int rl = q * 32 + lane;
-    uint8_t* rowp = box + rl * 128;
-    const uint32_t sw = static_cast<uint32_t>(rl & 7);
-    const bool issuer = (q == 0 && lane == 0);
+    uint8_t* rowp = box + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
 #pragma unroll 1
     for (int ch = 0; ch < BN / 64; ++ch) {
       const int cl = half * (BN / 2) + ch * 32;
       const int c0 = n0 + cl;
-      if (c0 >= N) break;  // uniform across the 4 warps of this column half
+      if (c0 >= N) break;  // warp-uniform
       float v[32];
       tmem_ld_32x32b_x32(tacc + cl, v);
       tmem_ld_wait();
@@ -147,17 +144,17 @@ struct EpiStoreF32 {
         if (P.relu) x = fmaxf(x, 0.f);
         v[j] = x;
       }
-      if (issuer) tma_store_wait_read();  // the previous box of this group has left shared memory
-      named_bar_sync(3 + half, 128);
+      if (lane == 0) tma_store_wait_read();  // this warp's previous box has left shared memory
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(j) ^ sw) << 4)) =
             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       fence_proxy_async_smem();
-      named_bar_sync(3 + half, 128);
-      if (issuer) {
-        if (P.mode == 0) tma_store_2d(cmap, box, c0, m0);
-        else tma_reduce_add_2d(cmap, box, c0, m0);
+      __syncwarp();
+      if (lane == 0) {
+        if (P.mode == 0) tma_store_2d(cmap, box, c0, m0 + q * 32);
+        else tma_reduce_add_2d(cmap, box, c0, m0 + q * 32);
         tma_store_commit();
       }
     }
@@ -167,9 +164,9 @@ struct EpiStoreF32 {
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
                                              uint8_t* staging, int force_atomic) {
-    (void)ewarp; (void)smem;
+    (void)smem;
     if (P.use_tma) {
-      run_tma<BN>(P, tacc, m0, n0, N, half, q, lane, cmap, staging);
+      run_tma<BN>(P, tacc, m0, n0, N, half, q, lane, cmap, staging + ewarp * 4096);
       return;
     }
     const int mode = force_atomic ? 2 : P.mode;
@@ -357,10 +354,11 @@ struct EpiLse {
 //   rinv[r] = s*gl/(2B*rowsum[r]),  cinv[c] = s*gl/(2B*colsum[c]),  dcoef = s*gl/B        (gl = d loss)
 // i.e. g = s * dloss/dlogit, so that dI = g . T and dT = g^T . I need no further scaling.  g goes out as bf16 into a
 // block scratch (never the full B x B) that the two gradient GEMMs consume; sum(g * cos) accumulates d loss / d log(s).
-// One accumulator row per thread (32x32b layout).  The column terms cinv of the tile are staged once in shared memory
-// (broadcast 16-byte loads).  The bf16 tile is assembled in a 128B-swizzled shared-memory staging buffer and written
-// with TMA bulk-tensor stores: full 128-byte lines, no LSU traffic, ragged edges clipped by the hardware.  No masking
-// is needed anywhere: out-of-range operand rows are zero-filled, so cos = 0 there and g*cos contributes nothing.
+// One accumulator row per thread (32x32b layout).  Everything is warp-local: each warp keeps a private copy of the
+// column terms cinv of its columns in shared memory (broadcast 16-byte loads), assembles its 32 x 64 block of bf16
+// coefficients in its own 128B-swizzled staging box and ships it with a TMA bulk-tensor store -- full 128-byte lines,
+// no LSU traffic to global memory, no CTA-level barrier, ragged edges clipped by the hardware.  No masking of g is
+// needed: out-of-range operand rows are zero-filled, so cos = 0 there and g*cos contributes nothing.
 struct EpiGrad {
   struct Params {
     const float* rinv;        // [M]
@@ -370,14 +368,14 @@ struct EpiGrad {
     float* dlogscale_acc;     // device scalar accumulator: sum g * cos
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
   };
-  // staging: BN/64 boxes of [128 rows x 128 bytes] (64 bf16 columns each)
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kBM * BN * 2; }
+  // one [32 rows x 64 bf16] (4 KB, 128B-swizzled) staging box per epilogue warp
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kEpiWarps * 4096; }
 
   template <int BN, bool kDiag>
-  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int half, int q,
-                                              int lane, const float* cs, float sl2, uint8_t* staging) {
-    const int rl = q * 32 + lane;  // row inside the tile
-    const int row = m0 + rl;
+  static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
+                                              int q, int lane, const float* cs, float sl2, const CUtensorMap* cmap,
+                                              uint8_t* box) {
+    const int row = m0 + q * 32 + lane;
     const int dcol = row + P.diag_offset;
     const float ri = (row < M) ? __ldg(P.rinv + row) : 0.f;
     float dcoef = 0.f;
@@ -386,19 +384,21 @@ struct EpiGrad {
       dcoef = __ldg(P.scal);
       zero_diag = __ldg(P.scal + 2) != 0.f;
     }
-    const uint32_t row_off = static_cast<uint32_t>(rl) * 128u;
-    const uint32_t sw = static_cast<uint32_t>(rl & 7);
+    uint8_t* rowp = box + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
     float dacc = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 64; ++ch) {
-      const int cl = half * (BN / 2) + ch * 32;
+      const int cw = ch * 32;                       // column inside this warp's half
+      const int cl = half * (BN / 2) + cw;          // column inside the tile
       const int c0 = n0 + cl;
+      if (c0 >= N) break;  // warp-uniform
       float v[32];
       tmem_ld_32x32b_x32(tacc + cl, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cs + cl + 4 * j4);  // broadcast LDS.128
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + cw + 4 * j4);  // broadcast LDS.128
         const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -411,9 +411,12 @@ struct EpiGrad {
           v[j] = g;
         }
       }
-      // 32 columns = 64 bytes = four 16-byte chunks of this row inside box cl/64; chunk c lives at (c ^ (row & 7))
-      uint8_t* box = staging + (cl >> 6) * (kBM * 128) + row_off;
-      const uint32_t cbase = static_cast<uint32_t>((cl & 63) >> 3);
+      // 32 columns = 64 bytes = four 16-byte chunks of this row; the box holds 64 columns (two chunks of work)
+      if ((ch & 1) == 0) {
+        if (lane == 0) tma_store_wait_read();  // this warp's previous box has left shared memory
+        __syncwarp();
+      }
+      const uint32_t cbase = static_cast<uint32_t>((ch & 1) * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 o;
@@ -421,7 +424,15 @@ struct EpiGrad {
         o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
         o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
         o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(box + (((cbase + j) ^ sw) << 4)) = o;
+        *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
+      }
+      if ((ch & 1) == 1 || c0 + 32 >= N) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(cmap, box, c0 - (ch & 1) * 32, m0 + q * 32);
+          tma_store_commit();
+        }
       }
     }
     dacc = warp_sum(dacc);
@@ -433,29 +444,24 @@ struct EpiGrad {
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
                                              uint8_t* staging, int force_atomic) {
     (void)force_atomic;
-    const int t = ewarp * 32 + lane;
-    // (1) the previous tile's bulk stores must have drained the staging buffer; stage this tile's column terms
-    if (t == 0) tma_store_wait_read();
-    if (t < BN) smem[t] = (n0 + t < N) ? __ldg(P.cinv + n0 + t) : 0.f;
-    named_bar_sync(1, kEpiWarps * 32);
+    // this warp's private copy of the column terms of its BN/2 columns (zero beyond N); warp-synchronous, no barrier
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < BN / 2; i += 32) {
+      const int c = n0 + half * (BN / 2) + i;
+      smem[i] = (c < N) ? __ldg(P.cinv + c) : 0.f;
+    }
+    __syncwarp();
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
-    if (has_diag) tile<BN, true>(P, tacc, m0, n0, M, half, q, lane, smem, sl2, staging);
-    else tile<BN, false>(P, tacc, m0, n0, M, half, q, lane, smem, sl2, staging);
-    // (2) make the generic-proxy writes visible to the async proxy, then one thread stores the tile
-    fence_proxy_async_smem();
-    named_bar_sync(2, kEpiWarps * 32);
-    if (t == 0) {
-#pragma unroll
-      for (int b = 0; b < BN / 64; ++b)
-        if (n0 + 64 * b < N) tma_store_2d(cmap, staging + b * (kBM * 128), n0 + 64 * b, m0);
-      tma_store_commit();
-    }
+    uint8_t* box = staging + ewarp * 4096;
+    if (has_diag) tile<BN, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box);
+    else tile<BN, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box);
   }
 
-  static __device__ __forceinline__ void finish(int ewarp, int lane) {
-    if (ewarp == 0 && lane == 0) tma_store_wait_all();
+  static __device__ __forceinline__ void finish(int, int lane) {
+    if (lane == 0) tma_store_wait_all();
   }
 };
 
@@ -486,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA     (leader's copy is the live one)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   // epilogue scratch: 2 accumulator stages x 256 floats, after the barriers (inside the 4 KB tail reserved in GemmSmem)
-  float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // 128 floats per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -662,7 +668,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       if (tc.kb_begin < tc.kb_end)
         Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
-                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + acc_stage * 256,
+                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + (warp - 4) * 128,
                               tc.prob ? &tmC1 : &tmC0, staging, tc.atomic);
       tcgen05_fence_before();
       __syncwarp();

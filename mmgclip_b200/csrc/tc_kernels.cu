@@ -49,13 +49,13 @@ static int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long
   return 0;
 }
 
-// fp32 row-major output matrix [rows, cols] with pitch ld: box = [128 rows x 32 columns] (32 fp32 = 128 bytes)
+// fp32 row-major output matrix [rows, cols] with pitch ld: box = [32 rows x 32 columns] (one epilogue warp's block)
 static int make_out_tmap_f32(CUtensorMap* m, const float* ptr, long long cols, long long rows, long long ld) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(-4, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)kBM};
+  cuuint32_t box[2] = {32u, 32u};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -294,9 +294,9 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   if ((rc = make_operand_map(&mb, B, cb, D, tcfg.BN / tcfg.cg)) != 0) return rc;
   GemmProblem p0 = make_problem(rb, cb, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
-  // output tile map: g block [rb, cb] bf16 (pitch ldg), box = 128 rows x 64 columns, 128-byte swizzle
+  // output map: g block [rb, cb] bf16 (pitch ldg), box = 32 rows x 64 columns (one epilogue warp's block)
   CUtensorMap mc;
-  if ((rc = make_tmap(&mc, G, cb, rb, ldg, kBM)) != 0) return rc;
+  if ((rc = make_tmap(&mc, G, cb, rb, ldg, 32)) != 0) return rc;
   EpiGrad::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
   e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
