@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -353,6 +354,12 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   if ((size_t)((long long)Rb * ldg * esz) > workspace_bytes)
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd: workspace too small (%zu bytes)", workspace_bytes);
 
+  // measurement hook (bench.py's per-kernel roofline): MMG_BWD_PHASES=1 runs only the coefficient launches, =2 only
+  // the gradient-GEMM launches (on whatever the scratch holds); unset / 3 = the real thing
+  int phases = 3;
+  if (const char* e = getenv("MMG_BWD_PHASES")) phases = atoi(e);
+  if (phases < 1 || phases > 3) phases = 3;
+
   for (int r0 = 0; r0 < rows; r0 += Rb) {
     const int rb = rows - r0 < Rb ? rows - r0 : Rb;
     for (int c0 = 0; c0 < cols; c0 += Cb) {
@@ -362,8 +369,10 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
         const char* a = static_cast<const char*>(a_hat) + (long long)r0 * D * 2;
         const char* b = static_cast<const char*>(b_hat) + (long long)c0 * D * 2;
         // (1) recompute the cosine block on tensor cores; epilogue turns it into bf16 gradient coefficients g
-        MMG_TRY(tc_infonce_grad_block(a, b, rb, cb, D, doff, scale, rinv + r0, cinv + c0, scal, workspace, ldg,
-                                      dlogscale_acc, st));
+        if (phases & 1)
+          MMG_TRY(tc_infonce_grad_block(a, b, rb, cb, D, doff, scale, rinv + r0, cinv + c0, scal, workspace, ldg,
+                                        dlogscale_acc, st));
+        if (!(phases & 2)) continue;
         // (2) dA[r0:, :] += g . b_blk   and   dB[c0:, :] += g^T . a_blk   in one launch
         TcOperand A0{workspace, ldg, 0}, B0{b, D, 1};
         TcOperand A1{workspace, ldg, 1}, B1{a, D, 1};
