@@ -202,7 +202,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from mmgclip_b200 import _lib, ops
-    from mmgclip_b200.distributed import allreduce_gradients, sharded_info_nce
+    from mmgclip_b200.distributed import allreduce_gradients, gather_columns_async, sharded_info_nce
     from mmgclip_b200.projection import LinearProjectionLayer
     from oracle import clip_oracle as oc  # only for the synthetic-input recipe and the cpu_baseline leg
 
@@ -249,13 +249,13 @@ def run_gpu(args):
     def step(xi, xt):
         head_i.layer.weight.grad = None
         head_t.layer.weight.grad = None
-        ie = head_i.forward_normalized(xi)
         te = head_t.forward_normalized(xt)
-        loss = sharded_info_nce(ie, te, logit_scale, group=group, prec=prec)
+        gathered = gather_columns_async(te, group=group, prec=prec) if world > 1 else None  # overlaps the image head
+        ie = head_i.forward_normalized(xi)
+        loss = sharded_info_nce(ie, te, logit_scale, group=group, prec=prec, gathered=gathered)
         loss.backward()
         if world > 1:
-            allreduce_gradients(head_i, group)
-            allreduce_gradients(head_t, group)
+            allreduce_gradients(head_i, head_t, group=group)
         return loss
 
     def barrier():
@@ -438,6 +438,47 @@ def kernel_breakdown(torch, ops, dev, rows, cols, d):
     }
 
 
+def run_zeroshot(args):
+    """BASELINE config 4 (secondary line, not the headline): zero-shot prompt scoring of N image embeddings against 64
+    prompts, D = 512, fp32 -> argmax + top-5.  HBM-roofline: algorithmic bytes N*D*4 + C*D*4 + N*(8 + 5*12)."""
+    import torch
+    from mmgclip_b200 import _lib, ops
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n, c, d, k = args.zeroshot_rows, 64, 512, 5
+    gen = torch.Generator(device=dev).manual_seed(4)
+    sets = [torch.nn.functional.normalize(torch.randn(n, d, device=dev, generator=gen), dim=1) for _ in range(2)]
+    txt = torch.nn.functional.normalize(torch.randn(c, d, device=dev, generator=gen), dim=1)
+    s = torch.tensor(1 / 0.07, device=dev)
+    fn = lambda i: ops.zeroshot_score(sets[i % 2], txt, s, k=k, want_logits=False, want_probs=False)  # noqa: E731
+    for i in range(max(args.warmup, 3)):
+        fn(i)
+    torch.cuda.synchronize()
+    n0 = _lib.load().mmg_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peaks = measured_peaks()
+    alg_bytes = n * d * 4 + c * d * 4 + n * (8 + k * 12)
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "zero-shot prompt scoring rows/sec (1M x 64 prompts, D=512, fp32, argmax + top-5)",
+        "value": n / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"zero-shot scoring N={n} C={c} D={d} k={k}",
+                                         "l2": "two 2 GiB embedding sets alternate (larger than L2)"},
+        "gpu_launches": int(_lib.load().mmg_kernel_launch_count() - n0),
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "zeroshot_kernel"}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,7 +491,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-breakdown", action="store_true", default=True)
     ap.add_argument("--no-kernel-breakdown", dest="kernel_breakdown", action="store_false")
+    ap.add_argument("--workload", default="clip", choices=["clip", "zeroshot"],
+                    help="clip = the headline metric (default); zeroshot = BASELINE config 4 (secondary line)")
+    ap.add_argument("--zeroshot-rows", type=int, default=1 << 20)
     args = ap.parse_args()
+    if args.workload == "zeroshot":
+        return run_zeroshot(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

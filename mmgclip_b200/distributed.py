@@ -58,9 +58,36 @@ class _Kernels:
                                         a32=a32, b32=b32_paired, diag=diag)
 
 
+class GatheredColumns:
+    """Column-side embeddings being all-gathered in the background (see :func:`gather_columns_async`)."""
+
+    def __init__(self, local, b_all, work):
+        self.local, self.b_all, self.work = local, b_all, work
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()  # the current stream waits for the collective; no host sync
+            self.work = None
+        return self.b_all
+
+
+def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] = None, _kernels=None):
+    """Start the all-gather of the column-side embeddings now and let it run while the caller projects the other
+    modality; pass the result to :func:`sharded_info_nce` as ``gathered=``."""
+    kernels = _kernels or _Kernels
+    prec = ops._resolve(prec)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    world = dist.get_world_size(group)
+    b_op = kernels.operand(b_local, prec).contiguous()
+    b_all = torch.empty((b_op.shape[0] * world, b_op.shape[1]), dtype=b_op.dtype, device=b_op.device)
+    work = dist.all_gather_into_tensor(b_all, b_op, group=group, async_op=True)
+    return GatheredColumns(b_local, b_all, work)
+
+
 class _ShardedInfoNCEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a_local, b_local, scale, group, prec, kernels):
+    def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         bl, D = a_local.shape
@@ -69,9 +96,12 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         B = bl * world
         s = scale.detach().reshape(()).to(device=a_local.device, dtype=torch.float32).contiguous()
         a_op = kernels.operand(a_local, prec)
-        b_op = kernels.operand(b_local, prec)
-        b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
-        dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
+        if gathered is not None and gathered.local is b_local:
+            b_all = gathered.wait()
+        else:
+            b_op = kernels.operand(b_local, prec)
+            b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
+            dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
         off = rank * bl
         rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec)
         dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
@@ -98,11 +128,11 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
             dscale = (dls / s).reshape(ctx.scale_shape)
-        return dA, dB, dscale, None, None, None
+        return dA, dB, dscale, None, None, None, None
 
 
 def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, group=None, prec: Optional[str] = None,
-                     _kernels=_Kernels) -> torch.Tensor:
+                     _kernels=_Kernels, gathered: Optional[GatheredColumns] = None) -> torch.Tensor:
     """Global symmetric InfoNCE for a batch sharded by rows; every rank gets the same (global mean) loss and, on
     backward, the exact gradient of that global loss with respect to ITS rows (no 1/world rescaling is needed)."""
     prec = ops._resolve(prec)
@@ -110,14 +140,15 @@ def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, 
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_local.device)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return ops.info_nce(a_local, b_local, logit_scale, prec=prec)
-    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels)
+    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels, gathered)
 
 
-def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
-    """Sum parameter gradients across ranks: with the global loss above each rank's head gradient covers its own rows."""
+def allreduce_gradients(*modules: torch.nn.Module, group=None) -> None:
+    """Sum parameter gradients across ranks (one flat all-reduce for all given modules): with the global loss above each
+    rank's head gradient covers only its own rows."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])

@@ -67,7 +67,7 @@ def _worker(rank, world, port, out_dir):
     torch.manual_seed(rank)
     lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
     lin.bias.grad = torch.full_like(lin.bias, float(10 * (rank + 1)))
-    D.allreduce_gradients(lin)
+    D.allreduce_gradients(lin, group=None)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss.detach().numpy(), da=al.grad.numpy(), db=blt.grad.numpy(),
              ds=s.grad.numpy(), wg=lin.weight.grad.numpy(), bg=lin.bias.grad.numpy())
     dist.destroy_process_group()

@@ -254,3 +254,38 @@ def test_bf16_full_size_properties(mm):
         g[np.arange(48), idx] -= 2 * coef
         ref_da = g @ b.double().cpu().numpy()
         assert rel_err(dA.cpu().numpy()[idx], ref_da) < GRAD["bf16"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_multilinear_head_training_dropout(mm, prec):
+    """MultiLinearHead in train mode: Linear -> ReLU -> Dropout(p) per hidden layer (projection.py:54-61).  The keep
+    masks come from torch's CUDA generator, so re-seeding reproduces them for the oracle."""
+    P = mm.projection
+    torch.manual_seed(5)
+    head = P.MultiLinearHead(40, [48, 24], dropout=0.25, precision=prec).cuda().train()
+    x = torch.randn(64, 40, device="cuda")
+    torch.manual_seed(123)
+    y = head(x)
+    torch.manual_seed(123)
+    keep = torch.rand((64, 48), device="cuda") >= 0.25
+    w = [l.weight.detach().cpu() for l in head.layers]
+    b = [l.bias.detach().cpu() for l in head.layers]
+    ref = oc.torch_multi_linear_head(x.cpu(), w, b, keep_masks=[keep.cpu()], p=0.25)
+    assert rel_err(y.detach().cpu(), ref) < EMB[prec] * 5
+    frac_dropped = ((y.detach() != 0).float().mean().item())
+    assert frac_dropped > 0.5  # sanity: not everything was zeroed
+    # gradients flow only through kept, active units
+    wts = torch.randn(64, 24, device="cuda")
+    (y * wts).sum().backward()
+    ws = [t.clone().requires_grad_() for t in w]
+    bs = [t.clone().requires_grad_() for t in b]
+    yr = oc.torch_multi_linear_head(x.cpu(), ws, bs, keep_masks=[keep.cpu()], p=0.25)
+    (yr * wts.cpu()).sum().backward()
+    tol = 1e-5 if prec == "fp32" else 2e-5
+    for i, layer in enumerate(head.layers):
+        assert rel_err(layer.weight.grad.cpu(), ws[i].grad) < tol * 5
+        assert rel_err(layer.bias.grad.cpu(), bs[i].grad) < tol * 5
+    head.eval()
+    y_eval = head(x)
+    ref_eval = oc.torch_multi_linear_head(x.cpu(), w, b)
+    assert rel_err(y_eval.detach().cpu(), ref_eval) < EMB[prec] * 5
