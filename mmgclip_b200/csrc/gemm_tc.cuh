@@ -24,8 +24,9 @@ namespace mmg {
 constexpr int kBM = 128;        // UMMA M (rows per tile)
 constexpr int kBK = 64;         // K elements per pipeline stage (= one 128-byte swizzle span of bf16)
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit operands
-constexpr int kEpiWarps = 8;    // warps 4..11
-constexpr int kGemmThreads = 32 * (4 + kEpiWarps);
+// Epilogue warps come in groups of four (one per TMEM lane quarter); an epilogue declares kWarps = 8 or 16, i.e. each
+// warp owns 32 accumulator rows and BN/2 or BN/4 of the tile's columns.  More warps = more latency hiding for the
+// MUFU / TMEM-load bound InfoNCE epilogues; with 16 the register file is re-balanced with setmaxnreg.
 
 struct GemmProblem {
   int M, N, K;           // logical extents (ragged edges are zero-filled by TMA and masked in the epilogue)
@@ -44,7 +45,7 @@ struct GemmSmem {
   static constexpr int kBBytes = kBRows * kBK * 2;
   // operand ring: whatever is left of ~192 KB after the epilogue's output staging tile (TMA-store epilogues)
   static constexpr int kStages = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
-  static constexpr int kBarBytes = 5120;  // mbarriers + TMEM slot (first 512 B) and 8 x 512 B of per-warp epilogue scratch
+  static constexpr int kBarBytes = 9216;  // mbarriers + TMEM slot (first 512 B) and up to 16 x 512 B of per-warp scratch
   static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kBarBytes + 1024 /* alignment slack */;
 };
 
@@ -98,7 +99,7 @@ __device__ __forceinline__ TileCoord decode_virtual(int t, const GemmProblem& p0
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogues.  Every epilogue warp owns 32 accumulator rows (TMEM lanes 32q..32q+31, q = warp % 4, one row per
-// thread) and half of the tile's columns (h = (warp-4)/4), visited 32 columns at a time.
+// thread) and one column group (cg = (warp-4)/4) of BN / (kWarps/4) columns, visited 32 columns at a time.
 // ---------------------------------------------------------------------------------------------------------
 
 // C = alpha * acc (+ bias[col]) (ReLU) stored / accumulated / atomically added to fp32 row-major C.
@@ -113,8 +114,9 @@ struct EpiStoreF32 {
     int relu;
     int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
   };
+  static constexpr int kWarps = 8;
   // one [32 rows x 32 fp32] (4 KB, 128B-swizzled) staging box per epilogue warp
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kEpiWarps * 4096; }
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
   static __device__ __forceinline__ void finish(int, int lane) {
     if (lane == 0) tma_store_wait_all();
@@ -126,12 +128,13 @@ struct EpiStoreF32 {
   template <int BN>
   static __device__ __forceinline__ void run_tma(const Params& P, uint32_t tacc, int m0, int n0, int N, int half, int q,
                                                  int lane, const CUtensorMap* cmap, uint8_t* box) {
+    constexpr int kCols = BN / (kWarps / 4);
     const float alpha = P.alpha_ptr ? P.alpha * __ldg(P.alpha_ptr) : P.alpha;
     uint8_t* rowp = box + lane * 128;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 64; ++ch) {
-      const int cl = half * (BN / 2) + ch * 32;
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+      const int cl = half * kCols + ch * 32;
       const int c0 = n0 + cl;
       if (c0 >= N) break;  // warp-uniform
       float v[32];
@@ -169,14 +172,15 @@ struct EpiStoreF32 {
       run_tma<BN>(P, tacc, m0, n0, N, half, q, lane, cmap, staging + ewarp * 4096);
       return;
     }
+    constexpr int kCols = BN / (kWarps / 4);
     const int mode = force_atomic ? 2 : P.mode;
     const int row = m0 + q * 32 + lane;
     float* crow = P.C + static_cast<long long>(row) * P.ldc;
     const bool vec_ok = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
     const float alpha = P.alpha_ptr ? P.alpha * __ldg(P.alpha_ptr) : P.alpha;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 64; ++ch) {
-      const int cl = half * (BN / 2) + ch * 32;
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+      const int cl = half * kCols + ch * 32;
       const int c0 = n0 + cl;
       if (c0 >= N) break;  // warp-uniform
       float v[32];
@@ -248,19 +252,21 @@ struct EpiLse {
     const float* scale_ptr;   // device scalar s = exp(logit_scale)
     int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
   };
+  static constexpr int kWarps = 16;
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
   static __device__ __forceinline__ void finish(int, int) {}
 
   template <int BN, bool kMasked, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                               int q, int lane, float s, float sl2) {
+    constexpr int kCols = BN / (kWarps / 4);
     const int lr = lane >> 2;          // row within an 8-row group
     const int lc = (lane & 3) * 2;     // first of this thread's two columns within an 8-column group
     const int rbase = m0 + q * 32 + lr;  // rows rbase + 8*i, i = 0..3
     float racc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 64; ++ch) {
-      const int cl = half * (BN / 2) + ch * 32;
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+      const int cl = half * kCols + ch * 32;
       const int c0 = n0 + cl;
       if (kMasked && c0 >= N) break;  // warp-uniform
       float va[16], vb[16];
@@ -368,13 +374,15 @@ struct EpiGrad {
     float* dlogscale_acc;     // device scalar accumulator: sum g * cos
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
   };
+  static constexpr int kWarps = 16;
   // one [32 rows x 64 bf16] (4 KB, 128B-swizzled) staging box per epilogue warp
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kEpiWarps * 4096; }
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
   template <int BN, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                               int q, int lane, const float* cs, float sl2, const CUtensorMap* cmap,
                                               uint8_t* box) {
+    constexpr int kCols = BN / (kWarps / 4);
     const int row = m0 + q * 32 + lane;
     const int dcol = row + P.diag_offset;
     const float ri = (row < M) ? __ldg(P.rinv + row) : 0.f;
@@ -388,9 +396,9 @@ struct EpiGrad {
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     float dacc = 0.f;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 64; ++ch) {
+    for (int ch = 0; ch < kCols / 32; ++ch) {
       const int cw = ch * 32;                       // column inside this warp's half
-      const int cl = half * (BN / 2) + cw;          // column inside the tile
+      const int cl = half * kCols + cw;          // column inside the tile
       const int c0 = n0 + cl;
       if (c0 >= N) break;  // warp-uniform
       float v[32];
@@ -444,11 +452,12 @@ struct EpiGrad {
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
                                              uint8_t* staging, int force_atomic) {
     (void)force_atomic;
-    // this warp's private copy of the column terms of its BN/2 columns (zero beyond N); warp-synchronous, no barrier
+    constexpr int kCols = BN / (kWarps / 4);
+    // this warp's private copy of the column terms of its columns (zero beyond N); warp-synchronous, no barrier
     __syncwarp();
 #pragma unroll
-    for (int i = lane; i < BN / 2; i += 32) {
-      const int c = n0 + half * (BN / 2) + i;
+    for (int i = lane; i < kCols; i += 32) {
+      const int c = n0 + half * kCols + i;
       smem[i] = (c < N) ? __ldg(P.cinv + c) : 0.f;
     }
     __syncwarp();
@@ -469,7 +478,7 @@ struct EpiGrad {
 // The kernel
 // ---------------------------------------------------------------------------------------------------------
 template <int BN, class Epi, int kCG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(32 * (4 + Epi::kWarps), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
@@ -517,7 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps * kCG);
+      mbar_init(&tempty_bar[i], Epi::kWarps * kCG);
     }
     fence_barrier_init();
   }
@@ -531,10 +540,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+
   const int real_tiles = p0.num_tiles() + p1.num_tiles();
   const int total_tiles = tail.rem_split > 1 ? tail.full_tiles + (real_tiles - tail.full_tiles) * tail.rem_split
                                              : real_tiles;
 
+  // 16 epilogue warps: 640 threads only get 96 registers each at launch; the four non-epilogue warps (one warpgroup) give
+  // most of theirs back (setmaxnreg.dec) and the epilogue warpgroups take 112 (setmaxnreg.inc).
+  if (warp < 4) {
+  if (Epi::kWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
     // The warp stays converged; one elected lane arms the barrier and issues the bulk-tensor copies.
@@ -653,7 +667,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if (Epi::kWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===================== epilogue (both CTAs: 128 accumulator rows each) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's columns

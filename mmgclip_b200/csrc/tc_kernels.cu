@@ -163,7 +163,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(32 * (4 + Epi::kWarps));
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
