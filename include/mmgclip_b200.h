@@ -126,7 +126,7 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
  * dominant, heavily cancelling term).  b32, dB and cinv_paired point at the `rows` column-side entries paired with the
  * local rows (column diag_offset + r); diag is the forward's diag[] (the pair's logit):
  *   g = exp(diag[r] - s)*(rinv[r] + cinv_paired[r]) - dcoef
- *   dA[r,:] += g*b32[r,:],   dB[r,:] += g*a32[r,:],   dlogscale_acc += g * diag[r]/s. */
+ *   dA[r,:] += g*b32[r,:],   dB[r,:] += g*a32[r,:],   dlogscale_acc += g * diag[r]/s   (dlogscale_acc may be NULL). */
 int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                          const float* rinv, const float* cinv_paired, const float* scal, float* dA, float* dB,
                          float* dlogscale_acc, mmg_stream_t stream);
@@ -134,7 +134,8 @@ int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, co
 /* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
  *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - scal[0]*[c == r + diag_offset]    ( = s * dloss/dlogit; the
  *         matching-pair element is zeroed instead when scal[2] != 0, see mmg_infonce_bwd_diag )
- * dA, dB, dlogscale_acc are fp32 and must be zero-filled (or hold a running sum) by the caller.
+ * dA, dB, dlogscale_acc are fp32 and must be zero-filled (or hold a running sum) by the caller; dlogscale_acc may be
+ * NULL when d loss / d logit_scale is not wanted (the reference's logit_scale is not a Parameter on CUDA).
  * Works block by block (block_rows x block_cols, 0 = library default) through `workspace`. */
 int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                     const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA, float* dB,

@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p, POI
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmgclip_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# MMGCLIP_B200_LIB: load an alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("MMGCLIP_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
 MMG_PREC_FP32 = 0
 MMG_PREC_BF16 = 1

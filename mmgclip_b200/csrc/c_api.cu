@@ -323,7 +323,7 @@ int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, co
   MMG_REQ(scal);
   MMG_REQ(dA);
   MMG_REQ(dB);
-  MMG_REQ(dlogscale_acc);
+  if (dlogscale_acc != nullptr) MMG_REQ(dlogscale_acc);  // NULL: d/d logit_scale not wanted
   return simt_infonce_bwd_diag(a32, b32, rows, D, diag, scale, rinv, cinv_paired, scal, dA, dB, dlogscale_acc,
                                static_cast<cudaStream_t>(stream));
 }
@@ -338,7 +338,7 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   MMG_REQ(scal);
   MMG_REQ(dA);
   MMG_REQ(dB);
-  MMG_REQ(dlogscale_acc);
+  if (dlogscale_acc != nullptr) MMG_REQ(dlogscale_acc);  // NULL: d/d logit_scale not wanted (skips sum g*cos)
   MMG_REQ(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dflt = prec == MMG_PREC_BF16 ? kDefaultBlockBf16 : kDefaultBlockFp32;

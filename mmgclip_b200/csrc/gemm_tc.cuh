@@ -44,7 +44,11 @@ struct GemmSmem {
   static constexpr int kBRows = BN / kCG;
   static constexpr int kBBytes = kBRows * kBK * 2;
   // operand ring: whatever is left of ~192 KB after the epilogue's output staging tile (TMA-store epilogues)
-  static constexpr int kStages = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
+#ifndef MMG_MAX_STAGES
+#define MMG_MAX_STAGES 64  // A/B builds cap the ring depth (-DMMG_MAX_STAGES=n) to measure its effect
+#endif
+  static constexpr int kFit = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
+  static constexpr int kStages = kFit < MMG_MAX_STAGES ? kFit : MMG_MAX_STAGES;
   static constexpr int kBarBytes = 9216;  // mbarriers + TMEM slot (first 512 B) and up to 16 x 512 B of per-warp scratch
   static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kBarBytes + 1024 /* alignment slack */;
 };
@@ -118,7 +122,7 @@ struct EpiStoreF32 {
   // one [32 rows x 32 fp32] (4 KB, 128B-swizzled) staging box per epilogue warp
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
-  static __device__ __forceinline__ void finish(int, int lane) {
+  static __device__ __forceinline__ void finish(const Params&, float, int lane) {
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -166,8 +170,8 @@ struct EpiStoreF32 {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging, int force_atomic) {
-    (void)smem;
+                                             uint8_t* staging, int force_atomic, float& carry) {
+    (void)smem; (void)carry;
     if (P.use_tma) {
       run_tma<BN>(P, tacc, m0, n0, N, half, q, lane, cmap, staging + ewarp * 4096);
       return;
@@ -244,7 +248,8 @@ struct EpiStoreF32 {
 // accumulate in registers for the whole tile, column sums are pre-reduced over the thread's 4 rows and finished with a
 // 3-stage / 7-shuffle transposing butterfly.  Interior tiles take a mask-free path; the diagonal is looked at only in
 // tiles that contain it.
-struct EpiLse {
+template <int kW>
+struct EpiLseT {
   struct Params {
     float* rowsum;            // [M]   (atomic accumulate; zero-initialised by the caller)
     float* colsum;            // [N]
@@ -252,9 +257,9 @@ struct EpiLse {
     const float* scale_ptr;   // device scalar s = exp(logit_scale)
     int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
   };
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = kW;
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
-  static __device__ __forceinline__ void finish(int, int) {}
+  static __device__ __forceinline__ void finish(const Params&, float, int) {}
 
   template <int BN, bool kMasked, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
@@ -341,8 +346,8 @@ struct EpiLse {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging, int force_atomic) {
-    (void)ewarp; (void)smem; (void)cmap; (void)staging; (void)force_atomic;
+                                             uint8_t* staging, int force_atomic, float& carry) {
+    (void)ewarp; (void)smem; (void)cmap; (void)staging; (void)force_atomic; (void)carry;
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
@@ -365,24 +370,63 @@ struct EpiLse {
 // coefficients in its own 128B-swizzled staging box and ships it with a TMA bulk-tensor store -- full 128-byte lines,
 // no LSU traffic to global memory, no CTA-level barrier, ragged edges clipped by the hardware.  No masking of g is
 // needed: out-of-range operand rows are zero-filled, so cos = 0 there and g*cos contributes nothing.
-struct EpiGrad {
+template <int kW>
+struct EpiGradT {
   struct Params {
     const float* rinv;        // [M]
     const float* cinv;        // [N]
     const float* scale_ptr;   // device scalar s
     const float* scal;        // device scalars: [0] diagonal coefficient subtracted here, [2] != 0 -> zero the diagonal
-    float* dlogscale_acc;     // device scalar accumulator: sum g * cos
+    float* dlogscale_acc;     // device scalar accumulator: sum g * cos; NULL = not wanted (logit_scale is not trained)
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
+    int g_row_off;            // row offset of this block inside the coefficient scratch (fused backward: buffer * Rb)
+    int dbg;                  // measurement hook: bit 0 = skip the math (g = cos), bit 1 = skip staging + store
   };
-  static constexpr int kWarps = 16;
+  static constexpr int kWarps = kW;
   // one [32 rows x 64 bf16] (4 KB, 128B-swizzled) staging box per epilogue warp
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
-  template <int BN, bool kDiag>
+  // 32 accumulator columns of this thread's row -> coefficients, packed to bf16 into the row's slot of the staging box
+  template <bool kDiag, bool kDls>
+  static __device__ __forceinline__ void chunk(float (&v)[32], const float* cs, float ri, float sl2, int c0, int dcol,
+                                               float dcoef, bool zero_diag, float (&dacc)[2], uint8_t* rowp, uint32_t sw,
+                                               uint32_t cbase, int dbg) {
+    if (!(dbg & 1)) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + 4 * j4);  // broadcast LDS.128
+        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * j4 + jj;
+          const float cosv = v[j];
+          const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
+          float g = e * (ri + cv[jj]);
+          if (kDiag && c0 + j == dcol) g = zero_diag ? 0.f : g - dcoef;
+          if (kDls) dacc[jj & 1] = fmaf(g, cosv, dacc[jj & 1]);  // two independent chains
+          v[j] = g;
+        }
+      }
+    }
+    if (!(dbg & 2)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
+      }
+    }
+  }
+
+  template <int BN, bool kDiag, bool kDls>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                               int q, int lane, const float* cs, float sl2, const CUtensorMap* cmap,
-                                              uint8_t* box) {
+                                              uint8_t* box, float& carry) {
     constexpr int kCols = BN / (kWarps / 4);
+    constexpr int kChunks = kCols / 32;  // 2 (16 warps) or 4 (8 warps) at BN = 256
     const int row = m0 + q * 32 + lane;
     const int dcol = row + P.diag_offset;
     const float ri = (row < M) ? __ldg(P.rinv + row) : 0.f;
@@ -394,63 +438,37 @@ struct EpiGrad {
     }
     uint8_t* rowp = box + lane * 128;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    float dacc = 0.f;
+    const int cbeg = n0 + half * kCols;                       // first column of this warp
+    const int nch = min(kChunks, (N - cbeg + 31) / 32);       // chunks that hold real columns (warp-uniform)
+    const int dbg = P.dbg;
+    float dacc[2] = {0.f, 0.f};
+    float va[32];
 #pragma unroll 1
-    for (int ch = 0; ch < kCols / 32; ++ch) {
-      const int cw = ch * 32;                       // column inside this warp's half
-      const int cl = half * kCols + cw;          // column inside the tile
-      const int c0 = n0 + cl;
-      if (c0 >= N) break;  // warp-uniform
-      float v[32];
-      tmem_ld_32x32b_x32(tacc + cl, v);
+    for (int ch = 0; ch < nch; ++ch) {
+      tmem_ld_32x32b_x32(tacc + half * kCols + ch * 32, va);
       tmem_ld_wait();
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cs + cw + 4 * j4);  // broadcast LDS.128
-        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = 4 * j4 + jj;
-          const float cosv = v[j];
-          const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
-          float g = e * (ri + cv[jj]);
-          if (kDiag && c0 + j == dcol) g = zero_diag ? 0.f : g - dcoef;
-          dacc = fmaf(g, cosv, dacc);
-          v[j] = g;
-        }
-      }
-      // 32 columns = 64 bytes = four 16-byte chunks of this row; the box holds 64 columns (two chunks of work)
       if ((ch & 1) == 0) {
         if (lane == 0) tma_store_wait_read();  // this warp's previous box has left shared memory
         __syncwarp();
       }
-      const uint32_t cbase = static_cast<uint32_t>((ch & 1) * 4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
-      }
-      if ((ch & 1) == 1 || c0 + 32 >= N) {
+      chunk<kDiag, kDls>(va, cs + ch * 32, ri, sl2, cbeg + ch * 32, dcol, dcoef, zero_diag, dacc, rowp, sw,
+                         static_cast<uint32_t>((ch & 1) * 4), dbg);
+      if ((ch & 1) == 1 || ch + 1 == nch) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(cmap, box, c0 - (ch & 1) * 32, m0 + q * 32);
+          tma_store_2d(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32);
           tma_store_commit();
         }
       }
     }
-    dacc = warp_sum(dacc);
-    if (lane == 0 && dacc != 0.f) atomicAdd(P.dlogscale_acc, dacc);
+    if (kDls) carry += dacc[0] + dacc[1];  // per-thread partial; reduced and added once per warp in finish()
   }
 
   template <int BN>
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
-                                             uint8_t* staging, int force_atomic) {
+                                             uint8_t* staging, int force_atomic, float& carry) {
     (void)force_atomic;
     constexpr int kCols = BN / (kWarps / 4);
     // this warp's private copy of the column terms of its columns (zero beyond N); warp-synchronous, no barrier
@@ -464,12 +482,23 @@ struct EpiGrad {
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
+    const bool dls = P.dlogscale_acc != nullptr;
     uint8_t* box = staging + ewarp * 4096;
-    if (has_diag) tile<BN, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box);
-    else tile<BN, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box);
+    if (has_diag) {
+      if (dls) tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
+      else tile<BN, true, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
+    } else {
+      if (dls) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
+      else tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
+    }
   }
 
-  static __device__ __forceinline__ void finish(int, int lane) {
+  // sum g*cos: one atomic per warp per launch (not per tile: 10^5 same-address atomics per launch serialise at L2)
+  static __device__ __forceinline__ void finish(const Params& P, float carry, int lane) {
+    if (P.dlogscale_acc != nullptr) {
+      const float d = warp_sum(carry);
+      if (lane == 0 && d != 0.f) atomicAdd(P.dlogscale_acc, d);
+    }
     if (lane == 0) tma_store_wait_all();
   }
 };
@@ -490,7 +519,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int kTileM = kBM * kCG;       // rows of one (pair) tile
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would turn every access
+  // below into a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
   uint8_t* staging = sB + kStages * S::kBBytes;  // epilogue output tile (TMA-store epilogues), 1024-byte aligned
@@ -545,8 +576,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int total_tiles = tail.rem_split > 1 ? tail.full_tiles + (real_tiles - tail.full_tiles) * tail.rem_split
                                              : real_tiles;
 
-  // 16 epilogue warps: 640 threads only get 96 registers each at launch; the four non-epilogue warps (one warpgroup) give
-  // most of theirs back (setmaxnreg.dec) and the epilogue warpgroups take 112 (setmaxnreg.inc).
+  // 16 epilogue warps: 640 threads only get 96 registers each at launch.  The four non-epilogue warps (one warpgroup)
+  // release 128 x (96 - 56) = 5120 registers (setmaxnreg.dec) and the four epilogue warpgroups take 512 x (104 - 96) = 4096
+  // of them (setmaxnreg.inc blocks until the CTA's pool holds enough: asking for more than was released dead-locks).
   if (warp < 4) {
   if (Epi::kWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -669,11 +701,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
   } else {
-    if (Epi::kWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if (Epi::kWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== epilogue (both CTAs: 128 accumulator rows each) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's columns
     int it = 0;
+    float carry = 0.f;  // per-thread running value an epilogue may keep across tiles (EpiGrad: sum g*cos)
     for (int t = tile_first; t < total_tiles; t += tile_step, ++it) {
       const TileCoord tc = decode_virtual(t, p0, p1, tail);
       const GemmProblem& p = tc.prob ? p1 : p0;
@@ -685,7 +718,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (tc.kb_begin < tc.kb_end)
         Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
                               tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + (warp - 4) * 128,
-                              tc.prob ? &tmC1 : &tmC0, staging, tc.atomic);
+                              tc.prob ? &tmC1 : &tmC0, staging, tc.atomic, carry);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -693,7 +726,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
       }
     }
-    Epi::finish(warp - 4, lane);
+    Epi::finish(e0, carry, lane);
   }
 
   tcgen05_fence_before();

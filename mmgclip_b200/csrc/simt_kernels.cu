@@ -555,7 +555,7 @@ grad_block_kernel(float* __restrict__ S, long long lds, int rb, int cb, int row0
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += wsum[i];
-    if (t != 0.f) atomicAdd(dlogscale_acc, t);
+    if (t != 0.f && dlogscale_acc != nullptr) atomicAdd(dlogscale_acc, t);
   }
 }
 
@@ -731,7 +731,7 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += wsum[i];
-    atomicAdd(dlogscale_acc, t);
+    if (dlogscale_acc != nullptr) atomicAdd(dlogscale_acc, t);
   }
 }
 

@@ -117,6 +117,14 @@ static GemmProblem empty_problem() {
 
 static bool tail_balance_enabled();
 static int prefetch_distance();
+static bool dual_split_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMG_TC_DUAL_SPLIT");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower at 8192^2 blocks (1.84 vs 1.75 ms): opt-in
+  }
+  return v == 1;
+}
 
 template <int BN, class Epi, int kCG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1,
@@ -206,6 +214,17 @@ static int prefetch_distance() {
   }
   return v;
 }
+// Epilogue warps of the InfoNCE epilogues: 8 (default) or 16 (MMG_EPI_WARPS=16; both instantiations are built).
+// Measured on B200 at 32768^2 x 512 (tests/gpu_epi_probe.py): 8 warps 0.723 / 1.019 ms (forward / coefficient launches),
+// 16 warps 0.754 / 1.095 ms -- the deeper operand ring the smaller staging area leaves matters more than latency hiding.
+static int epi_warps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMG_EPI_WARPS");
+    v = (e != nullptr && atoi(e) == 16) ? 16 : 8;
+  }
+  return v;
+}
 struct TileCfg { int BN, cg; };
 static TileCfg pick_tile(int M, int N) {
   TileCfg c;
@@ -253,11 +272,29 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   if ((rc = make_operand_map(&mb0, B0, N0, K0, tcfg.BN / tcfg.cg)) != 0) return rc;
   if ((rc = make_operand_map(&ma1, A1, M1, K1, kBM)) != 0) return rc;
   if ((rc = make_operand_map(&mb1, B1, N1, K1, tcfg.BN / tcfg.cg)) != 0) return rc;
-  GemmProblem p0 = make_problem(M0, N0, K0, tcfg.BN, 1, A0.mn_major, B0.mn_major, tcfg.cg);
-  GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, 1, A1.mn_major, B1.mn_major, tcfg.cg);
   EpiStoreF32::Params e0, e1;
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e0.use_tma = out_tma_ok(C0, ldc0) && out_tma_ok(C1, ldc1);
+  // Wave quantisation: the two problems of one 8192 x 8192 block are 128 pair tiles on 74 CTA pairs = 2 rounds at 86%.
+  // With TMA reduce-add outputs (atomic at L2) every tile may be cut into K slices, so pick the split whose slice
+  // count fills whole rounds best (128 x 4 = 512 slices = 6.92 rounds of 7 -> 99%); slices stay >= 16 K-blocks long.
+  int ks = 1;
+  if (e0.use_tma && dual_split_enabled()) {
+    const int groups = sm_count() / tcfg.cg;
+    const int t0 = ((M0 + kBM * tcfg.cg - 1) / (kBM * tcfg.cg)) * ((N0 + tcfg.BN - 1) / tcfg.BN);
+    const int t1 = ((M1 + kBM * tcfg.cg - 1) / (kBM * tcfg.cg)) * ((N1 + tcfg.BN - 1) / tcfg.BN);
+    const int nkb = ((K0 < K1 ? K0 : K1) + kBK - 1) / kBK;
+    double best = 0.0;
+    for (int sdiv = 1; sdiv <= 8; ++sdiv) {
+      if (sdiv > 1 && nkb / sdiv < 16) break;
+      const int total = (t0 + t1) * sdiv;
+      const int rounds = (total + groups - 1) / groups;
+      const double eff = (double)total / ((double)rounds * groups) - 0.004 * (sdiv - 1);  // slight bias to fewer slices
+      if (eff > best + 1e-9) { best = eff; ks = sdiv; }
+    }
+  }
+  GemmProblem p0 = make_problem(M0, N0, K0, tcfg.BN, ks, A0.mn_major, B0.mn_major, tcfg.cg);
+  GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, ks, A1.mn_major, B1.mn_major, tcfg.cg);
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
   CUtensorMap mc0 = ma0, mc1 = ma0;
@@ -278,9 +315,14 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
   if ((rc = make_operand_map(&mb, B, cols, D, tcfg.BN / tcfg.cg)) != 0) return rc;
   GemmProblem p0 = make_problem(rows, cols, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
-  EpiLse::Params e;
+  if (epi_warps() == 8) {
+    EpiLseT<8>::Params e;
+    e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
+    MMG_DISPATCH(EpiLseT<8>, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
+  }
+  EpiLseT<16>::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
-  MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiLseT<16>, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
@@ -297,10 +339,18 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   // output map: g block [rb, cb] bf16 (pitch ldg), box = 32 rows x 64 columns (one epilogue warp's block)
   CUtensorMap mc;
   if ((rc = make_tmap(&mc, G, cb, rb, ldg, 32)) != 0) return rc;
-  EpiGrad::Params e;
+  int dbg = 0;  // measurement hook (tests/gpu_epi_probe.py): results are wrong when set
+  if (const char* d = getenv("MMG_EPI_DBG")) dbg = atoi(d);
+  if (epi_warps() == 8) {
+    EpiGradT<8>::Params e;
+    e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
+    e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
+    MMG_DISPATCH(EpiGradT<8>, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
+  }
+  EpiGradT<16>::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
-  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset;
-  MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
+  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
+  MMG_DISPATCH(EpiGradT<16>, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
 }
 
 }  // namespace mmg

@@ -53,9 +53,9 @@ class _Kernels:
 
     @staticmethod
     def backward(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec, a32, b32_paired,
-                 diag):
+                 diag, need_dscale=True):
         return ops.infonce_backward_raw(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec,
-                                        a32=a32, b32=b32_paired, diag=diag)
+                                        a32=a32, b32=b32_paired, diag=diag, need_dscale=need_dscale)
 
 
 class GatheredColumns:
@@ -121,7 +121,7 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if not (prec == "bf16" and a32.dtype == torch.float32):
             a32 = b32_local = None
         dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
-                                           b32_local, diag)
+                                           b32_local, diag, need_dscale=ctx.needs_input_grad[2])
         dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)
         _reduce_scatter_sum(dB, dB_all, group)
         dscale = None

@@ -255,8 +255,12 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
 
 
 def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, prec: str,
-                         block_rows: int = 0, block_cols: int = 0, a32=None, b32=None, diag=None):
+                         block_rows: int = 0, block_cols: int = 0, a32=None, b32=None, diag=None,
+                         need_dscale: bool = True):
     """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header.
+
+    ``need_dscale=False`` (the scale carries no gradient -- the reference's CUDA behaviour) skips the
+    ``sum g*cos`` accumulation in the epilogue and returns ``None`` for it.
 
     When the fp32 embeddings (a32 [rows,D]; b32 [rows,D] = the column-side rows paired with the local rows) are supplied
     to the bf16 path, the matching-pair term of the
@@ -274,7 +278,7 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
                                    int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
     dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
-    dls = torch.zeros((), dtype=torch.float32, device=dev)
+    dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
     block_rows = block_rows or int(os.environ.get("MMGCLIP_B200_BLOCK_ROWS", "0"))
     block_cols = block_cols or int(os.environ.get("MMGCLIP_B200_BLOCK_COLS", "0"))
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
@@ -497,7 +501,7 @@ class _InfoNCEFn(torch.autograd.Function):
             a32 = b32 = diag = None
         n = a_op.shape[0]
         dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec,
-                                           a32=a32, b32=b32, diag=diag)
+                                           a32=a32, b32=b32, diag=diag, need_dscale=ctx.needs_input_grad[2])
         dscale = None
         if ctx.needs_input_grad[2]:
             dscale = (dls / s).reshape(ctx.scale_shape)  # d loss / d s ; sum g*cos = s * dloss/ds

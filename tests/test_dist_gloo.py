@@ -35,7 +35,7 @@ class NumpyKernels:
         return (inv_two_b * (torch.log(rowsum) + torch.log(colsum_slice) + 2 * sv - 2 * diag).sum()).reshape(())
 
     @staticmethod
-    def backward(a, b_all, s, rowsum, colsum, grad_loss, inv_two_b, off, prec, a32, b32, diag):
+    def backward(a, b_all, s, rowsum, colsum, grad_loss, inv_two_b, off, prec, a32, b32, diag, need_dscale=True):
         sv, gl = float(s), float(grad_loss)
         cos = a.numpy() @ b_all.numpy().T
         e = np.exp(sv * cos - sv)
