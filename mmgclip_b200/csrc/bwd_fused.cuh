@@ -1,0 +1,383 @@
+// mmgclip_b200 -- the whole InfoNCE backward as ONE persistent launch.
+//
+// The block-by-block backward (c_api.cu: one coefficient launch + one gradient-GEMM launch per logit block) pays a
+// launch / pipeline-fill / wave-quantisation cost per launch (measured ~6-10 us x 32 launches at B = 32768) and sends
+// the coefficient block g through HBM.  This kernel keeps the same three contractions per block
+//
+//     (A)  g[Rb x Cb]   = EpiGrad( a[rows of the block] . b[cols of the block]^T )        K = D      -> bf16 scratch
+//     (I)  dA[rows]    += g . b[cols]                                                     K = Cb     (slices of kslI x 64)
+//     (T)  dB[cols]    += g^T . a[rows]                                                   K = Rb     (slices of kslT x 64)
+//
+// but runs them as a stream of work items over a persistent grid (one CTA pair per two SMs, the tcgen05 mainloop of
+// gemm_tc.cuh).  Items of different blocks overlap: the coefficient tiles of block s are interleaved with the gradient
+// slices of block s-2, so the MUFU-heavy coefficient epilogues hide behind the long-K gradient MMAs, the small
+// coefficient blocks (nbuf x Rb x Cb bf16, default 4 x 16 MiB) stay in L2, and there is one prologue and one tail.
+//
+// Ordering.  Every item has a key (group, position); item lists are merged by key.  Coefficient tiles of block s have
+// group s, gradient slices of block s have group s + 2.  CTA pair p owns the coefficient tiles with index = p mod P
+// and the gradient slices with index = p mod P and walks them in key order; all three roles of a CTA (TMA producer,
+// MMA issuer, epilogue warps) enumerate the same list independently.  Dependencies go through two global counters per
+// block:
+//     doneA[s] : (CTA, coefficient tile) pairs of block s whose stores are complete   (gradient loads of s wait for all)
+//     doneB[s] : gradient slices of block s whose MMAs have completed               (block s + nbuf may then overwrite
+//                                                                                    the scratch buffer)
+// An item only ever waits for items with a strictly smaller key and every pair processes its items in key order, so the
+// unfinished item with the smallest key can always run: no dead-lock as long as all CTAs are resident (grid <= #SMs).
+#pragma once
+
+#include "gemm_tc.cuh"
+
+namespace mmg {
+
+struct BwdFusedParams {
+  int rows, cols, D;   // local rows, all columns, embedding width
+  int Rb, Cb;          // block shape (multiples of 256 that divide rows / cols)
+  int nbc, nblk;       // column blocks per block row; blocks in total (row-major over the block grid)
+  int nbuf;            // coefficient scratch buffers
+  int tAm, tAn, tDn;   // Rb/256, Cb/256, D/256
+  int kslI, kslT;      // 64-wide K blocks per dA slice / per dB slice
+  int sI, sT;          // slices per dA tile (Cb/64/kslI) / per dB tile (Rb/64/kslT)
+  int nA, nBI, nB;     // items per block: coefficient tiles; dA slices; all gradient slices
+  int diag_offset;     // global column paired with local row 0
+  const float* rinv;
+  const float* cinv;
+  const float* scale;
+  const float* scal;
+  float* dlogscale_acc;
+  unsigned int* doneA;  // [nblk], zeroed by the host before the launch
+  unsigned int* doneB;  // [nblk]
+};
+
+struct BwdItem {
+  int type;      // 0 coefficient tile, 1 dA slice, 2 dB slice
+  int blk;
+  int tm, tn;
+  int kb0, nkb;
+};
+
+// Merged, key-ordered walk over the items one CTA pair owns.
+struct BwdCursor {
+  int a, b, na_total, nb_total, step;
+  __device__ __forceinline__ void init(const BwdFusedParams& p, int pair, int pairs) {
+    a = pair; b = pair; step = pairs;
+    na_total = p.nblk * p.nA;
+    nb_total = p.nblk * p.nB;
+  }
+  __device__ __forceinline__ bool next(const BwdFusedParams& p, BwdItem& it) {
+    const bool have_a = a < na_total, have_b = b < nb_total;
+    if (!have_a && !have_b) return false;
+    bool take_a;
+    if (!have_b) take_a = true;
+    else if (!have_a) take_a = false;
+    else {
+      const int sa = a / p.nA, ja = a - sa * p.nA;
+      const int sb = b / p.nB, jb = b - sb * p.nB;
+      const int ga = sa, gb = sb + 2;
+      take_a = (ga != gb) ? (ga < gb) : ((2 * ja + 1) * p.nB <= (2 * jb + 1) * p.nA);
+    }
+    if (take_a) {
+      it.type = 0;
+      it.blk = a / p.nA;
+      const int j = a - it.blk * p.nA;
+      it.tm = j / p.tAn;
+      it.tn = j - it.tm * p.tAn;
+      it.kb0 = 0;
+      it.nkb = p.D / kBK;
+      a += step;
+    } else {
+      it.blk = b / p.nB;
+      int j = b - it.blk * p.nB;
+      int spt, ksl;  // slices per tile, K blocks per slice
+      if (j < p.nBI) { it.type = 1; spt = p.sI; ksl = p.kslI; }
+      else { it.type = 2; j -= p.nBI; spt = p.sT; ksl = p.kslT; }
+      const int tile = j / spt;
+      const int q = j - tile * spt;
+      it.tm = tile / p.tDn;
+      it.tn = tile - it.tm * p.tDn;
+      it.kb0 = q * ksl;
+      it.nkb = ksl;
+      b += step;
+    }
+    return true;
+  }
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned int atom_acq_rel_cta_add(unsigned int* smem_ctr, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(smem_ctr)), "r"(v) : "memory");
+  return old;
+}
+
+// A coefficient tile is published (doneA) once per CTA: every epilogue warp waits for its own bulk stores, then bumps a
+// shared-memory counter; whoever arrives last (acq_rel at CTA scope chains the others' completed stores in) pays for the
+// one gpu-scope release.  Nobody waits for anybody.  Four slots: warps are never more than two tiles apart (two TMEM
+// accumulator stages), so a slot is never reused before all eight arrivals of its previous use.
+__device__ __forceinline__ void publish_tile(unsigned int* pub_cnt, unsigned int seq, unsigned int* done_ctr, int lane) {
+  if (lane == 0) {
+    tma_store_wait_all();
+    const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 3u), 1u);
+    if ((old & 7u) == 7u) {
+      fence_proxy_async_all();
+      red_release_gpu_add(done_ctr, 1u);
+    }
+  }
+  __syncwarp();
+}
+
+// one lane spins until *ctr >= want (with the same hang guard as mbar_wait), then the warp re-converges
+__device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned int want, int lane) {
+  if (lane == 0) {
+    if (ld_acquire_gpu(ctr) < want) {
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(ctr) < want) {
+        __nanosleep(64);
+        if (clock64() - t0 > MMG_HANG_GUARD_CYCLES) {
+          printf("[mmgclip_b200] fused backward: counter wait timed out (block %d thread %d want %u have %u)\n",
+                 (int)blockIdx.x, (int)threadIdx.x, want, ld_acquire_gpu(ctr));
+          __trap();
+        }
+      }
+    }
+    fence_proxy_async_all();  // the acquired data is touched next by TMA (async proxy)
+  }
+  __syncwarp();
+}
+
+constexpr int kFusedBN = 256;
+using FusedGrad = EpiGradT<8>;
+using FusedSmem = GemmSmem<kFusedBN, 2, 8 * 4096, FusedGrad::kScratchBytes>;
+constexpr int kFusedThreads = 32 * (4 + 8);
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
+                         const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
+                         const __grid_constant__ CUtensorMap mGk, const __grid_constant__ CUtensorMap mGmn,
+                         const __grid_constant__ CUtensorMap mGst, const __grid_constant__ CUtensorMap mdA,
+                         const __grid_constant__ CUtensorMap mdB, const BwdFusedParams p) {
+  using S = FusedSmem;
+  constexpr int kStages = S::kStages;
+  constexpr int BN = kFusedBN;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("[mmgclip_b200] dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* smem = smem_raw;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * S::kABytes;
+  uint8_t* staging = sB + kStages * S::kBBytes;
+  float* epi_scratch = reinterpret_cast<float*>(staging + 8 * 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 8 * 4096 + S::kScratch);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  unsigned int* pub_cnt = reinterpret_cast<unsigned int*>(bars) + 96;  // [4] arrival counters of the publish slots
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int pairs = gridDim.x >> 1;
+
+  cluster_sync_all();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mAk); tma_prefetch_desc(&mBk); tma_prefetch_desc(&mAmn); tma_prefetch_desc(&mBmn);
+    tma_prefetch_desc(&mGk); tma_prefetch_desc(&mGmn);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8 * 2);
+    }
+    for (int i = 0; i < 4; ++i) pub_cnt[i] = 0u;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg2(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  BwdCursor cur;
+  cur.init(p, pair, pairs);
+  BwdItem it;
+  const unsigned int wantA = static_cast<unsigned int>(p.nA) * 2u;  // one arrival per CTA per coefficient tile
+  const unsigned int wantB = static_cast<unsigned int>(p.nB);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
+    while (cur.next(p, it)) {
+      const int rb = it.blk / p.nbc, cb = it.blk - rb * p.nbc;
+      const int buf = it.blk % p.nbuf;
+      if (it.type != 0 && it.blk > verified) {
+        wait_counter(p.doneA + it.blk, wantA, lane);
+        verified = it.blk;
+      }
+      const int half_off = static_cast<int>(cta_rank) * kBM;
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (S::kABytes + S::kBBytes));
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          uint8_t* a_dst = sA + stage * S::kABytes;
+          uint8_t* b_dst = sB + stage * S::kBBytes;
+          const int k0 = (it.kb0 + kb) * kBK;
+          if (it.type == 0) {
+            tma_load_2d_cg2(&mAk, &full_bar[stage], a_dst, k0, rb * p.Rb + it.tm * 256 + half_off, kEvictNormal);
+            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, cb * p.Cb + it.tn * 256 + half_off, kEvictNormal);
+          } else if (it.type == 1) {
+            // dA[rows] += g . b[cols]:  A = g (K-major, K = block columns),  B = b (MN-major: [K = column index][N = D])
+            tma_load_2d_cg2(&mGk, &full_bar[stage], a_dst, k0, buf * p.Rb + it.tm * 256 + half_off, kEvictNormal);
+            const int n0 = it.tn * 256 + half_off;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              tma_load_2d_cg2(&mBmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, cb * p.Cb + k0, kEvictNormal);
+          } else {
+            // dB[cols] += g^T . a[rows]:  A = g (MN-major: [K = block row][M = block column]),  B = a (MN-major)
+            const int m0 = it.tm * 256 + half_off;
+            const int n0 = it.tn * 256 + half_off;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              tma_load_2d_cg2(&mGmn, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, buf * p.Rb + k0, kEvictNormal);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              tma_load_2d_cg2(&mAmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, rb * p.Rb + k0, kEvictNormal);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int n = 0;
+      while (cur.next(p, it)) {
+        const int acc_stage = n & 1;
+        const uint32_t acc_phase = (n >> 1) & 1;
+        ++n;
+        mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t a_mn = it.type == 2 ? 1u : 0u, b_mn = it.type != 0 ? 1u : 0u;
+        const uint32_t idesc = make_idesc_bf16(256, BN, a_mn, b_mn);
+        const uint32_t tmem_d = tmem_base + acc_stage * BN;
+        const uint32_t a_lbo = a_mn ? kBK * 128 : 0, b_lbo = b_mn ? kBK * 128 : 0;
+        const uint32_t a_kstep = a_mn ? kUmmaK * 128 : kUmmaK * 2;
+        const uint32_t b_kstep = b_mn ? kUmmaK * 128 : kUmmaK * 2;
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
+            const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+              const uint64_t db = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+              umma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_cg2(&empty_bar[stage]);
+            if (kb == it.nkb - 1) umma_commit_cg2(&tfull_bar[acc_stage]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (n > 0) {
+        const int last = n - 1;
+        mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);  // the peer's remote arrivals have landed
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int ewarp = warp - 4;
+    int n = 0;
+    float carry = 0.f;
+    int pending = -1;     // block whose coefficient-tile stores of this warp are not yet published in doneA
+    unsigned int a_seq = 0;  // coefficient tiles this warp has finished (identical across the CTA's epilogue warps)
+    int verified = -1;    // scratch buffers of blocks [0, verified + nbuf] are known to be free
+    FusedGrad::Params gp;
+    gp.scale_ptr = p.scale; gp.scal = p.scal; gp.dlogscale_acc = p.dlogscale_acc; gp.dbg = 0;
+    EpiStoreF32::Params sp;
+    sp.C = nullptr; sp.ldc = 0; sp.bias = nullptr; sp.alpha = 1.f; sp.alpha_ptr = nullptr; sp.mode = 1; sp.relu = 0;
+    sp.use_tma = 1;
+    while (cur.next(p, it)) {
+      if (pending >= 0) {
+        // publish the previous coefficient tile (deferred to here so the stores' latency is off the critical path, and
+        // done BEFORE blocking on the next accumulator so it never depends on this item's progress)
+        publish_tile(pub_cnt, a_seq++, p.doneA + pending, lane);
+        pending = -1;
+      }
+      const int acc_stage = n & 1;
+      const uint32_t acc_phase = (n >> 1) & 1;
+      ++n;
+      const int rb = it.blk / p.nbc, cb = it.blk - rb * p.nbc;
+      const int buf = it.blk % p.nbuf;
+      mbar_wait(&tfull_bar[acc_stage], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
+      const int half_off = static_cast<int>(cta_rank) * kBM;
+      if (it.type == 0) {
+        if (it.blk >= p.nbuf && it.blk - p.nbuf > verified) {
+          wait_counter(p.doneB + (it.blk - p.nbuf), wantB, lane);  // the buffer's previous block has been consumed
+          verified = it.blk - p.nbuf;
+        }
+        gp.rinv = p.rinv + rb * p.Rb;
+        gp.cinv = p.cinv + cb * p.Cb;
+        gp.diag_offset = rb * p.Rb + p.diag_offset - cb * p.Cb;
+        gp.g_row_off = buf * p.Rb;
+        FusedGrad::run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * 256, p.Rb, p.Cb, half, q, lane, ewarp,
+                           epi_scratch + acc_stage * BN + half * (BN / 2), &mGst, staging, 0, carry);
+        pending = it.blk;
+      } else {
+        // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
+        if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
+        const int m0 = (it.type == 1 ? rb * p.Rb : cb * p.Cb) + it.tm * 256 + half_off;
+        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * 256, p.D, half, q, lane, it.type == 1 ? &mdA : &mdB,
+                                 staging + ewarp * 4096);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[acc_stage]);
+        else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
+      }
+    }
+    if (pending >= 0) publish_tile(pub_cnt, a_seq++, p.doneA + pending, lane);
+    FusedGrad::finish(gp, carry, lane);
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace mmg

@@ -228,7 +228,9 @@ size_t mmg_infonce_workspace_bytes(int prec, int rows, int cols, int D) {
   if (prec == MMG_PREC_BF16) {
     const long long rb = rows < kDefaultBlockBf16 ? rows : kDefaultBlockBf16;
     const long long cb = round_up(cols < kDefaultBlockBf16 ? cols : kDefaultBlockBf16, 64);
-    return (size_t)(rb * cb * 2 + 256);
+    const size_t loop = (size_t)(rb * cb * 2 + 256);
+    const size_t fused = tc_infonce_bwd_fused_workspace(rows, cols, D);
+    return loop > fused ? loop : fused;
   }
   const long long rb = rows < kDefaultBlockFp32 ? rows : kDefaultBlockFp32;
   const long long cb = round_up(cols < kDefaultBlockFp32 ? cols : kDefaultBlockFp32, 4);
@@ -359,6 +361,15 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   int phases = 3;
   if (const char* e = getenv("MMG_BWD_PHASES")) phases = atoi(e);
   if (phases < 1 || phases > 3) phases = 3;
+
+  // One persistent launch for the whole backward when the shape allows it (bwd_fused.cuh); explicit block shapes and
+  // the phase hook select the block loop below.
+  if (prec == MMG_PREC_BF16 && phases == 3 && block_rows <= 0 && block_cols <= 0) {
+    int used = 0;
+    MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, dB,
+                                 dlogscale_acc, workspace, workspace_bytes, st, &used));
+    if (used) return 0;
+  }
 
   for (int r0 = 0; r0 < rows; r0 += Rb) {
     const int rb = rows - r0 < Rb ? rows - r0 : Rb;

@@ -38,19 +38,24 @@ struct GemmProblem {
 
 // kCG = 1: one CTA owns a 128 x BN tile.  kCG = 2: a CTA pair (cta_group::2) owns a 256 x BN tile -- each CTA stages
 // its own 128 A rows and HALF of the B rows, which halves the B-operand shared-memory / L2 traffic per FLOP.
-template <int BN, int kCG, int kStagingBytes = 0>
+template <int BN, int kCG, int kStagingBytes = 0, int kScratchBytes = 0>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBRows = BN / kCG;
   static constexpr int kBBytes = kBRows * kBK * 2;
-  // operand ring: whatever is left of ~192 KB after the epilogue's output staging tile (TMA-store epilogues)
+  // operand ring: whatever is left of the 227 KB a CTA may use after the epilogue's output staging boxes (TMA-store
+  // epilogues), the barriers and the alignment slack -- 7 stages of 32 KB without staging, 6 with 32 KB of boxes
 #ifndef MMG_MAX_STAGES
 #define MMG_MAX_STAGES 64  // A/B builds cap the ring depth (-DMMG_MAX_STAGES=n) to measure its effect
 #endif
-  static constexpr int kFit = (192 * 1024 - kStagingBytes) / (kABytes + kBBytes);
+  // The dynamic shared-memory window is declared 1024-byte aligned (the kernels trap if it is not), so there is no
+  // alignment slack: 6 x 32 KB + 32 KB of boxes + 2 KB of scratch + 512 B of barriers = 226.5 KB.
+  static constexpr int kSmemMax = 227 * 1024;
+  static constexpr int kBarBytes = 512;   // mbarriers + TMEM slot
+  static constexpr int kFit = (kSmemMax - kBarBytes - kStagingBytes - kScratchBytes) / (kABytes + kBBytes);
   static constexpr int kStages = kFit < MMG_MAX_STAGES ? kFit : MMG_MAX_STAGES;
-  static constexpr int kBarBytes = 9216;  // mbarriers + TMEM slot (first 512 B) and up to 16 x 512 B of per-warp scratch
-  static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kBarBytes + 1024 /* alignment slack */;
+  static constexpr int kScratch = kScratchBytes;
+  static constexpr int kTotal = kStages * (kABytes + kBBytes) + kStagingBytes + kScratchBytes + kBarBytes;
 };
 
 struct TileCoord {
@@ -119,6 +124,7 @@ struct EpiStoreF32 {
     int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
   };
   static constexpr int kWarps = 8;
+  static constexpr int kScratchBytes = 0;
   // one [32 rows x 32 fp32] (4 KB, 128B-swizzled) staging box per epilogue warp
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
@@ -259,6 +265,7 @@ struct EpiLseT {
   };
   static constexpr int kWarps = kW;
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
+  static constexpr int kScratchBytes = 0;
   static __device__ __forceinline__ void finish(const Params&, float, int) {}
 
   template <int BN, bool kMasked, bool kDiag>
@@ -383,18 +390,21 @@ struct EpiGradT {
     int dbg;                  // measurement hook: bit 0 = skip the math (g = cos), bit 1 = skip staging + store
   };
   static constexpr int kWarps = kW;
+  // column terms of a tile's columns, one copy per accumulator stage: 2 x 256 floats
+  static constexpr int kScratchBytes = 2048;
   // one [32 rows x 64 bf16] (4 KB, 128B-swizzled) staging box per epilogue warp
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
 
   // 32 accumulator columns of this thread's row -> coefficients, packed to bf16 into the row's slot of the staging box
-  template <bool kDiag, bool kDls>
+  // (cs: the column terms of these 32 columns in shared memory -- broadcast LDS.128)
+  template <bool kDiag>
   static __device__ __forceinline__ void chunk(float (&v)[32], const float* cs, float ri, float sl2, int c0, int dcol,
-                                               float dcoef, bool zero_diag, float (&dacc)[2], uint8_t* rowp, uint32_t sw,
-                                               uint32_t cbase, int dbg) {
+                                               float dcoef, bool zero_diag, bool dls, float (&dacc)[2], uint8_t* rowp,
+                                               uint32_t sw, uint32_t cbase, int dbg) {
     if (!(dbg & 1)) {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cs + 4 * j4);  // broadcast LDS.128
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + 4 * j4);
         const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -403,7 +413,7 @@ struct EpiGradT {
           const float e = ex2_approx(fmaf(cosv, sl2, -sl2));
           float g = e * (ri + cv[jj]);
           if (kDiag && c0 + j == dcol) g = zero_diag ? 0.f : g - dcoef;
-          if (kDls) dacc[jj & 1] = fmaf(g, cosv, dacc[jj & 1]);  // two independent chains
+          if (dls) dacc[jj & 1] = fmaf(g, cosv, dacc[jj & 1]);  // two independent chains (warp-uniform predicate)
           v[j] = g;
         }
       }
@@ -421,12 +431,16 @@ struct EpiGradT {
     }
   }
 
-  template <int BN, bool kDiag, bool kDls>
+  // One thread = one accumulator row, 32 columns at a time.  (Two variants were measured slower at 32768^2 x 512 and are
+  // not kept: column terms read from global memory instead of shared memory, 1.23 vs 1.02 ms for the coefficient
+  // launches; 16-column TMEM loads issued one step ahead, 1.28 ms.)
+  template <int BN, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                               int q, int lane, const float* cs, float sl2, const CUtensorMap* cmap,
                                               uint8_t* box, float& carry) {
     constexpr int kCols = BN / (kWarps / 4);
-    constexpr int kChunks = kCols / 32;  // 2 (16 warps) or 4 (8 warps) at BN = 256
+    constexpr int kChunks = kCols / 32;
+    const bool dls = P.dlogscale_acc != nullptr;
     const int row = m0 + q * 32 + lane;
     const int dcol = row + P.diag_offset;
     const float ri = (row < M) ? __ldg(P.rinv + row) : 0.f;
@@ -451,18 +465,21 @@ struct EpiGradT {
         if (lane == 0) tma_store_wait_read();  // this warp's previous box has left shared memory
         __syncwarp();
       }
-      chunk<kDiag, kDls>(va, cs + ch * 32, ri, sl2, cbeg + ch * 32, dcol, dcoef, zero_diag, dacc, rowp, sw,
-                         static_cast<uint32_t>((ch & 1) * 4), dbg);
+      chunk<kDiag>(va, cs + ch * 32, ri, sl2, cbeg + ch * 32, dcol, dcoef, zero_diag, dls, dacc, rowp, sw,
+                   static_cast<uint32_t>((ch & 1) * 4), dbg);
       if ((ch & 1) == 1 || ch + 1 == nch) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32);
-          tma_store_commit();
+        if (!(dbg & 2)) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // columns beyond N are clipped by the hardware
+            tma_store_2d(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32);
+            tma_store_commit();
+          }
         }
       }
     }
-    if (kDls) carry += dacc[0] + dacc[1];  // per-thread partial; reduced and added once per warp in finish()
+    if (dls) carry += dacc[0] + dacc[1];  // per-thread partial; reduced and added once per warp in finish()
   }
 
   template <int BN>
@@ -471,7 +488,10 @@ struct EpiGradT {
                                              uint8_t* staging, int force_atomic, float& carry) {
     (void)force_atomic;
     constexpr int kCols = BN / (kWarps / 4);
-    // this warp's private copy of the column terms of its columns (zero beyond N); warp-synchronous, no barrier
+    // Column terms of this warp's columns (zero beyond N) in shared memory.  `smem` is shared by the four warps that
+    // work on the same columns of the same tile: each writes all the values it will read (identical values, so the
+    // overlap is benign) and only synchronises with itself; the caller alternates two copies by accumulator stage, and
+    // a warp cannot be two tiles ahead of another (the MMA of tile t+2 needs every warp's release of tile t).
     __syncwarp();
 #pragma unroll
     for (int i = lane; i < kCols; i += 32) {
@@ -482,15 +502,9 @@ struct EpiGradT {
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
-    const bool dls = P.dlogscale_acc != nullptr;
     uint8_t* box = staging + ewarp * 4096;
-    if (has_diag) {
-      if (dls) tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
-      else tile<BN, true, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
-    } else {
-      if (dls) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
-      else tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
-    }
+    if (has_diag) tile<BN, true>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
+    else tile<BN, false>(P, tacc, m0, n0, M, N, half, q, lane, smem, sl2, cmap, box, carry);
   }
 
   // sum g*cos: one atomic per warp per launch (not per tile: 10^5 same-address atomics per launch serialise at L2)
@@ -513,26 +527,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
                const GemmProblem p0, const GemmProblem p1, const TailSplit tail, const typename Epi::Params e0,
                const typename Epi::Params e1) {
-  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
+  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>(), Epi::kScratchBytes>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: a power of two >= 32
   constexpr int kTileM = kBM * kCG;       // rows of one (pair) tile
 
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would turn every access
-  // below into a generic LD/ST instead of LDS/STS)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // Pointers are derived from the __shared__ array by pointer arithmetic only (an integer round trip would turn every
+  // access below into a generic LD/ST instead of LDS/STS).  128B-swizzled TMA boxes need 1024-byte alignment.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("[mmgclip_b200] dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* smem = smem_raw;
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
   uint8_t* staging = sB + kStages * S::kBBytes;  // epilogue output tile (TMA-store epilogues), 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Epi::template staging_bytes<BN>());
+  float* epi_scratch = reinterpret_cast<float*>(staging + Epi::template staging_bytes<BN>());
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Epi::template staging_bytes<BN>() + Epi::kScratchBytes);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's copy is the live one)
   uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA          (multicast to both CTAs)
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue     (multicast to both CTAs)
   uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA     (leader's copy is the live one)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  // epilogue scratch: 2 accumulator stages x 256 floats, after the barriers (inside the 4 KB tail reserved in GemmSmem)
-  float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // 128 floats per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -717,7 +734,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       if (tc.kb_begin < tc.kb_end)
         Epi::template run<BN>(tc.prob ? e1 : e0, tacc, tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM,
-                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4, epi_smem + (warp - 4) * 128,
+                              tc.n_blk * BN, p.M, p.N, half, q, lane, warp - 4,
+                              epi_scratch + acc_stage * BN + half * (BN / (Epi::kWarps / 4)),
                               tc.prob ? &tmC1 : &tmC0, staging, tc.atomic, carry);
       tcgen05_fence_before();
       __syncwarp();

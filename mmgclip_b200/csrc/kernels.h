@@ -35,6 +35,15 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
                           const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
                           long long ldg, float* dlogscale_acc, cudaStream_t st);
 
+// The whole bf16 backward as one persistent launch (bwd_fused.cuh).  *used = 0 (and nothing launched) when the shape is
+// not covered (rows / cols / D not multiples of 256, workspace too small, MMG_BWD_FUSED=0): the caller falls back to the
+// block loop.  tc_infonce_bwd_fused_workspace = bytes it needs (0 = not covered).
+size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D);
+int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                         const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
+                         float* dB, float* dlogscale_acc, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                         int* used);
+
 // ---- SIMT (fp32) launchers: simt_kernels.cu ----
 int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
               int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,

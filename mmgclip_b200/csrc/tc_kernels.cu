@@ -2,11 +2,13 @@
 // tile-shape selection, persistent-grid sizing (one CTA per SM).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 
+#include "bwd_fused.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.h"
 
@@ -132,7 +134,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
                   const typename Epi::Params& e0, const typename Epi::Params& e1, cudaStream_t st,
                   bool balance_tail = false) {
   auto kern = gemm_tc_kernel<BN, Epi, kCG>;
-  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>()>;
+  using S = GemmSmem<BN, kCG, Epi::template staging_bytes<BN>(), Epi::kScratchBytes>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -214,17 +216,11 @@ static int prefetch_distance() {
   }
   return v;
 }
-// Epilogue warps of the InfoNCE epilogues: 8 (default) or 16 (MMG_EPI_WARPS=16; both instantiations are built).
-// Measured on B200 at 32768^2 x 512 (tests/gpu_epi_probe.py): 8 warps 0.723 / 1.019 ms (forward / coefficient launches),
-// 16 warps 0.754 / 1.095 ms -- the deeper operand ring the smaller staging area leaves matters more than latency hiding.
-static int epi_warps() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMG_EPI_WARPS");
-    v = (e != nullptr && atoi(e) == 16) ? 16 : 8;
-  }
-  return v;
-}
+// The InfoNCE epilogues run on 8 epilogue warps.  A 16-warp variant (4 column groups, setmaxnreg re-balancing) was
+// measured slower on B200 at 32768^2 x 512 (forward 0.754 vs 0.723 ms, coefficient launches 1.095 vs 1.019 ms): the
+// staging boxes of 16 warps cost an operand-ring stage, which matters more than the extra latency hiding.
+using EpiLse = EpiLseT<8>;
+using EpiGrad = EpiGradT<8>;
 struct TileCfg { int BN, cg; };
 static TileCfg pick_tile(int M, int N) {
   TileCfg c;
@@ -315,14 +311,9 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
   if ((rc = make_operand_map(&mb, B, cols, D, tcfg.BN / tcfg.cg)) != 0) return rc;
   GemmProblem p0 = make_problem(rows, cols, D, tcfg.BN, 1, 0, 0, tcfg.cg);
   GemmProblem p1 = empty_problem();
-  if (epi_warps() == 8) {
-    EpiLseT<8>::Params e;
-    e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
-    MMG_DISPATCH(EpiLseT<8>, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
-  }
-  EpiLseT<16>::Params e;
+  EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
-  MMG_DISPATCH(EpiLseT<16>, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
@@ -341,16 +332,134 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   if ((rc = make_tmap(&mc, G, cb, rb, ldg, 32)) != 0) return rc;
   int dbg = 0;  // measurement hook (tests/gpu_epi_probe.py): results are wrong when set
   if (const char* d = getenv("MMG_EPI_DBG")) dbg = atoi(d);
-  if (epi_warps() == 8) {
-    EpiGradT<8>::Params e;
-    e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
-    e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
-    MMG_DISPATCH(EpiGradT<8>, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
-  }
-  EpiGradT<16>::Params e;
+  EpiGrad::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
   e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
-  MMG_DISPATCH(EpiGradT<16>, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// fused persistent backward (bwd_fused.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
+struct FusedPlan {
+  int ok, Rb, Cb, nbuf, kslI, kslT;
+  size_t g_bytes, total_bytes;
+};
+
+static int largest_divisor(int n, int cap) {
+  for (int b = cap; b >= 256; b >>= 1)
+    if (n % b == 0) return b;
+  return 0;
+}
+
+static FusedPlan fused_plan(int rows, int cols, int D) {
+  FusedPlan f;
+  memset(&f, 0, sizeof(f));
+  if (env_int("MMG_BWD_FUSED", 1) == 0) return f;
+  if (rows < 256 || cols < 256 || D < 256 || (D % 256) != 0) return f;
+  int Rb = env_int("MMG_FUSED_RB", 0), Cb = env_int("MMG_FUSED_CB", 0);
+  if (Rb <= 0) Rb = largest_divisor(rows, 4096);
+  if (Cb <= 0) Cb = largest_divisor(cols, 2048);
+  if (Rb < 256 || Cb < 256 || (Rb % 256) || (Cb % 256) || (rows % Rb) || (cols % Cb)) return f;
+  // K blocks (of 64) per gradient slice: every slice ends in a 256 x 256 fp32 reduce-add at L2, so slices are long
+  int kslI = env_int("MMG_FUSED_KSL", 32), kslT = env_int("MMG_FUSED_KSL_T", env_int("MMG_FUSED_KSL", 32));
+  while (kslI > 1 && ((Cb / kBK) % kslI) != 0) kslI >>= 1;
+  while (kslT > 1 && ((Rb / kBK) % kslT) != 0) kslT >>= 1;
+  if (kslI < 1 || kslT < 1) return f;
+  int nbuf = env_int("MMG_FUSED_NBUF", 4);
+  if (nbuf < 3) nbuf = 3;
+  const int nblk = (rows / Rb) * (cols / Cb);
+  if (nbuf > nblk) nbuf = nblk < 1 ? 1 : nblk;
+  f.Rb = Rb; f.Cb = Cb; f.nbuf = nbuf; f.kslI = kslI; f.kslT = kslT;
+  f.g_bytes = ((size_t)nbuf * Rb * Cb * 2 + 255) / 256 * 256;
+  f.total_bytes = f.g_bytes + (size_t)2 * nblk * sizeof(unsigned int) + 256;
+  f.ok = 1;
+  return f;
+}
+
+size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
+  const FusedPlan f = fused_plan(rows, cols, D);
+  return f.ok ? f.total_bytes : 0;
+}
+
+int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                         const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
+                         float* dB, float* dlogscale_acc, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                         int* used) {
+  *used = 0;
+  const FusedPlan f = fused_plan(rows, cols, D);
+  if (!f.ok || workspace_bytes < f.total_bytes) return 0;
+  if (!out_tma_ok(dA, D) || !out_tma_ok(dB, D)) return 0;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return 0;
+  BwdFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.cols = cols; p.D = D;
+  p.Rb = f.Rb; p.Cb = f.Cb;
+  p.nbc = cols / f.Cb;
+  p.nblk = (rows / f.Rb) * p.nbc;
+  p.nbuf = f.nbuf;
+  p.tAm = f.Rb / 256; p.tAn = f.Cb / 256; p.tDn = D / 256;
+  p.kslI = f.kslI; p.kslT = f.kslT;
+  p.sI = (f.Cb / kBK) / f.kslI;
+  p.sT = (f.Rb / kBK) / f.kslT;
+  p.nA = p.tAm * p.tAn;
+  p.nBI = p.tAm * p.tDn * p.sI;
+  p.nB = p.nBI + p.tAn * p.tDn * p.sT;
+  p.diag_offset = diag_offset;
+  p.rinv = rinv; p.cinv = cinv; p.scale = scale; p.scal = scal; p.dlogscale_acc = dlogscale_acc;
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
+  p.doneA = ctr;
+  p.doneB = ctr + p.nblk;
+  cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)2 * p.nblk * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
+
+  CUtensorMap mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA, mdB;
+  int rc;
+  const long long grow = (long long)f.nbuf * f.Rb;
+  if ((rc = make_tmap(&mAk, a_hat, D, rows, D, kBM)) != 0) return rc;
+  if ((rc = make_tmap(&mBk, b_hat, D, cols, D, kBM)) != 0) return rc;
+  if ((rc = make_tmap(&mAmn, a_hat, D, rows, D, kBK)) != 0) return rc;
+  if ((rc = make_tmap(&mBmn, b_hat, D, cols, D, kBK)) != 0) return rc;
+  if ((rc = make_tmap(&mGk, workspace, f.Cb, grow, f.Cb, kBM)) != 0) return rc;
+  if ((rc = make_tmap(&mGmn, workspace, f.Cb, grow, f.Cb, kBK)) != 0) return rc;
+  if ((rc = make_tmap(&mGst, workspace, f.Cb, grow, f.Cb, 32)) != 0) return rc;
+  if ((rc = make_out_tmap_f32(&mdA, dA, D, rows, D)) != 0) return rc;
+  if ((rc = make_out_tmap_f32(&mdB, dB, D, cols, D)) != 0) return rc;
+
+  auto kern = infonce_bwd_fused_kernel;
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::kTotal);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
+    configured = true;
+  }
+  const int pairs = sm_count() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pairs * 2);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = FusedSmem::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // (An L2 persisting access-policy window on the coefficient scratch was tried and is much slower -- 4.1 vs 2.65 ms at
+  // 32768^2 -- and the device-wide set-aside also slows every later kernel of the process; not used.)
+  e = cudaLaunchKernelEx(&cfg, kern, mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA, mdB, p);
+  if (e != cudaSuccess) return check_cuda(e, "infonce_bwd_fused_kernel launch");
+  count_launch();
+  *used = 1;
+  return 0;
 }
 
 }  // namespace mmg
