@@ -126,10 +126,13 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
  * dominant, heavily cancelling term).  b32, dB and cinv_paired point at the `rows` column-side entries paired with the
  * local rows (column diag_offset + r); diag is the forward's diag[] (the pair's logit):
  *   g = exp(diag[r] - s)*(rinv[r] + cinv_paired[r]) - dcoef
- *   dA[r,:] += g*b32[r,:],   dB[r,:] += g*a32[r,:],   dlogscale_acc += g * diag[r]/s   (dlogscale_acc may be NULL). */
+ *   dA[r,:] += g*b32[r,:],   dB[r,:] += g*a32[r,:],   dlogscale_acc += g * diag[r]/s   (dlogscale_acc may be NULL).
+ * init != 0: the rows are WRITTEN (dA[r,:] = g*b32[r,:], dB[r,:] = g*a32[r,:]) instead of accumulated -- call it before
+ * mmg_infonce_bwd on uninitialised dA / dB rows and skip their zero-fill (column rows of dB that are not paired with a
+ * local row still have to be zeroed by the caller). */
 int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                          const float* rinv, const float* cinv_paired, const float* scal, float* dA, float* dB,
-                         float* dlogscale_acc, mmg_stream_t stream);
+                         float* dlogscale_acc, int init, mmg_stream_t stream);
 
 /* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
  *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - scal[0]*[c == r + diag_offset]    ( = s * dloss/dlogit; the

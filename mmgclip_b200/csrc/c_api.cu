@@ -314,7 +314,7 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
 
 int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                          const float* rinv, const float* cinv_paired, const float* scal, float* dA, float* dB,
-                         float* dlogscale_acc, mmg_stream_t stream) {
+                         float* dlogscale_acc, int init, mmg_stream_t stream) {
   if (rows <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_diag: bad shape");
   MMG_REQ(a32);
   MMG_REQ(b32);
@@ -327,7 +327,7 @@ int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, co
   MMG_REQ(dB);
   if (dlogscale_acc != nullptr) MMG_REQ(dlogscale_acc);  // NULL: d/d logit_scale not wanted
   return simt_infonce_bwd_diag(a32, b32, rows, D, diag, scale, rinv, cinv_paired, scal, dA, dB, dlogscale_acc,
-                               static_cast<cudaStream_t>(stream));
+                               init != 0, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,

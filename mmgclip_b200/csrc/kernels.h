@@ -78,7 +78,7 @@ int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, in
                           float* scal, cudaStream_t st);
 int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                           const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
-                          float* dlogscale_acc, cudaStream_t st);
+                          float* dlogscale_acc, int init, cudaStream_t st);
 int simt_dot_sum(const float* x, const float* y, long long n, float* out, cudaStream_t st);
 int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
                 float* loss_out, cudaStream_t st);

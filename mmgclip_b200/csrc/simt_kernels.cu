@@ -704,7 +704,7 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
                         const float* __restrict__ diag, const float* __restrict__ scale,
                         const float* __restrict__ rinv, const float* __restrict__ cinvm,
                         const float* __restrict__ scal, float* __restrict__ dA, float* __restrict__ dB,
-                        float* __restrict__ dlogscale_acc) {
+                        float* __restrict__ dlogscale_acc, int init) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const float s = *scale;
@@ -717,10 +717,27 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
     const float* br = b32 + (long long)r * D;
     float* dar = dA + (long long)r * D;
     float* dbr = dB + (long long)r * D;
-    for (int i = lane; i < D; i += 32) {
-      const float av = ar[i], bv = br[i];
-      dar[i] = fmaf(g, bv, dar[i]);
-      dbr[i] = fmaf(g, av, dbr[i]);
+    if (init) {
+      // first writer of the gradient rows: no read-modify-write (the contraction kernels then accumulate on top)
+      if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(ar) | reinterpret_cast<uintptr_t>(br) |
+                            reinterpret_cast<uintptr_t>(dar) | reinterpret_cast<uintptr_t>(dbr)) & 15) == 0) {
+        for (int i = lane * 4; i < D; i += 128) {
+          const float4 av = *reinterpret_cast<const float4*>(ar + i), bv = *reinterpret_cast<const float4*>(br + i);
+          *reinterpret_cast<float4*>(dar + i) = make_float4(g * bv.x, g * bv.y, g * bv.z, g * bv.w);
+          *reinterpret_cast<float4*>(dbr + i) = make_float4(g * av.x, g * av.y, g * av.z, g * av.w);
+        }
+      } else {
+        for (int i = lane; i < D; i += 32) {
+          dar[i] = g * br[i];
+          dbr[i] = g * ar[i];
+        }
+      }
+    } else {
+      for (int i = lane; i < D; i += 32) {
+        const float av = ar[i], bv = br[i];
+        dar[i] = fmaf(g, bv, dar[i]);
+        dbr[i] = fmaf(g, av, dbr[i]);
+      }
     }
     contrib = g * (lg / s);
   }
@@ -737,10 +754,10 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
 
 int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                           const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
-                          float* dlogscale_acc, cudaStream_t st) {
+                          float* dlogscale_acc, int init, cudaStream_t st) {
   if (rows <= 0) return 0;
   infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, diag, scale, rinv, cinvm, scal, dA, dB,
-                                                          dlogscale_acc);
+                                                          dlogscale_acc, init);
   MMG_LAUNCH_CHECK("infonce_bwd_diag_kernel");
   return 0;
 }

@@ -276,9 +276,22 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None and diag is not None
     check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
                                    int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
-    dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
-    dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
+    if diag_fp32:
+        # the fp32 matching-pair term is the FIRST writer of the gradient rows (no zero-fill, no read-modify-write);
+        # the contraction kernels then accumulate on top.  Column rows without a local partner start from zero.
+        dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        if cols == rows:
+            dB = torch.empty((cols, D), dtype=torch.float32, device=dev)
+        else:
+            dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
+        dBm = dB[diag_offset:diag_offset + rows]
+        cinvm = cinv[diag_offset:diag_offset + rows]
+        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
+                                       _p(dA), _p(dBm), _p(dls), 1, _stream()), "mmg_infonce_bwd_diag")
+    else:
+        dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+        dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
     block_rows = block_rows or int(os.environ.get("MMGCLIP_B200_BLOCK_ROWS", "0"))
     block_cols = block_cols or int(os.environ.get("MMGCLIP_B200_BLOCK_COLS", "0"))
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
@@ -291,11 +304,6 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
                               _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
                               _stream()), "mmg_infonce_bwd")
-    if diag_fp32:
-        dBm = dB[diag_offset:diag_offset + rows]
-        cinvm = cinv[diag_offset:diag_offset + rows]
-        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
-                                       _p(dA), _p(dBm), _p(dls), _stream()), "mmg_infonce_bwd_diag")
     return dA, dB, dls
 
 
@@ -378,10 +386,13 @@ class _L2NormFn(torch.autograd.Function):
         if yb is None:
             yb = y.new_empty(0)
         ctx.mark_non_differentiable(yb)
+        ctx.set_materialize_grads(False)  # no zero-filled [B, D] gradient for the bf16 copy (an 11 us fill at B = 32768)
         return y, yb
 
     @staticmethod
     def backward(ctx, dy, _unused):
+        if dy is None:
+            return None, None
         y, inv = ctx.saved_tensors
         du, _ = l2norm_bwd(dy, y, inv, True, False)
         return du, None
@@ -421,10 +432,13 @@ class _ProjNormFn(torch.autograd.Function):
         if yb is None:
             yb = y.new_empty(0)
         ctx.mark_non_differentiable(yb)
+        ctx.set_materialize_grads(False)  # no zero-filled [B, D] gradient for the bf16 copy (an 11 us fill at B = 32768)
         return y, yb
 
     @staticmethod
     def backward(ctx, dy, _unused):
+        if dy is None:
+            return None, None, None
         saved = ctx.saved_tensors
         xo = _Operand.from_tensors(saved[:ctx.nx])
         wo = _Operand.from_tensors(saved[ctx.nx:ctx.nx + ctx.nw])
