@@ -1,0 +1,84 @@
+"""The fused persistent backward launch (csrc/bwd_fused.cuh) against the block loop it replaces and against float64:
+square and row-sharded (rectangular, offset diagonal) problems, D = 256 / 512 / 1024, several block shapes, with and
+without d logit_scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+ENV = ("MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF", "MMG_FUSED_KSL", "MMG_FUSED_KSL_T")
+
+
+def _setenv(**kw):
+    for k in ENV:
+        os.environ.pop(k, None)
+    for k, v in kw.items():
+        os.environ[k] = str(v)
+
+
+def _problem(rows, cols, d, off, seed=3):
+    from mmgclip_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.nn.functional.normalize(torch.randn(rows, d, device="cuda", generator=gen), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(cols, d, device="cuda", generator=gen), dim=1)
+    b[off:off + rows] = torch.nn.functional.normalize(b[off:off + rows] + 0.7 * a, dim=1)
+    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    s = torch.tensor(1 / 0.07, device="cuda")
+    rs, cs, diag = ops.infonce_forward_raw(ab, bb, s, off, "bf16")
+    return ops, a, b, ab, bb, s, rs, cs, diag
+
+
+@pytest.mark.parametrize("rows,cols,d,off,cfg", [
+    (512, 512, 256, 0, {}),
+    (768, 768, 1024, 0, {}),
+    (1024, 2048, 512, 512, {}),
+    (1024, 2048, 512, 1024, {"MMG_FUSED_RB": 256, "MMG_FUSED_CB": 512, "MMG_FUSED_NBUF": 3, "MMG_FUSED_KSL": 2}),
+    (4096, 8192, 512, 4096, {}),
+    (4096, 4096, 512, 0, {"MMG_FUSED_RB": 1024, "MMG_FUSED_CB": 1024, "MMG_FUSED_NBUF": 5, "MMG_FUSED_KSL": 4, "MMG_FUSED_KSL_T": 16}),
+])
+def test_fused_backward_matches_block_loop(rows, cols, d, off, cfg):
+    ops, a, b, ab, bb, s, rs, cs, diag = _problem(rows, cols, d, off)
+    one = torch.ones((), device="cuda")
+    b32 = b[off:off + rows].contiguous()
+    run = lambda: ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, off, "bf16", a32=a, b32=b32, diag=diag)  # noqa: E731
+    try:
+        _setenv(MMG_BWD_FUSED=0)
+        dA0, dB0, dl0 = run()
+        torch.cuda.synchronize()
+        _setenv(**cfg)
+        n0 = ops._lib.load().mmg_kernel_launch_count()
+        dA1, dB1, dl1 = run()
+        torch.cuda.synchronize()
+        launches = ops._lib.load().mmg_kernel_launch_count() - n0
+    finally:
+        _setenv()
+    assert launches == 3, "prep + matching-pair init + ONE fused launch expected"
+    # same bf16 operands and coefficients; only the fp32 accumulation order differs
+    assert rel_err(dA1.cpu(), dA0.cpu()) < 2e-4
+    assert rel_err(dB1.cpu(), dB0.cpu()) < 2e-4
+    assert abs(dl1.item() - dl0.item()) <= 2e-4 * max(abs(dl0.item()), 1e-3)
+
+
+def test_fused_backward_vs_float64():
+    rows = cols = 512
+    d = 256
+    ops, a, b, ab, bb, s, rs, cs, diag = _problem(rows, cols, d, 0, seed=9)
+    one = torch.ones((), device="cuda")
+    dA, dB, dls = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, 0, "bf16", a32=a, b32=b, diag=diag)
+    torch.cuda.synchronize()
+    A, Bm = a.double().cpu().numpy(), b.double().cpu().numpy()
+    sv = float(s.item())
+    cos = A @ Bm.T
+    e = np.exp(sv * cos - sv)
+    coef = sv * 0.5 / cols
+    g = e * (coef / e.sum(1)[:, None] + coef / e.sum(0)[None, :])
+    g[np.arange(rows), np.arange(rows)] -= 2 * coef
+    # bf16 operand rounding: same bars as tests/test_gpu_parity.py (GRAD bf16 = 4e-3)
+    assert rel_err(dA.cpu(), g @ Bm) < 4e-3
+    assert rel_err(dB.cpu(), g.T @ A) < 4e-3
+    assert abs(dls.item() - float((g * cos).sum())) < 4e-3 * max(1.0, abs(float((g * cos).sum())))
