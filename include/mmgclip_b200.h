@@ -164,6 +164,16 @@ int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, 
                        float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
                        mmg_stream_t stream);
 
+/* Same contract on the tensor pipe: both operands are split into two TF32 terms inside the kernel (a ~ a_hi + a_lo) and
+ * a_hi.b_hi + a_lo.b_hi + a_hi.b_lo is accumulated in fp32 (tcgen05.mma kind::tf32), which keeps the logits within
+ * ~1e-6 (max-abs / max-abs) of the fp32 FFMA evaluation above while the embeddings stream from HBM exactly once.
+ * Needs D % 4 == 0, 16-byte aligned img, and a 256-byte aligned workspace of mmg_zeroshot_workspace_bytes(C, D) bytes
+ * (the prompts' TF32 terms); returns MMG_ERR_UNSUPPORTED_SHAPE otherwise. */
+size_t mmg_zeroshot_workspace_bytes(int C, int D);
+int mmg_zeroshot_score_tc(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                          float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
+                          void* workspace, size_t workspace_bytes, mmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

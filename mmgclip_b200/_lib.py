@@ -57,6 +57,9 @@ SIGNATURES = {
     "mmg_ce_bwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                            c_longlong, c_void_p]),
     "mmg_dot_sum": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "mmg_zeroshot_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mmg_zeroshot_score_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmg_zeroshot_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p]),
 }

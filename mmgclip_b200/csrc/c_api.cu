@@ -448,4 +448,25 @@ int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, 
                        static_cast<cudaStream_t>(stream));
 }
 
+
+size_t mmg_zeroshot_workspace_bytes(int C, int D) { return tc_zeroshot_workspace_bytes(C, D); }
+
+int mmg_zeroshot_score_tc(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                          float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
+                          void* workspace, size_t workspace_bytes, mmg_stream_t stream) {
+  if (N < 0 || C <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score_tc: bad shape %dx%dx%d", N, C, D);
+  if (C > 64) return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "mmg_zeroshot_score_tc: at most 64 prompts (got %d)", C);
+  if (k < 0 || k > 8 || k > C) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score_tc: need 0 <= k <= min(8, C)");
+  if (N == 0) return 0;
+  MMG_REQ(img);
+  MMG_REQ(txt);
+  MMG_REQ(scale);
+  MMG_REQ(workspace);
+  if (!tc_zeroshot_supported(img, N, C, D))
+    return set_error(MMG_ERR_UNSUPPORTED_SHAPE,
+                     "mmg_zeroshot_score_tc: needs D %% 4 == 0 and 16-byte aligned embeddings (use mmg_zeroshot_score)");
+  return tc_zeroshot(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k, topk_idx_out, topk_val_out,
+                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

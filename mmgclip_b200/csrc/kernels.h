@@ -44,6 +44,13 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
                          float* dB, float* dlogscale_acc, void* workspace, size_t workspace_bytes, cudaStream_t st,
                          int* used);
 
+// Zero-shot prompt scoring on the tensor pipe (zeroshot_tc.cu): 3xTF32, fp32-faithful, HBM-bound at large N.
+size_t tc_zeroshot_workspace_bytes(int C, int D);
+bool tc_zeroshot_supported(const float* img, int N, int C, int D);
+int tc_zeroshot(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
+                float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val, void* workspace,
+                size_t workspace_bytes, cudaStream_t st);
+
 // ---- SIMT (fp32) launchers: simt_kernels.cu ----
 int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
               int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,

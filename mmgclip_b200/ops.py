@@ -708,12 +708,18 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 # ----------------------------------------------------------------------------------------------------------------
 # zero-shot scoring (inference only)
 # ----------------------------------------------------------------------------------------------------------------
+_ZEROSHOT_TC_MIN_ROWS = 4096
+
+
 def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, logit_scale, k: int = 0,
-                   want_logits: bool = True, want_probs: bool = True):
+                   want_logits: bool = True, want_probs: bool = True, impl: str = "auto"):
     """logits = (s*I) @ T^T, softmax(-1), argmax (ties -> lowest index), top-k (value desc, index asc).
 
     Returns dict(logits, probs, argmax[int64], topk_idx[int64, k], topk_val).  C <= 64 prompts, k <= 8.
-    (mmgclip_model.py:201-209; evaluator.py:182-188, 282-299, 354-368)"""
+    (mmgclip_model.py:201-209; evaluator.py:182-188, 282-299, 354-368)
+
+    ``impl``: "ffma" = fp32 FFMA kernel (what small batches use); "tc" = tensor-core kernel (3xTF32 split, logits within
+    ~1e-6 of the FFMA evaluation, HBM-bound at large N); "auto" = "tc" from 4096 rows when the layout allows it."""
     _need_cuda(image_embeddings, text_embeddings)
     img = image_embeddings.detach().to(torch.float32).contiguous()
     txt = text_embeddings.detach().to(torch.float32).contiguous()
@@ -731,6 +737,17 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
     amax = torch.empty(N, dtype=torch.int64, device=dev)
     tki = torch.empty((N, k), dtype=torch.int64, device=dev) if k > 0 else None
     tkv = torch.empty((N, k), dtype=torch.float32, device=dev) if k > 0 else None
-    check(_lib.load().mmg_zeroshot_score(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
-                                         _p(tkv), _stream()), "mmg_zeroshot_score")
+    if impl not in ("auto", "tc", "ffma"):
+        raise ValueError(f"Invalid impl: {impl}")
+    lib = _lib.load()
+    tc_ok = N > 0 and C <= 64 and D % 4 == 0 and img.data_ptr() % 16 == 0 and os.environ.get("MMG_ZEROSHOT_TC", "1") != "0"
+    if impl == "tc" and not tc_ok:
+        raise ValueError("zeroshot_score(impl='tc') needs C <= 64, D % 4 == 0 and 16-byte aligned embeddings")
+    if tc_ok and (impl == "tc" or (impl == "auto" and N >= _ZEROSHOT_TC_MIN_ROWS)):
+        ws = _workspace(dev, lib.mmg_zeroshot_workspace_bytes(C, D))
+        check(lib.mmg_zeroshot_score_tc(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
+                                        _p(tkv), _p(ws), ws.numel(), _stream()), "mmg_zeroshot_score_tc")
+    else:
+        check(lib.mmg_zeroshot_score(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
+                                     _p(tkv), _stream()), "mmg_zeroshot_score")
     return {"logits": logits, "probs": probs, "argmax": amax, "topk_idx": tki, "topk_val": tkv}
