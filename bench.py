@@ -501,7 +501,8 @@ def run_zeroshot(args):
     sets = [torch.nn.functional.normalize(torch.randn(n, d, device=dev, generator=gen), dim=1) for _ in range(2)]
     txt = torch.nn.functional.normalize(torch.randn(c, d, device=dev, generator=gen), dim=1)
     s = torch.tensor(1 / 0.07, device=dev)
-    fn = lambda i: ops.zeroshot_score(sets[i % 2], txt, s, k=k, want_logits=False, want_probs=False)  # noqa: E731
+    impl = args.zeroshot_impl
+    fn = lambda i: ops.zeroshot_score(sets[i % 2], txt, s, k=k, want_logits=False, want_probs=False, impl=impl)  # noqa: E731
     for i in range(max(args.warmup, 3)):
         fn(i)
     torch.cuda.synchronize()
@@ -524,7 +525,9 @@ def run_zeroshot(args):
                                          "l2": "two 2 GiB embedding sets alternate (larger than L2)"},
         "gpu_launches": int(_lib.load().mmg_kernel_launch_count() - n0),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "zeroshot_kernel"}}))
+                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "zeroshot_kernel (fp32 FFMA)" if impl == "ffma" else
+                               "zeroshot_tc_kernel (tcgen05 kind::tf32, 3xTF32 split in shared memory; + a 2 us prompt prep)"}}))
     return 0
 
 
@@ -546,6 +549,7 @@ def main():
     ap.add_argument("--workload", default="clip", choices=["clip", "zeroshot"],
                     help="clip = the headline metric (default); zeroshot = BASELINE config 4 (secondary line)")
     ap.add_argument("--zeroshot-rows", type=int, default=1 << 20)
+    ap.add_argument("--zeroshot-impl", default="auto", choices=["auto", "tc", "ffma"])
     args = ap.parse_args()
     if args.workload == "zeroshot":
         return run_zeroshot(args)

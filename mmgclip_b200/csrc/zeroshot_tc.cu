@@ -12,18 +12,21 @@
 //     a.b' ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo       (products of TF32 terms are exact in the fp32 accumulator;
 //                                                      what is dropped is O(2^-21) relative per product)
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of accumulations
-// (measured 5e-6 of the largest logit after 192 of them), so the dominant hi.hi term is spread over three partial
-// accumulators (k-blocks round robin), the two small terms go to a fourth, and the epilogue adds the four in fp32 --
-// logits then agree with an fp32 FFMA evaluation to ~1e-6 (max-abs over max-abs).  The image tile is split by four
+// (measured 5e-6 of the largest logit after 192 of them), so the dominant hi.hi term alternates between two partial
+// accumulators, the small terms have their own columns, and the epilogue adds the four in fp32 -- logits then agree
+// with an fp32 FFMA evaluation to ~1e-6 (max-abs over max-abs).  Shared-memory bandwidth is the scarce resource (TMA
+// writes, splitter read + write, tensor-core operand reads), so the prompt hi and lo tiles sit back to back and one
+// N = 128 MMA computes a_hi.[b_hi ; b_lo] (a_hi is read once), followed by an N = 64 MMA for a_lo.b_hi.  The image tile is split by four
 // CUDA-core warps in shared memory right after the TMA lands it, so HBM sees the embeddings exactly once:
 //
-//   warp 0      TMA producer : img tile [128 rows x 32 fp32] + prompt hi/lo tiles [64 x 32] per stage (4 x 48 KB ring)
-//   warps 4-7   splitter     : in place a -> a_hi, second buffer a_lo; fence.proxy.async; arrive
-//   warp 1      MMA issuer   : 4 k-steps x 3 tcgen05.mma (M128 N64 K8, kind::tf32) per stage, accumulators in TMEM
-//   warp 2      TMEM alloc   : 2 accumulator stages x 4 accumulators x 64 columns (all 512)
-//   warps 8-15  epilogue     : two groups of four warps take alternate tiles; one row per thread (64 logits in
-//                              registers): top-k by k branch-free selection passes, softmax, argmax of the
-//                              probabilities (ties -> lowest index), coalesced index stores
+//   warp 0      image producer  : img tile [128 rows x 32 fp32] per k-block, 8 x 16 KB in flight
+//   warp 3      prompt producer : prompt hi/lo tiles [64 x 32] per k-block (3 x 16 KB ring, from L2)
+//   warps 4-11  splitter     : two groups of four warps take alternate k-blocks: a_lo = rn_tf32(a - trunc(a)) into a
+//                              4-slot ring (the raw tile serves as a_hi); fence.proxy.async; arrive
+//   warp 1      MMA issuer   : 4 k-steps x (M128 N128 K8 + M128 N64 K8) tcgen05.mma kind::tf32 per k-block
+//   warp 2      TMEM alloc   : 2 accumulator stages x 2 pairs x 128 columns (all 512)
+//   warps 12-15 epilogue     : one row per thread (64 logits in registers): top-k by k branch-free selection passes,
+//                              softmax, argmax of the probabilities (ties -> lowest index), coalesced index stores
 // Persistent grid (one CTA per SM), the prompts' hi/lo tiles (2 x 64 x D fp32, L2 resident) come from a small prep kernel.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -44,13 +47,14 @@ constexpr int kZsRows = 128;      // image rows per tile (UMMA M)
 constexpr int kZsC = 64;          // prompt slots (UMMA N); prompts beyond C are zero rows
 constexpr int kZsBK = 32;         // fp32 elements per stage along D (= one 128-byte swizzle span)
 constexpr int kZsUK = 8;          // K per tcgen05.mma for TF32
-constexpr int kZsStages = 4;
+constexpr int kZsA = 6;           // image-tile ring (HBM latency is hidden here)
+constexpr int kZsL = 4;           // lo-term ring (splitter -> MMA), two slots per splitter group
+constexpr int kZsB = 3;           // prompt-tile ring (L2)
 constexpr int kZsABytes = kZsRows * kZsBK * 4;   // 16 KB
-constexpr int kZsBBytes = kZsC * kZsBK * 4;      // 8 KB
-constexpr int kZsStageBytes = 2 * kZsABytes + 2 * kZsBBytes;  // a (-> a_hi), a_lo, b_hi, b_lo = 48 KB
-constexpr int kZsSmem = kZsStages * kZsStageBytes + 512;
+constexpr int kZsBBytes = kZsC * kZsBK * 4;      // 8 KB (hi or lo)
+constexpr int kZsSmem = (kZsA + kZsL) * kZsABytes + kZsB * 2 * kZsBBytes + 512;  // 208.5 KB
 constexpr int kZsThreads = 32 * 16;
-constexpr int kZsAccCols = 4 * kZsC;  // per accumulator stage: three hi.hi partials + the small terms
+constexpr int kZsAccCols = 4 * kZsC;  // per accumulator stage: two [hi.hi partial | small terms] pairs
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // round-to-nearest (ties away) to 10 explicit mantissa bits; the inputs here are tiny remainders, never near overflow
@@ -93,41 +97,48 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, u
 
 __global__ void __launch_bounds__(kZsThreads, 1)
 zeroshot_tc_kernel(const __grid_constant__ CUtensorMap mImg, const __grid_constant__ CUtensorMap mThi,
-                   const __grid_constant__ CUtensorMap mTlo, int N, int C, int D, float* __restrict__ logits_out, float* __restrict__ probs_out, long long* __restrict__ argmax_out,
+                   const __grid_constant__ CUtensorMap mTlo, int N, int C, int D, int flags,
+                   float* __restrict__ logits_out, float* __restrict__ probs_out, long long* __restrict__ argmax_out,
                    int k, long long* __restrict__ topk_idx, float* __restrict__ topk_val) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0u) {
     if (threadIdx.x == 0) printf("[mmgclip_b200] dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  // Three rings of different depth: the image tiles are what HBM latency has to be hidden for (8 x 16 KB in flight per
+  // SM); their low-order terms only live between the splitter and the MMA (2 slots); the prompt tiles come from L2.
   uint8_t* smem = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kZsStages * kZsStageBytes);
-  uint64_t* full_bar = bars;                     // [stages] TMA -> splitter
-  uint64_t* split_bar = bars + kZsStages;        // [stages] splitter -> MMA
-  uint64_t* empty_bar = bars + 2 * kZsStages;    // [stages] MMA -> TMA
-  uint64_t* tfull_bar = bars + 3 * kZsStages;    // [2] MMA -> epilogue
-  uint64_t* tempty_bar = bars + 3 * kZsStages + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kZsStages + 4);
+  uint8_t* sA = smem;                                   // [kZsA] image tile, raw fp32 -> hi term in place
+  uint8_t* sL = sA + kZsA * kZsABytes;                  // [kZsL] lo term of the image tile
+  uint8_t* sB = sL + kZsL * kZsABytes;                  // [kZsB] prompt tile: hi (8 KB) + lo (8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kZsB * 2 * kZsBBytes);
+  uint64_t* fullA = bars;                      // [kZsA] TMA -> splitter
+  uint64_t* emptyA = fullA + kZsA;             // [kZsA] MMA -> image producer
+  uint64_t* fullB = emptyA + kZsA;             // [kZsB] TMA -> MMA
+  uint64_t* emptyB = fullB + kZsB;             // [kZsB] MMA -> prompt producer
+  uint64_t* split_bar = emptyB + kZsB;         // [kZsL] splitter -> MMA (hi written in place, lo written)
+  uint64_t* emptyL = split_bar + kZsL;         // [kZsL] MMA -> splitter
+  uint64_t* tfull_bar = emptyL + kZsL;         // [2] MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntiles = (N + kZsRows - 1) / kZsRows;
   const int nkb = (D + kZsBK - 1) / kZsBK;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mImg);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&mImg);
+  if (warp == 3 && lane == 0) {
     tma_prefetch_desc(&mThi);
     tma_prefetch_desc(&mTlo);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kZsStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&split_bar[i], 4);
-      mbar_init(&empty_bar[i], 1);
-    }
+    for (int i = 0; i < kZsA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < kZsB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < kZsL; ++i) { mbar_init(&split_bar[i], 4); mbar_init(&emptyL[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // the four warps of the epilogue group that owns the stage
+      mbar_init(&tempty_bar[i], 4);
     }
     fence_barrier_init();
   }
@@ -138,28 +149,43 @@ zeroshot_tc_kernel(const __grid_constant__ CUtensorMap mImg, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
+    // ===================== image producer: runs up to kZsA k-blocks ahead =====================
+    int sa = 0;
+    uint32_t pa = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait(&emptyA[sa], pa ^ 1);
         if (elect_one_sync()) {
-          uint8_t* st = smem + stage * kZsStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kZsABytes + 2 * kZsBBytes);
-          tma_load_2d(&mImg, &full_bar[stage], st, kb * kZsBK, t * kZsRows, kEvictFirst);            // streamed once
-          tma_load_2d(&mThi, &full_bar[stage], st + 2 * kZsABytes, kb * kZsBK, 0, kEvictLast);       // L2 resident
-          tma_load_2d(&mTlo, &full_bar[stage], st + 2 * kZsABytes + kZsBBytes, kb * kZsBK, 0, kEvictLast);
+          mbar_arrive_expect_tx(&fullA[sa], kZsABytes);
+          tma_load_2d(&mImg, &fullA[sa], sA + sa * kZsABytes, kb * kZsBK, t * kZsRows, kEvictFirst);  // streamed once
         }
         __syncwarp();
-        if (++stage == kZsStages) { stage = 0; phase ^= 1; }
+        if (++sa == kZsA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== prompt producer (L2-resident hi / lo tiles) =====================
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&emptyB[sb], pb ^ 1);
+        if (elect_one_sync()) {
+          uint8_t* dst = sB + sb * 2 * kZsBBytes;
+          mbar_arrive_expect_tx(&fullB[sb], 2 * kZsBBytes);
+          tma_load_2d(&mThi, &fullB[sb], dst, kb * kZsBK, 0, kEvictLast);
+          tma_load_2d(&mTlo, &fullB[sb], dst + kZsBBytes, kb * kZsBK, 0, kEvictLast);
+        }
+        __syncwarp();
+        if (++sb == kZsB) { sb = 0; pb ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_tf32(kZsRows, kZsC);
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t idesc128 = make_idesc_tf32(kZsRows, 2 * kZsC);
+    const uint32_t idesc64 = make_idesc_tf32(kZsRows, kZsC);
+    int sa = 0, sb = 0, sl = 0;
+    uint32_t pb = 0, pl = 0;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int acc_stage = it & 1;
@@ -168,67 +194,75 @@ zeroshot_tc_kernel(const __grid_constant__ CUtensorMap mImg, const __grid_consta
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc_stage * kZsAccCols;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&split_bar[stage], phase);
+        mbar_wait(&split_bar[sl], pl);   // image tile: hi in place (slot sa), lo in slot sl
+        mbar_wait(&fullB[sb], pb);
         tcgen05_fence_after();
         if (elect_one_sync()) {
-          const uint32_t a_hi = smem_u32(smem + stage * kZsStageBytes);
-          const uint32_t a_lo = a_hi + kZsABytes;
-          const uint32_t b_hi = a_hi + 2 * kZsABytes;
-          const uint32_t b_lo = b_hi + kZsBBytes;
+          const uint32_t a_hi = smem_u32(sA + sa * kZsABytes);
+          const uint32_t a_lo = smem_u32(sL + sl * kZsABytes);
+          const uint32_t b_hi = smem_u32(sB + sb * 2 * kZsBBytes);
 #pragma unroll
           for (int ks = 0; ks < kZsBK / kZsUK; ++ks) {
             const uint32_t off = ks * kZsUK * 4;
             const uint64_t dah = make_smem_desc_sw128(a_hi + off, 0, 1024);
             const uint64_t dal = make_smem_desc_sw128(a_lo + off, 0, 1024);
-            const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 0, 1024);
-            const uint64_t dbl = make_smem_desc_sw128(b_lo + off, 0, 1024);
-            // hi.hi -> partial accumulator kb % 3 (first touched at kb = 0, 1, 2); small terms -> accumulator 3
-            umma_tf32_ss(tmem_d + (kb % 3) * kZsC, dah, dbh, idesc, (kb >= 3 || ks > 0) ? 1u : 0u);
-            umma_tf32_ss(tmem_d + 3 * kZsC, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32_ss(tmem_d + 3 * kZsC, dah, dbl, idesc, 1u);
+            const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 0, 1024);  // 128 rows: hi prompts, then lo prompts
+            // a_hi x [b_hi ; b_lo] (N = 128) -> pair kb & 1 = [hi.hi partial | hi.lo]; a_lo x b_hi (N = 64) -> the small-term
+            // columns of pair 0 (after the N = 128 MMA of kb = 0 has initialised them)
+            umma_tf32_ss(tmem_d + (kb & 1) * 2 * kZsC, dah, dbh, idesc128, (kb >= 2 || ks > 0) ? 1u : 0u);
+            umma_tf32_ss(tmem_d + kZsC, dal, dbh, idesc64, 1u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit(&emptyA[sa]);
+          umma_commit(&emptyL[sl]);
+          umma_commit(&emptyB[sb]);
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc_stage]);
         }
         __syncwarp();
-        if (++stage == kZsStages) { stage = 0; phase ^= 1; }
+        if (++sa == kZsA) sa = 0;
+        if (++sb == kZsB) { sb = 0; pb ^= 1; }
+        if (++sl == kZsL) { sl = 0; pl ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== splitter: a -> s*a -> (hi in place, lo in the second buffer) =====================
-    const int tid = threadIdx.x - 128;
-    int stage = 0;
-    uint32_t phase = 0;
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== splitter: a -> (hi in place, lo in the lo ring).  Two groups of four warps take alternate
+    // k-blocks, so two image tiles are being split at any time =====================
+    const int grp = (warp - 4) >> 2;
+    const int tid = threadIdx.x - 128 - grp * 128;
+    int sa = 0, sl = 0, seq = 0;
+    uint32_t pa = 0, pl = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        float4* a = reinterpret_cast<float4*>(smem + stage * kZsStageBytes);
-        float4* lo = reinterpret_cast<float4*>(smem + stage * kZsStageBytes + kZsABytes);
+      for (int kb = 0; kb < nkb; ++kb, ++seq) {
+        if ((seq & 1) == grp) {
+          mbar_wait(&fullA[sa], pa);
+          mbar_wait(&emptyL[sl], pl ^ 1);
+          float4* a = reinterpret_cast<float4*>(sA + sa * kZsABytes);
+          float4* lo = reinterpret_cast<float4*>(sL + sl * kZsABytes);
 #pragma unroll
-        for (int i = 0; i < kZsABytes / 16 / 128; ++i) {
-          const int idx = tid + i * 128;
-          const float4 v = a[idx];
-          const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
-          a[idx] = h;
-          lo[idx] = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z),
-                                tf32_round(v.w - h.w));
+          for (int i = 0; i < kZsABytes / 16 / 128; ++i) {
+            const int idx = tid + i * 128;
+            const float4 v = a[idx];
+            // The tensor core reads TF32 operands as fp32 words with the 13 low mantissa bits ignored (checked on B200:
+            // writing the truncated hi term back changes no result bit), so the raw tile IS the hi operand.
+            const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+            if (flags & 1) a[idx] = h;  // measurement hook: explicit write-back
+            lo[idx] = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z),
+                                  tf32_round(v.w - h.w));
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[sl]);
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[stage]);
-        if (++stage == kZsStages) { stage = 0; phase ^= 1; }
+        if (++sa == kZsA) { sa = 0; pa ^= 1; }
+        if (++sl == kZsL) { sl = 0; pl ^= 1; }
       }
     }
-  } else if (warp >= 8) {
-    // ===================== epilogue: one row per thread; group 0 (warps 8-11) takes the even tiles of this CTA,
-    // group 1 (warps 12-15) the odd ones -- i.e. each group owns one accumulator stage =====================
+  } else if (warp >= 12) {
+    // ===================== epilogue (warps 12-15): one row per thread =====================
     const int q = warp & 3;
-    const int grp = (warp - 8) >> 2;
-    const int nmain = nkb < 3 ? nkb : 3;  // hi.hi partial accumulators that were written
+    const int nmain = nkb < 2 ? nkb : 2;  // accumulator pairs that were written
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const int acc_stage = grp;
+      const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tcgen05_fence_after();
@@ -236,18 +270,24 @@ zeroshot_tc_kernel(const __grid_constant__ CUtensorMap mImg, const __grid_consta
       float l[64];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        // (small0 [+ small1]) [+ main1] + main0, fp32 round-to-nearest adds; pair p = columns [128 p, 128 p + 128)
         float v[32], w[32];
-        tmem_ld_32x32b_x32(tacc + 3 * kZsC + h * 32, v);  // small terms
+        tmem_ld_32x32b_x32(tacc + kZsC + h * 32, v);
         tmem_ld_wait();
-#pragma unroll 1
-        for (int m = nmain - 1; m >= 0; --m) {             // ((small + m2) + m1) + m0, fp32 round-to-nearest adds
-          tmem_ld_32x32b_x32(tacc + m * kZsC + h * 32, w);
+        if (nmain > 1) {
+          tmem_ld_32x32b_x32(tacc + 3 * kZsC + h * 32, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          tmem_ld_32x32b_x32(tacc + 2 * kZsC + h * 32, w);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
         }
+        tmem_ld_32x32b_x32(tacc + h * 32, w);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) l[h * 32 + j] = v[j];
+        for (int j = 0; j < 32; ++j) l[h * 32 + j] = v[j] + w[j];
       }
       // the accumulator stage is free as soon as it is in registers
       tcgen05_fence_before();
@@ -417,7 +457,9 @@ int tc_zeroshot(const float* img, const float* txt, int N, int C, int D, const f
   }
   const int ntiles = (N + kZsRows - 1) / kZsRows;
   const int grid = ntiles < sms ? ntiles : sms;
-  zeroshot_tc_kernel<<<grid, kZsThreads, kZsSmem, st>>>(mImg, mThi, mTlo, N, C, D, logits_out, probs_out,
+  int flags = 0;  // measurement hook: bit 0 = write the truncated hi term back explicitly
+  if (const char* f = getenv("MMG_ZEROSHOT_FLAGS")) flags = atoi(f);
+  zeroshot_tc_kernel<<<grid, kZsThreads, kZsSmem, st>>>(mImg, mThi, mTlo, N, C, D, flags, logits_out, probs_out,
                                                         argmax_out, k, topk_idx, topk_val);
   e = cudaGetLastError();
   if (e != cudaSuccess) return check_cuda(e, "zeroshot_tc_kernel");

@@ -32,14 +32,31 @@ def test_zeroshot_vs_reference_fixture(golden):
     assert np.array_equal(pred, g["argmax_numpy"]) and rel_err(probs, g["probs_numpy"]) < 1e-6
 
 
-@pytest.mark.parametrize("n,c,d,k", [(1, 2, 512, 0), (3, 1, 64, 1), (1000, 7, 200, 3), (4097, 64, 512, 5)])
-def test_zeroshot_shapes_and_edge_cases(n, c, d, k):
+def test_zeroshot_tensor_core_path_vs_reference_fixture(golden):
+    """The 3xTF32 tensor-core kernel (what large batches use) on the reference fixture: logits fp32-faithful (2e-6),
+    indices bit-exact including the duplicated prompt (identical columns give identical logits -> lowest index)."""
+    from mmgclip_b200 import ops
+    g = golden("zeroshot_small")
+    out = ops.zeroshot_score(cuda(g["img"]), cuda(g["txt"]), cuda(g["logit_scale"]), k=5, impl="tc")
+    assert np.array_equal(out["argmax"].cpu().numpy(), g["argmax"])
+    assert rel_err(out["logits"].cpu(), g["logits"]) < 2e-6
+    assert rel_err(out["probs"].cpu(), g["probs"]) < 5e-6
+    ref = oc.closed_form_zeroshot(g["img"], g["txt"], float(g["logit_scale"]), k=5)
+    assert np.array_equal(out["topk_idx"].cpu().numpy(), ref["topk_idx"])
+    assert np.array_equal(out["topk_idx"][:, 0].cpu().numpy(), g["argmax"])
+    with pytest.raises(ValueError):
+        ops.zeroshot_score(cuda(g["img"])[:, :62].contiguous(), cuda(g["txt"])[:, :62].contiguous(), 1.0, impl="tc")
+
+
+@pytest.mark.parametrize("impl", ["ffma", "tc"])
+@pytest.mark.parametrize("n,c,d,k", [(1, 2, 512, 0), (3, 1, 64, 1), (1000, 7, 200, 3), (4097, 64, 512, 5), (300, 64, 36, 8)])
+def test_zeroshot_shapes_and_edge_cases(n, c, d, k, impl):
     from mmgclip_b200 import ops
     rng = np.random.RandomState(n + c)
     img = rng.standard_normal((n, d)).astype(np.float32); img /= np.linalg.norm(img, axis=1, keepdims=True)
     txt = rng.standard_normal((c, d)).astype(np.float32); txt /= np.linalg.norm(txt, axis=1, keepdims=True)
     s = float(np.float32(1 / 0.07))
-    out = ops.zeroshot_score(cuda(img), cuda(txt), s, k=k)
+    out = ops.zeroshot_score(cuda(img), cuda(txt), s, k=k, impl=impl)
     ref = oc.closed_form_zeroshot(img, txt, s, k=k)
     srt = np.sort(ref["logits"], axis=1)
     safe = np.ones(n, bool) if c == 1 else (srt[:, -1] - srt[:, -2]) > 1e-4   # rows without a float32 near-tie
