@@ -63,6 +63,15 @@ int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, lo
              long long ldc, int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu,
              int mode, int k_splits, mmg_stream_t stream);
 
+/* Split-precision bf16 contraction in ONE launch (what the projection heads use in bf16 mode):
+ *   C (op)= alpha * ( A_hi.B_hi^T + A_hi.B_lo^T + A_lo.B_hi^T )        (A ~ A_hi + A_lo, B ~ B_hi + B_lo, all bf16)
+ * run as a single contraction over the concatenated K range (3K), one TMEM accumulator, one epilogue -- instead of
+ * three accumulate passes over C.  A_lo and/or B_lo may be NULL (their term is dropped).  Same layouts, modes and
+ * split-K rules as mmg_gemm (k_splits divides the concatenated range). */
+int mmg_gemm_split(const void* A_hi, const void* A_lo, long long lda, int a_mn, const void* B_hi, const void* B_lo,
+                   long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, float alpha, const float* bias,
+                   int relu, int mode, int k_splits, mmg_stream_t stream);
+
 /* ---- element-wise helpers -------------------------------------------------------------------------------- */
 int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream);
 /* hi = bf16(x), lo = bf16(x - hi): operands of the three-pass "bf16x3" contraction A_hi.B_hi + A_hi.B_lo + A_lo.B_hi that

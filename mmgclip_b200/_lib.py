@@ -29,6 +29,8 @@ SIGNATURES = {
     "mmg_kernel_launch_count": (c_longlong, []),
     "mmg_gemm": (c_int, [c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong,
                          c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mmg_gemm_split": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p,
+                               c_longlong, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mmg_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_cast_f32_to_bf16_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -112,6 +112,23 @@ int mmg_gemm(int prec, const void* A, long long lda, int a_mn, const void* B, lo
   return set_error(MMG_ERR_BAD_ARG, "mmg_gemm: unknown precision %d", prec);
 }
 
+int mmg_gemm_split(const void* A_hi, const void* A_lo, long long lda, int a_mn, const void* B_hi, const void* B_lo,
+                   long long ldb, int b_mn, float* C, long long ldc, int M, int N, int K, float alpha, const float* bias,
+                   int relu, int mode, int k_splits, mmg_stream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm_split: empty problem %dx%dx%d", M, N, K);
+  if (mode < 0 || mode > 2) return set_error(MMG_ERR_BAD_ARG, "mmg_gemm_split: bad store mode %d", mode);
+  MMG_REQ(A_hi);
+  MMG_REQ(B_hi);
+  MMG_REQ(C);
+  TcOperand a0{A_hi, lda, a_mn}, a1{A_lo, lda, a_mn}, b0{B_hi, ldb, b_mn}, b1{B_lo, ldb, b_mn};
+  // segments: hi.hi, then hi.lo (if B has a low part), then lo.hi (if A has one)
+  int nseg = 1, seg_a = 0, seg_b = 0;
+  if (B_lo != nullptr) { seg_b |= 1 << nseg; ++nseg; }
+  if (A_lo != nullptr) { seg_a |= 1 << nseg; ++nseg; }
+  return tc_gemm_store_seg(a0, A_lo ? &a1 : nullptr, b0, B_lo ? &b1 : nullptr, nseg, seg_a, seg_b, C, ldc, M, N, K, alpha,
+                           nullptr, bias, relu, mode, k_splits, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream) {
   if (n < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_cast: negative length");
   if (n == 0) return 0;

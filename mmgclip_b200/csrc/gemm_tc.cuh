@@ -33,7 +33,13 @@ struct GemmProblem {
   int tiles_m, tiles_n;  // ceil(M/(128*kCG)), ceil(N/BN)
   int k_splits;          // >= 1; each split handles a contiguous range of 64-wide K blocks
   int a_mn, b_mn;        // 0 = K-major operand, 1 = MN-major operand
+  // K segments (single-problem launches only): the contraction runs over k_segs concatenated K ranges of K elements
+  // each, segment i reading A from tensor map (seg_a >> i) & 1 and B from (seg_b >> i) & 1 -- one launch and one
+  // accumulator for  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  (split-precision heads) instead of three accumulate passes.
+  int k_segs, seg_a, seg_b;
   __host__ __device__ int num_tiles() const { return tiles_m * tiles_n * k_splits; }
+  __host__ __device__ int seg_kb() const { return (K + 63) / 64; }
+  __host__ __device__ int total_kb() const { return seg_kb() * (k_segs > 1 ? k_segs : 1); }
 };
 
 // kCG = 1: one CTA owns a 128 x BN tile.  kCG = 2: a CTA pair (cta_group::2) owns a 256 x BN tile -- each CTA stages
@@ -83,7 +89,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const GemmProblem& p0, c
   const int r = t - split * mn;
   c.m_blk = r / p.tiles_n;
   c.n_blk = r - c.m_blk * p.tiles_n;
-  const int nkb = (p.K + kBK - 1) / kBK;
+  const int nkb = p.total_kb();
   const int per = (nkb + p.k_splits - 1) / p.k_splits;
   c.kb_begin = split * per;
   c.kb_end = min(nkb, c.kb_begin + per);
@@ -607,18 +613,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int t = tile_first; t < total_tiles; t += tile_step) {
       const TileCoord tc = decode_virtual(t, p0, p1, tail);
       const GemmProblem& p = tc.prob ? p1 : p0;
-      const CUtensorMap* mA = tc.prob ? &tmA1 : &tmA0;
-      const CUtensorMap* mB = tc.prob ? &tmB1 : &tmB0;
       const int m0 = tc.m_blk * kTileM + static_cast<int>(cta_rank) * kBM;       // this CTA's A rows
       const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * S::kBRows;     // this CTA's share of the B rows
+      const int seg_kb = p.seg_kb();
       for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+        // K segment of this block (problem 0 only): which of the two A / B tensor maps, and the K offset inside it
+        const int seg = p.k_segs > 1 ? kb / seg_kb : 0;
+        const CUtensorMap* mA = (tc.prob || ((p.seg_a >> seg) & 1)) ? &tmA1 : &tmA0;
+        const CUtensorMap* mB = (tc.prob || ((p.seg_b >> seg) & 1)) ? &tmB1 : &tmB0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], kCG * (S::kABytes + S::kBBytes));
           else mbar_arrive_cluster(&full_bar[stage], 0);
           uint8_t* a_dst = sA + stage * S::kABytes;
           uint8_t* b_dst = sB + stage * S::kBBytes;
-          const int k0 = kb * kBK;
+          const int k0 = (kb - seg * seg_kb) * kBK;
           auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
             if (kCG == 2) tma_load_2d_cg2(m, &full_bar[stage], dst, c0, c1, kEvictNormal);
             else tma_load_2d(m, &full_bar[stage], dst, c0, c1, kEvictNormal);
@@ -636,7 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int i = 0; i < S::kBRows / 64; ++i) load(mB, b_dst + i * (kBK * 128), n0 + i * 64, k0);
           }
           // long K loops stream at least one operand from HBM: pull the boxes kPrefetchKb blocks ahead into L2
-          if (tail.prefetch_kb > 0 && kb + tail.prefetch_kb < tc.kb_end) {
+          if (tail.prefetch_kb > 0 && p.k_segs <= 1 && kb + tail.prefetch_kb < tc.kb_end) {
             const int kp = k0 + tail.prefetch_kb * kBK;
             if (!p.a_mn) {
               tma_prefetch_l2_2d(mA, kp, m0);

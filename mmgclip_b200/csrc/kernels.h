@@ -23,6 +23,12 @@ struct TcOperand {
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
                   const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
 
+// Same with up to three K segments (operand pairs chosen per segment by the bit masks), e.g. the split-precision heads'
+// A_hi.B_hi + A_hi.B_lo + A_lo.B_hi as ONE contraction over 3K.  A1 / B1 may be NULL when no segment refers to them.
+int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand& B0, const TcOperand* B1, int nseg,
+                      int seg_a, int seg_b, float* C, long long ldc, int M, int N, int K, float alpha,
+                      const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st);
+
 // Two independent accumulate-GEMMs in one launch (dA and dB of one logit block).
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
                             const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,

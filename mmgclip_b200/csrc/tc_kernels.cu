@@ -96,7 +96,7 @@ static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (M + kBM * cg - 1) / (kBM * cg);
   p.tiles_n = (N + BN - 1) / BN;
-  const int nkb = (K + kBK - 1) / kBK;
+  const int nkb = (K + kBK - 1) / kBK;  // (callers that add K segments re-derive the split afterwards)
   if (k_splits < 1) k_splits = 1;
   if (k_splits > nkb) k_splits = nkb;
   // no empty splits: shrink until the last split still owns a K block
@@ -107,6 +107,7 @@ static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a
   }
   p.k_splits = k_splits;
   p.a_mn = a_mn; p.b_mn = b_mn;
+  p.k_segs = 1; p.seg_a = 0; p.seg_b = 0;
   return p;
 }
 
@@ -114,6 +115,7 @@ static GemmProblem empty_problem() {
   GemmProblem p;
   memset(&p, 0, sizeof(p));
   p.k_splits = 1;
+  p.k_segs = 1;
   return p;
 }
 
@@ -238,15 +240,40 @@ static TileCfg pick_tile(int M, int N) {
 
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
                   const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
+  return tc_gemm_store_seg(A, nullptr, B, nullptr, 1, 0, 0, C, ldc, M, N, K, alpha, alpha_dev, bias, relu, mode, k_splits,
+                           st);
+}
+
+// C (op)= alpha * sum_i A[(seg_a >> i) & 1] . B[(seg_b >> i) & 1]^T over nseg K segments, one launch, one accumulator.
+int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand& B0, const TcOperand* B1, int nseg,
+                      int seg_a, int seg_b, float* C, long long ldc, int M, int N, int K, float alpha,
+                      const float* alpha_dev, const float* bias, int relu, int mode, int k_splits, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(-1, "tc_gemm: empty problem %dx%dx%d", M, N, K);
   if (k_splits > 1 && mode != 2) return set_error(-1, "tc_gemm: k_splits > 1 needs MMG_ATOMIC_ADD");
   if (k_splits > 1 && (relu || bias)) return set_error(-1, "tc_gemm: bias/ReLU cannot be fused with split-K");
+  if (nseg < 1 || nseg > 3) return set_error(-1, "tc_gemm: 1..3 K segments (got %d)", nseg);
+  if (nseg > 1 && ((seg_a != 0 && A1 == nullptr) || (seg_b != 0 && B1 == nullptr)))
+    return set_error(-1, "tc_gemm: a K segment refers to a missing operand");
   const TileCfg tcfg = pick_tile(M, N);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma1, mb1;
   int rc;
-  if ((rc = make_operand_map(&ma, A, M, K, kBM)) != 0) return rc;
-  if ((rc = make_operand_map(&mb, B, N, K, tcfg.BN / tcfg.cg)) != 0) return rc;
-  GemmProblem p0 = make_problem(M, N, K, tcfg.BN, k_splits, A.mn_major, B.mn_major, tcfg.cg);
+  if ((rc = make_operand_map(&ma, A0, M, K, kBM)) != 0) return rc;
+  if ((rc = make_operand_map(&mb, B0, N, K, tcfg.BN / tcfg.cg)) != 0) return rc;
+  ma1 = ma;
+  mb1 = mb;
+  if (A1 != nullptr && (rc = make_operand_map(&ma1, *A1, M, K, kBM)) != 0) return rc;
+  if (B1 != nullptr && (rc = make_operand_map(&mb1, *B1, N, K, tcfg.BN / tcfg.cg)) != 0) return rc;
+  GemmProblem p0 = make_problem(M, N, K, tcfg.BN, 1, A0.mn_major, B0.mn_major, tcfg.cg);
+  p0.k_segs = nseg;
+  p0.seg_a = nseg > 1 ? seg_a : 0;
+  p0.seg_b = nseg > 1 ? seg_b : 0;
+  {
+    // split-K over the concatenated K range; no empty splits
+    const int nkb = p0.total_kb();
+    int ks = k_splits < 1 ? 1 : (k_splits > nkb ? nkb : k_splits);
+    while (ks > 1 && (ks - 1) * ((nkb + ks - 1) / ks) >= nkb) --ks;
+    p0.k_splits = ks;
+  }
   GemmProblem p1 = empty_problem();
   EpiStoreF32::Params e;
   e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
@@ -254,7 +281,7 @@ int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ld
   e.use_tma = out_tma_ok(C, ldc) && !(mode != 0 && (relu || bias != nullptr));
   CUtensorMap mc = ma;
   if (e.use_tma && (rc = make_out_tmap_f32(&mc, C, N, M, ldc)) != 0) return rc;
-  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
+  MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma1, mb1, mc, mc, p0, p1, e, e, st);
 }
 
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,

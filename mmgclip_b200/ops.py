@@ -139,25 +139,39 @@ class _Operand:
 
 def gemm_heads(A: "_Operand", B: "_Operand", M: int, N: int, K: int, *, a_mn=False, b_mn=False, bias=None, relu=False,
                k_splits: int = 1, prec: str = "bf16") -> torch.Tensor:
-    """alpha=1 contraction of head operands; split operands run hi.hi + hi.lo + lo.hi, bias/ReLU on the last pass."""
-    passes = [(A.hi, B.hi)]
-    if A.lo is not None or B.lo is not None:
-        if B.lo is not None:
-            passes.append((A.hi, B.lo))
-        if A.lo is not None:
-            passes.append((A.lo, B.hi))
+    """alpha=1 contraction of head operands.  Split operands (hi, lo) contract as hi.hi + hi.lo + lo.hi in ONE launch over
+    the concatenated K range (mmg_gemm_split); bias / ReLU ride in its epilogue."""
+    if A.lo is None and B.lo is None:
+        if k_splits > 1:
+            if bias is not None or relu:
+                raise ValueError("bias/ReLU cannot be combined with split-K")
+            out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
+            return gemm(A.hi, B.hi, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_ATOMIC_ADD, k_splits=k_splits,
+                        prec=prec)
+        return gemm(A.hi, B.hi, M, N, K, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=relu, prec=prec)
+    if prec != "bf16":
+        raise ValueError("split operands exist only on the bf16 path")
+    _need_cuda(A.hi, A.lo, B.hi, B.lo, bias)
+    for t in A.tensors() + B.tensors():
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("gemm_heads expects 2-D bf16 operands with a contiguous last dimension")
+    exp_a = (K, M) if a_mn else (M, K)
+    exp_b = (K, N) if b_mn else (N, K)
+    if tuple(A.hi.shape) != exp_a or tuple(B.hi.shape) != exp_b:
+        raise ValueError(f"gemm shape mismatch: A {tuple(A.hi.shape)} vs {exp_a}, B {tuple(B.hi.shape)} vs {exp_b}")
     if k_splits > 1:
-        out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
-        for (a, b) in passes:
-            gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_ATOMIC_ADD, k_splits=k_splits, prec=prec)
         if bias is not None or relu:
             raise ValueError("bias/ReLU cannot be combined with split-K")
-        return out
-    out = None
-    for i, (a, b) in enumerate(passes):
-        last = i == len(passes) - 1
-        out = gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_STORE if i == 0 else MMG_ACCUMULATE,
-                   bias=bias if last else None, relu=relu and last, prec=prec)
+        out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
+        mode = MMG_ATOMIC_ADD
+    else:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.hi.device)
+        mode = MMG_STORE
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm bias must be contiguous float32 [N]")
+    check(_lib.load().mmg_gemm_split(_p(A.hi), _p(A.lo), A.hi.stride(0), int(a_mn), _p(B.hi), _p(B.lo), B.hi.stride(0),
+                                     int(b_mn), _p(out), out.stride(0), M, N, K, 1.0, _p(bias), int(relu), mode,
+                                     k_splits, _stream()), "mmg_gemm_split")
     return out
 
 
@@ -191,6 +205,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
                                _stream()),
           "mmg_gemm")
     return out
+
+
+def _n_segments(A: "_Operand", B: "_Operand") -> int:
+    """K segments of a split-precision contraction: hi.hi (+ hi.lo) (+ lo.hi)."""
+    return 1 + (B.lo is not None) + (A.lo is not None)
 
 
 def _split_k_for(M: int, N: int, K: int) -> int:
@@ -362,7 +381,7 @@ class _LinearFn(torch.autograd.Function):
         dzo = _Operand.of(dz, prec)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
-            ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
+            ks = _split_k_for(D, E, Bn * _n_segments(dzo, xo)) if prec == "bf16" else 1
             dw = gemm_heads(dzo, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(D, dtype=torch.float32, device=dy.device)
@@ -454,7 +473,7 @@ class _ProjNormFn(torch.autograd.Function):
             dz = _Operand(l2norm_bwd(dy, y, inv, True, False)[0])
         dw = dx = None
         if ctx.needs_input_grad[1]:
-            ks = _split_k_for(D, E, Bn) if prec == "bf16" else 1
+            ks = _split_k_for(D, E, Bn * _n_segments(dz, xo)) if prec == "bf16" else 1
             dw = gemm_heads(dz, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if need_dx:
             dx = gemm_heads(dz, wo, Bn, E, D, b_mn=True, prec=prec)
