@@ -87,7 +87,8 @@ def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] 
 
 class _ShardedInfoNCEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None):
+    def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None, pending=None):
+        ctx.pending = pending
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         bl, D = a_local.shape
@@ -123,12 +124,20 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
                                            b32_local, diag, need_dscale=ctx.needs_input_grad[2])
         dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)
-        _reduce_scatter_sum(dB, dB_all, group)
+        pending = ctx.pending
+        if pending is not None and pending.get("deferred") and dist.get_backend(group) != "gloo":
+            # The column-side gradients travel while the caller's row-side (image head) backward runs: the current
+            # stream only waits for the reduce-scatter in the hook sharded_info_nce() put on b_local, i.e. right before
+            # the column side's producer runs its backward.
+            pending["work"] = dist.reduce_scatter_tensor(dB, dB_all, op=dist.ReduceOp.SUM, group=group, async_op=True)
+            pending["keep"] = dB_all  # stays referenced until the wait
+        else:
+            _reduce_scatter_sum(dB, dB_all, group)
         dscale = None
         if ctx.needs_input_grad[2]:
             dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
             dscale = (dls / s).reshape(ctx.scale_shape)
-        return dA, dB, dscale, None, None, None, None
+        return dA, dB, dscale, None, None, None, None, None
 
 
 def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, group=None, prec: Optional[str] = None,
@@ -140,7 +149,20 @@ def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, 
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_local.device)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return ops.info_nce(a_local, b_local, logit_scale, prec=prec)
-    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels, gathered)
+    pending = {}
+    if torch.is_grad_enabled() and b_local.requires_grad:
+        # tensor hooks run right before b_local's producer executes its backward (or before .grad accumulation for a
+        # leaf): that is where the asynchronous reduce-scatter of the column-side gradients is waited for
+        def _wait(grad, _pending=pending):
+            work = _pending.pop("work", None)
+            if work is not None:
+                work.wait()  # stream-ordered, no host sync
+            _pending.pop("keep", None)
+            return grad
+
+        b_local.register_hook(_wait)
+        pending["deferred"] = True
+    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels, gathered, pending)
 
 
 def allreduce_gradients(*modules: torch.nn.Module, group=None) -> None:
