@@ -440,7 +440,7 @@ struct EpiGradT {
   // One thread = one accumulator row, 32 columns at a time.  (Variants measured slower at 32768^2 x 512 and not kept,
   // coefficient launches 1.02-1.06 ms as written: column terms read from global memory instead of shared memory,
   // 1.23 ms; 16-column TMEM loads issued one step ahead, 1.28 ms; 32-column loads into two register buffers issued one
-  // chunk ahead, 1.18 ms.)
+  // chunk ahead, 1.18 ms; one 64-column TMEM load per staging box, 1.29 ms.)
   template <int BN, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                               int q, int lane, const float* cs, float sl2, const CUtensorMap* cmap,
