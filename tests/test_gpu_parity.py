@@ -256,6 +256,50 @@ def test_bf16_full_size_properties(mm):
         assert rel_err(dA.cpu().numpy()[idx], ref_da) < GRAD["bf16"]
 
 
+@pytest.mark.parametrize("rows,cols,d,off", [(32768, 32768, 512, 0), (16384, 131072, 1024, 5 * 16384)])
+def test_bf16_baseline_full_sizes(mm, rows, cols, d, off):
+    """BASELINE.json's full sizes -- config 3 (global batch 32768, D = 512) and one rank's share of config 5 (16384 local
+    rows x 131072 global columns, D = 1024, rank 5 of 8): the fused path end to end with size-independent checks --
+    sampled rows against float64, one fused backward launch, scratch independent of rows x cols."""
+    ops = mm.ops
+    gen = torch.Generator(device="cuda").manual_seed(rows + d)
+    a = torch.nn.functional.normalize(torch.randn(rows, d, device="cuda", generator=gen), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(cols, d, device="cuda", generator=gen), dim=1)
+    b[off:off + rows] = torch.nn.functional.normalize(b[off:off + rows] + 0.5 * a, dim=1)
+    s = torch.tensor(float(np.float32(1 / 0.07)), device="cuda")
+    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    rs, cs, dg = ops.infonce_forward_raw(ab, bb, s, off, "bf16")
+    one = torch.ones((), device="cuda")
+    n0 = ops._lib.load().mmg_kernel_launch_count()
+    b32 = b[off:off + rows].contiguous()
+    dA, dB, dls = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, off, "bf16", a32=a, b32=b32, diag=dg)
+    torch.cuda.synchronize()
+    assert ops._lib.load().mmg_kernel_launch_count() - n0 == 3      # prep + matching-pair init + ONE fused launch
+    peak = torch.cuda.max_memory_allocated() - base
+    # outputs + paired-row copy (O(B*D)) + the coefficient scratch; a bf16 logit block alone would be rows*cols*2
+    assert peak < (2 * rows + cols) * d * 4 + (256 << 20), peak
+    assert peak < rows * cols * 2 or rows * cols * 2 < (1 << 30)
+    assert torch.isfinite(dA).all() and torch.isfinite(dB).all()
+    idx = np.random.RandomState(1).choice(rows, 32, replace=False)
+    a64, b64 = ab[idx].double().cpu().numpy(), bb.double().cpu().numpy()
+    sv = float(s.item())
+    cos = a64 @ b64.T
+    e = np.exp(sv * cos - sv)
+    assert rel_err(rs.cpu().numpy()[idx], e.sum(1)) < 2e-4
+    assert rel_err(dg.cpu().numpy()[idx], sv * cos[np.arange(32), off + idx]) < 1e-5
+    coef = sv * 0.5 / cols
+    g = e * (coef / e.sum(1)[:, None] + coef / cs.double().cpu().numpy()[None, :])
+    g[np.arange(32), off + idx] -= 2 * coef
+    # the matching-pair element uses the fp32 embeddings in the kernel path; everything else the bf16-rounded ones
+    ref_da = g @ b64
+    ref_da += (g[np.arange(32), off + idx])[:, None] * (b[off + idx].double().cpu().numpy() - b64[off + idx])
+    assert rel_err(dA.cpu().numpy()[idx], ref_da) < GRAD["bf16"]
+    assert abs(dls.item() - 0.0) < 1e3  # finite, sane magnitude (exact value checked at small sizes)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_multilinear_head_training_dropout(mm, prec):
     """MultiLinearHead in train mode: Linear -> ReLU -> Dropout(p) per hidden layer (projection.py:54-61).  The keep
