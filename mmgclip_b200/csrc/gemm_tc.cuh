@@ -1,9 +1,9 @@
 // mmgclip_b200 -- the one tensor-core mainloop every dense contraction on the hot path runs through.
 //
-//   acc[128 x BN] (fp32, TMEM) = A[128 x K] * B[BN x K]^T      (bf16 operands, tcgen05.mma kind::f16)
+//   acc[128 kCG x BN] (fp32, TMEM) = A[128 kCG x K] * B[BN x K]^T      (bf16 operands, tcgen05.mma kind::f16)
 //
-// Persistent, warp-specialised CTA (one per SM):
-//   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled shared-memory ring (kStages deep)
+// Persistent, warp-specialised CTA (one per SM; kCG = 2: CTA pairs driving one 256-row MMA):
+//   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled shared-memory ring (6-7 stages of 32 KB)
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes tiles
 //   warp 2      TMEM allocator : 2 accumulator stages x BN columns (BN = 256 -> all 512 TMEM columns)
 //   warps 4..11 epilogue       : tcgen05.ld the accumulator (32 lanes x 32 columns at a time) and apply a fused
@@ -11,7 +11,9 @@
 //
 // Each operand may be K-major (row-major [rows x K]) or MN-major ([K x rows], rows contiguous), chosen at run time
 // per problem, so no transposed copies of embeddings / gradients are ever made.  A launch can carry two independent
-// problems (used for dI and dT of one logit block, which alone would each fill < half the SMs) and a split-K factor.
+// problems (dI and dT of one logit block in the block-loop backward), a split-K factor, or up to three K segments
+// (operand pair per segment, one accumulator: the split-precision heads).  bwd_fused.cuh reuses the same roles and
+// epilogues for the one-launch backward.
 //
 // The epilogues are where the CLIP-specific fusion lives (see EpiLse / EpiGrad below): the logit tile is consumed
 // straight out of TMEM and never written to HBM.
@@ -25,8 +27,8 @@ constexpr int kBM = 128;        // UMMA M (rows per tile)
 constexpr int kBK = 64;         // K elements per pipeline stage (= one 128-byte swizzle span of bf16)
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit operands
 // Epilogue warps come in groups of four (one per TMEM lane quarter); an epilogue declares kWarps = 8 or 16, i.e. each
-// warp owns 32 accumulator rows and BN/2 or BN/4 of the tile's columns.  More warps = more latency hiding for the
-// MUFU / TMEM-load bound InfoNCE epilogues; with 16 the register file is re-balanced with setmaxnreg.
+// warp owns 32 accumulator rows and BN/2 or BN/4 of the tile's columns.  Everything instantiated uses 8: the 16-warp
+// form (register file re-balanced with setmaxnreg) measured slower, its staging boxes cost an operand-ring stage.
 
 struct GemmProblem {
   int M, N, K;           // logical extents (ragged edges are zero-filled by TMA and masked in the epilogue)
