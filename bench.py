@@ -104,12 +104,14 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None):
+def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None):
     cfg = {"workload": f"mmg-clip hot path: LinearProjectionLayer heads {E_IMG}->{D_PROJ} (image, text) + L2 normalise + "
                        f"symmetric CLIPLoss fwd+bwd to head-weight grads, global batch {GLOBAL_BATCH}, synthetic "
                        f"ConvNeXt-like / BERT-like features",
            "global_batch": GLOBAL_BATCH, "embedding_dim": E_IMG, "projection_dim": D_PROJ,
-           "parallelism": f"row-sharded x{n_gpus} (all-gather text embeddings, all-reduce column sums, reduce-scatter dT)",
+           "parallelism": f"row-sharded x{n_gpus} (all-gather text embeddings, all-reduce column sums, " + (
+               "dT slices reduce-added into their owner's buffer over NVLink peer memory by the fused backward kernel)"
+               if peer else "reduce-scatter dT)"),
            "l2": "step inputs rotate over distinct buffer sets; each step also streams > 126 MB of intermediates "
                  "(128 MiB coefficient blocks, fp32 gradients), so nothing survives in the 126 MB L2 between steps"}
     if n_sets is not None:
@@ -208,7 +210,8 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from mmgclip_b200 import _lib, ops
-    from mmgclip_b200.distributed import allreduce_gradients, gather_columns_async, sharded_info_nce
+    from mmgclip_b200.distributed import (allreduce_gradients, gather_columns_async, peer_reduce_active,
+                                          sharded_info_nce)
     from mmgclip_b200.projection import LinearProjectionLayer
     from oracle import clip_oracle as oc  # only for the synthetic-input recipe and the cpu_baseline leg
 
@@ -397,7 +400,7 @@ def run_gpu(args):
         "metric": METRIC, "value": B / (ms_value * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(world, n_sets=n_sets, graph=gstep is not None),
+        "config": workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active()),
         "loss": loss_value,
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,

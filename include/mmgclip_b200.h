@@ -154,6 +154,18 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
                     float* dlogscale_acc, int block_rows, int block_cols, void* workspace, size_t workspace_bytes,
                     mmg_stream_t stream);
 
+/* The same backward with the column-side gradient DISTRIBUTED over `n_owners` buffers (<= 8): column c accumulates into
+ * dB_owners[c / (cols/n_owners)] at row c % (cols/n_owners).  dB_owners is a HOST array of device pointers, each an fp32
+ * [cols/n_owners, D] buffer -- in the row-sharded multi-GPU run the ranks' own gradient buffers mapped into this process
+ * (NVLink peer memory, e.g. torch symmetric memory), so the gradient GEMM's TMA reduce-add IS the reduce-scatter: no
+ * [cols, D] staging buffer and no separate collective.  The caller initialises the owners' buffers (zero, or the
+ * matching-pair term via mmg_infonce_bwd_diag(init=1)) and synchronises the ranks before and after the call.
+ * bf16 path only; runs as the one fused persistent launch or returns MMG_ERR_UNSUPPORTED_SHAPE. */
+int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                           const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
+                           float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
+                           size_t workspace_bytes, mmg_stream_t stream);
+
 /* ---- literal cross-entropy on materialised logits (losses.py:28-44, 207-212) ----------------------------- */
 /* F.cross_entropy(logits[n, m], labels) pieces; labels: int64 DEVICE array [n] or NULL = arange(n) (needs n <= m).
  * lse[n] is kept for the backward.   loss_out[0] += coef * sum_r (lse[r] - logits[r, labels[r]]). */

@@ -46,6 +46,14 @@ struct BwdFusedParams {
   float* dlogscale_acc;
   unsigned int* doneA;  // [nblk], zeroed by the host before the launch
   unsigned int* doneB;  // [nblk]
+  int owner_rows;       // column-side gradient rows per owner: column c accumulates into dB map c / owner_rows at row
+                        // c % owner_rows (one owner = the whole of dB on a single GPU; in the row-sharded run every
+                        // rank owns cols / world rows and the maps point at the owners' buffers over NVLink)
+};
+
+constexpr int kMaxOwners = 8;
+struct BwdOwnerMaps {
+  CUtensorMap m[kMaxOwners];  // fp32 [owner_rows, D] output maps (box 32 x 32), one per owner
 };
 
 struct BwdItem {
@@ -162,7 +170,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
                          const __grid_constant__ CUtensorMap mGk, const __grid_constant__ CUtensorMap mGmn,
                          const __grid_constant__ CUtensorMap mGst, const __grid_constant__ CUtensorMap mdA,
-                         const __grid_constant__ CUtensorMap mdB, const BwdFusedParams p) {
+                         const __grid_constant__ BwdOwnerMaps mdB, const BwdFusedParams p) {
   using S = FusedSmem;
   constexpr int kStages = S::kStages;
   constexpr int BN = kFusedBN;
@@ -357,9 +365,16 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       } else {
         // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
         if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
-        const int m0 = (it.type == 1 ? rb * p.Rb : cb * p.Cb) + it.tm * 256 + half_off;
-        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * 256, p.D, half, q, lane, it.type == 1 ? &mdA : &mdB,
-                                 staging + ewarp * 4096);
+        int m0 = (it.type == 1 ? rb * p.Rb : cb * p.Cb) + it.tm * 256 + half_off;
+        const CUtensorMap* cmap = &mdA;
+        if (it.type == 2) {
+          // the owner of these 128 gradient rows (owner_rows is a multiple of 256: a tile never straddles owners); a
+          // remote owner's buffer is reached by the same TMA reduce-add, over NVLink
+          const int owner = m0 / p.owner_rows;
+          m0 -= owner * p.owner_rows;
+          cmap = &mdB.m[owner];
+        }
+        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * 256, p.D, half, q, lane, cmap, staging + ewarp * 4096);
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -417,12 +417,15 @@ size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
 
 int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
-                         float* dB, float* dlogscale_acc, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                         int* used) {
+                         float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st, int* used) {
   *used = 0;
   const FusedPlan f = fused_plan(rows, cols, D);
   if (!f.ok || workspace_bytes < f.total_bytes) return 0;
-  if (!out_tma_ok(dA, D) || !out_tma_ok(dB, D)) return 0;
+  if (n_owners < 1 || n_owners > kMaxOwners || (cols % n_owners) != 0 || ((cols / n_owners) % 256) != 0) return 0;
+  if (!out_tma_ok(dA, D)) return 0;
+  for (int i = 0; i < n_owners; ++i)
+    if (dB_owners[i] == nullptr || !out_tma_ok(dB_owners[i], D)) return 0;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return 0;
   BwdFusedParams p;
   memset(&p, 0, sizeof(p));
@@ -443,10 +446,12 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
   p.doneA = ctr;
   p.doneB = ctr + p.nblk;
+  p.owner_rows = cols / n_owners;
   cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)2 * p.nblk * sizeof(unsigned int), st);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
 
-  CUtensorMap mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA, mdB;
+  CUtensorMap mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA;
+  BwdOwnerMaps mdB;
   int rc;
   const long long grow = (long long)f.nbuf * f.Rb;
   if ((rc = make_tmap(&mAk, a_hat, D, rows, D, kBM)) != 0) return rc;
@@ -457,7 +462,10 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   if ((rc = make_tmap(&mGmn, workspace, f.Cb, grow, f.Cb, kBK)) != 0) return rc;
   if ((rc = make_tmap(&mGst, workspace, f.Cb, grow, f.Cb, 32)) != 0) return rc;
   if ((rc = make_out_tmap_f32(&mdA, dA, D, rows, D)) != 0) return rc;
-  if ((rc = make_out_tmap_f32(&mdB, dB, D, cols, D)) != 0) return rc;
+  for (int i = 0; i < kMaxOwners; ++i) {
+    const int o = i < n_owners ? i : 0;  // unused slots repeat owner 0 (never selected)
+    if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, cols / n_owners, D)) != 0) return rc;
+  }
 
   auto kern = infonce_bwd_fused_kernel;
   static bool configured = false;

@@ -16,12 +16,57 @@ uses the CUDA kernels.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Callable, Optional
 
 import torch
 import torch.distributed as dist
 
 from . import ops
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Column-side gradients over NVLink peer memory: every rank owns one [B/R, D] fp32 buffer in torch symmetric memory; the
+# fused backward's gradient slices TMA-reduce-add straight into the owner's buffer (mmg_infonce_bwd_owners), so the
+# gradient GEMM *is* the reduce-scatter.  MMGCLIP_B200_PEER_REDUCE=0 (or any failure to set the mapping up, which is a
+# collective decision) falls back to a [B, D] staging buffer + NCCL reduce-scatter.
+# ---------------------------------------------------------------------------------------------------------------------
+_peer_cache = {}
+
+
+class _PeerBuffers:
+    def __init__(self, rows, D, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.own = symm_mem.empty((rows, D), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.own, group=group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def pre_sync(self):
+        self.handle.barrier(channel=0)
+
+    def post_sync(self):
+        self.handle.barrier(channel=1)
+
+
+def peer_reduce_active() -> bool:
+    """True once a sharded backward has run with the NVLink peer reduction (i.e. not on the NCCL fallback)."""
+    return any(v is not None for v in _peer_cache.values())
+
+
+def _peer_buffers(rows, D, device, group):
+    if os.environ.get("MMGCLIP_B200_PEER_REDUCE", "1") == "0":
+        return None
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) != "nccl" or world > 8 or rows % 256 != 0 or D % 256 != 0 or D < 256:
+        return None
+    key = (rows, D, device.index, id(group))
+    if key not in _peer_cache:
+        try:
+            _peer_cache[key] = _PeerBuffers(rows, D, device, group)
+        except Exception as e:  # noqa: BLE001  (no symmetric-memory support on this platform / torch build)
+            warnings.warn(f"mmgclip_b200: NVLink peer reduction unavailable ({e}); using NCCL reduce-scatter")
+            _peer_cache[key] = None
+    return _peer_cache[key]
 
 
 def _reduce_scatter_sum(out: torch.Tensor, full: torch.Tensor, group) -> None:
@@ -121,6 +166,20 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         # fp32 embeddings for the matching-pair term: the columns paired with this rank's rows are its own b rows
         if not (prec == "bf16" and a32.dtype == torch.float32):
             a32 = b32_local = None
+        peer = None
+        if kernels is _Kernels and prec == "bf16" and a_op.is_cuda:
+            peer = _peer_buffers(bl, D, a_op.device, group)
+        if peer is not None:
+            # gradient GEMM + reduce-scatter in one kernel: the slices add into their owners' buffers over NVLink
+            dA, own, dls = ops.infonce_backward_owners(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off,
+                                                       peer.own, peer.ptrs, peer.pre_sync, peer.post_sync, a32=a32,
+                                                       b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2])
+            dB = own.clone()  # the symmetric buffer is reused by the next step
+            dscale = None
+            if ctx.needs_input_grad[2]:
+                dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
+                dscale = (dls / s).reshape(ctx.scale_shape)
+            return dA, dB, dscale, None, None, None, None, None
         dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
                                            b32_local, diag, need_dscale=ctx.needs_input_grad[2])
         dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)

@@ -8,6 +8,7 @@ Arithmetic follows the reference lines cited in ``include/mmgclip_b200.h``; clos
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional, Tuple
 
@@ -324,6 +325,48 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
                               _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
                               _stream()), "mmg_infonce_bwd")
     return dA, dB, dls
+
+
+def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, own: torch.Tensor,
+                            owner_ptrs, pre_sync, post_sync, a32=None, b32=None, diag=None, need_dscale: bool = True):
+    """Row-sharded backward whose column-side gradient goes straight to its owners (mmg_infonce_bwd_owners).
+
+    ``own`` is this rank's fp32 [cols/world, D] gradient buffer, ``owner_ptrs`` the device pointers of every rank's buffer
+    as mapped into this process (NVLink peer memory), in rank order.  ``pre_sync`` / ``post_sync`` are stream-ordered
+    cross-rank barriers: every owner's buffer is initialised before anybody adds into it, and all adds have landed before
+    anybody reads its own.  Returns (dA [rows, D], own, sum g*cos or None)."""
+    rows, D = a.shape
+    cols = b.shape[0]
+    world = len(owner_ptrs)
+    if rows * world != cols or diag_offset % rows != 0 or tuple(own.shape) != (rows, D) or own.dtype != torch.float32:
+        raise ValueError("infonce_backward_owners: every rank must own cols/world rows paired with its local rows")
+    dev = a.device
+    lib = _lib.load()
+    rinv = torch.empty(rows, dtype=torch.float32, device=dev)
+    cinv = torch.empty(cols, dtype=torch.float32, device=dev)
+    scal = torch.empty(4, dtype=torch.float32, device=dev)
+    gl = grad_loss.reshape(()).to(torch.float32).contiguous()
+    diag_fp32 = a32 is not None and b32 is not None and diag is not None
+    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+                                   int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
+    dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
+    if diag_fp32:
+        dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        cinvm = cinv[diag_offset:diag_offset + rows]
+        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
+                                       _p(dA), _p(own), _p(dls), 1, _stream()), "mmg_infonce_bwd_diag")
+    else:
+        dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+        own.zero_()
+    nbytes = lib.mmg_infonce_workspace_bytes(_PREC["bf16"], rows, cols, D)
+    ws = _workspace(dev, nbytes)
+    ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
+    pre_sync()
+    check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv), _p(scal),
+                                     _p(dA), ptrs, world, _p(dls), _p(ws), ws.numel(), _stream()),
+          "mmg_infonce_bwd_owners")
+    post_sync()
+    return dA, own, dls
 
 
 # ----------------------------------------------------------------------------------------------------------------
