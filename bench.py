@@ -104,7 +104,7 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None):
+def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None, symm=None):
     cfg = {"workload": f"mmg-clip hot path: LinearProjectionLayer heads {E_IMG}->{D_PROJ} (image, text) + L2 normalise + "
                        f"symmetric CLIPLoss fwd+bwd to head-weight grads, global batch {GLOBAL_BATCH}, synthetic "
                        f"ConvNeXt-like / BERT-like features",
@@ -114,6 +114,8 @@ def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=Non
                if peer else "reduce-scatter dT)"),
            "l2": "step inputs rotate over distinct buffer sets; each step also streams > 126 MB of intermediates "
                  "(128 MiB coefficient blocks, fp32 gradients), so nothing survives in the 126 MB L2 between steps"}
+    if symm:
+        cfg["small_allreduces"] = "torch symmetric memory one-shot / two-shot kernels over NVLink (column sums, loss, head grads)"
     if n_sets is not None:
         cfg["input_sets"] = n_sets
     if graph is not None:
@@ -211,7 +213,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from mmgclip_b200 import _lib, ops
     from mmgclip_b200.distributed import (allreduce_gradients, gather_columns_async, peer_reduce_active,
-                                          sharded_info_nce)
+                                          sharded_info_nce, symm_allreduce_active)
     from mmgclip_b200.projection import LinearProjectionLayer
     from oracle import clip_oracle as oc  # only for the synthetic-input recipe and the cpu_baseline leg
 
@@ -400,7 +402,8 @@ def run_gpu(args):
         "metric": METRIC, "value": B / (ms_value * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active()),
+        "config": workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active(),
+                                  symm=symm_allreduce_active()),
         "loss": loss_value,
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,

@@ -71,6 +71,52 @@ def _peer_buffers(rows, D, device, group):
     return _peer_cache[key]
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Small all-reduces (column sums [B], the loss scalar, the flat head gradients) through torch symmetric memory: one-shot /
+# two-shot kernels that read the peers' buffers over NVLink cost a few microseconds, where an NCCL all-reduce inside a
+# replayed graph costs tens (launch + 8-way rendezvous) -- and an 8-GPU step has three of them on its critical path.
+# MMGCLIP_B200_SYMM_ALLREDUCE=0, a non-NCCL backend or a failed set-up (a collective decision) select dist.all_reduce.
+# ---------------------------------------------------------------------------------------------------------------------
+_symm_vectors = {}
+
+
+class _SymmVector:
+    """A persistent fp32 vector in symmetric memory with an in-place-style sum across the group."""
+
+    def __init__(self, numel, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.numel = (numel + 1023) // 1024 * 1024
+        self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group=self.group)
+        self.name = self.group.group_name
+
+    def all_reduce(self) -> torch.Tensor:
+        """Sum of every rank's buffer (a new tensor for small vectors, the buffer itself for large ones)."""
+        if self.numel * 4 <= (1 << 20):
+            return torch.ops.symm_mem.one_shot_all_reduce(self.buf, "sum", self.name)
+        return torch.ops.symm_mem.two_shot_all_reduce_(self.buf, "sum", self.name)
+
+
+def _symm_vector(tag, numel, device, group):
+    if os.environ.get("MMGCLIP_B200_SYMM_ALLREDUCE", "1") == "0" or device.type != "cuda":
+        return None
+    if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 8:
+        return None
+    key = (tag, numel, device.index, id(group))
+    if key not in _symm_vectors:
+        try:
+            _symm_vectors[key] = _SymmVector(numel, device, group)
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"mmgclip_b200: symmetric-memory all-reduce unavailable ({e}); using NCCL")
+            _symm_vectors[key] = None
+    return _symm_vectors[key]
+
+
+def symm_allreduce_active() -> bool:
+    return any(v is not None for v in _symm_vectors.values())
+
+
 def _reduce_scatter_sum(out: torch.Tensor, full: torch.Tensor, group) -> None:
     """out = this rank's slice of sum_over_ranks(full).  NCCL: one reduce-scatter; gloo (CPU host-logic tests) has no
     reduce-scatter, so all-reduce and slice."""
@@ -91,8 +137,8 @@ class _Kernels:
         return ops._operand(t, prec)
 
     @staticmethod
-    def forward(a_op, b_all_op, scale, diag_offset, prec):
-        return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec)
+    def forward(a_op, b_all_op, scale, diag_offset, prec, colsum=None):
+        return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec, colsum=colsum)
 
     @staticmethod
     def loss(rowsum, colsum_slice, diag, scale, inv_two_b):
@@ -151,10 +197,21 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
             dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
         off = rank * bl
-        rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec)
-        dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+        cvec = _symm_vector("colsum", B, a_local.device, group) if kernels is _Kernels else None
+        if cvec is not None:
+            cvec.buf.zero_()  # the partial column sums accumulate straight into the symmetric buffer
+            rowsum, _, diag = kernels.forward(a_op, b_all, s, off, prec, colsum=cvec.buf[:B])
+            colsum = cvec.all_reduce()[:B]
+        else:
+            rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec)
+            dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
         loss = kernels.loss(rowsum, colsum[off:off + bl], diag, s, 0.5 / B)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        lvec = _symm_vector("loss", 1, a_local.device, group) if kernels is _Kernels else None
+        if lvec is not None:
+            lvec.buf[:1].copy_(loss.reshape(1))
+            loss = lvec.all_reduce()[0]
+        else:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
         ctx.scale_shape = scale.shape
         ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach(), diag)
@@ -234,8 +291,14 @@ def allreduce_gradients(*modules: torch.nn.Module, group=None) -> None:
     grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
     if not grads:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    n = sum(g.numel() for g in grads)
+    vec = _symm_vector("grads", n, grads[0].device, group) if all(g.dtype == torch.float32 for g in grads) else None
+    if vec is not None:
+        torch.cat([g.reshape(-1) for g in grads], out=vec.buf[:n])
+        flat = vec.all_reduce()
+    else:
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     o = 0
     for g in grads:
         g.copy_(flat[o:o + g.numel()].view_as(g))
