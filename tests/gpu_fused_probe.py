@@ -59,11 +59,9 @@ def main():
     print(f"{rows}x{cols}: block loop {t_loop:.3f} ms ({3 * f / t_loop / 1e9:.0f} TF exec)", flush=True)
     cfgs = [dict()]
     if not quick:
-        cfgs += [dict(MMG_FUSED_KSL=16), dict(MMG_FUSED_KSL_T=64), dict(MMG_FUSED_NBUF=3), dict(MMG_FUSED_NBUF=3, MMG_FUSED_KSL_T=64),
-                 dict(MMG_FUSED_RB=4096, MMG_FUSED_CB=4096, MMG_FUSED_NBUF=3, MMG_FUSED_KSL=64),
-                 dict(MMG_FUSED_RB=8192, MMG_FUSED_CB=2048, MMG_FUSED_NBUF=3, MMG_FUSED_KSL_T=128),
-                 dict(MMG_FUSED_RB=8192, MMG_FUSED_CB=4096, MMG_FUSED_NBUF=3, MMG_FUSED_KSL=64, MMG_FUSED_KSL_T=128),
-                 dict(MMG_FUSED_NBUF=6), dict()]
+        cfgs += [dict(MMG_FUSED_KSL_T=16), dict(MMG_FUSED_KSL=16, MMG_FUSED_KSL_T=32), dict(MMG_FUSED_NBUF=5),
+                 dict(MMG_FUSED_RB=2048, MMG_FUSED_CB=2048), dict(MMG_FUSED_RB=4096, MMG_FUSED_CB=1024),
+                 dict(MMG_FUSED_RB=2048, MMG_FUSED_CB=4096, MMG_FUSED_KSL=64, MMG_FUSED_KSL_T=32), dict()]
     for c in cfgs:
         c = {k: v for k, v in c.items() if not (k == "MMG_FUSED_RB" and rows % v) and not (k == "MMG_FUSED_CB" and cols % v)}
         setenv(**c)

@@ -34,6 +34,8 @@ def _problem(rows, cols, d, off, seed=3):
 
 
 @pytest.mark.parametrize("rows,cols,d,off,cfg", [
+    (256, 256, 256, 0, {}),
+    (256, 1024, 256, 768, {}),
     (512, 512, 256, 0, {}),
     (768, 768, 1024, 0, {}),
     (1024, 2048, 512, 512, {}),
