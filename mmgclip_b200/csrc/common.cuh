@@ -219,30 +219,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
       : "memory");
 }
 
-// Same, 16 columns.
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-// tcgen05.wait::ld with the destination registers of an in-flight load tied to it ("+r"): when a load is issued one
-// step ahead of its use (software pipelining) nothing else tells the compiler that reads of those registers must stay
-// below the wait.
-__device__ __forceinline__ void tmem_ld_wait_tied16(float (&v)[16]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-
 // 16 TMEM lanes x 32 fp32 columns in the mma-fragment layout: thread l holds rows {l/4, l/4 + 8} (relative to the lane
 // field of taddr) and, for each 8-column group g = 0..3, columns 8g + 2*(l%4) + {0,1}:
 //     v[4g + 2h + e] = D[row l/4 + 8h][col 8g + 2*(l%4) + e]
