@@ -34,7 +34,7 @@ struct BwdFusedParams {
   int Rb, Cb;          // block shape (multiples of 256 that divide rows / cols)
   int nbc, nblk;       // column blocks per block row; blocks in total (row-major over the block grid)
   int nbuf;            // coefficient scratch buffers
-  int tAm, tAn, tDn;   // Rb/256, Cb/256, D/256
+  int tAm, tAn, tDn;   // Rb/256, Cb/BN, D/BN
   int kslI, kslT;      // 64-wide K blocks per dA slice / per dB slice
   int sI, sT;          // slices per dA tile (Cb/64/kslI) / per dB tile (Rb/64/kslT)
   int nA, nBI, nB;     // items per block: coefficient tiles; dA slices; all gradient slices
@@ -127,12 +127,12 @@ __device__ __forceinline__ unsigned int atom_acq_rel_cta_add(unsigned int* smem_
 
 // A coefficient tile is published (doneA) once per CTA: every epilogue warp waits for its own bulk stores, then bumps a
 // shared-memory counter; whoever arrives last (acq_rel at CTA scope chains the others' completed stores in) pays for the
-// one gpu-scope release.  Nobody waits for anybody.  Four slots: warps are never more than two tiles apart (two TMEM
-// accumulator stages), so a slot is never reused before all eight arrivals of its previous use.
+// one gpu-scope release.  Nobody waits for anybody.  Eight slots: warps are never more than three tiles apart (at most
+// four TMEM accumulator stages), so a slot is never reused before all eight arrivals of its previous use.
 __device__ __forceinline__ void publish_tile(unsigned int* pub_cnt, unsigned int seq, unsigned int* done_ctr, int lane) {
   if (lane == 0) {
     tma_store_wait_all();
-    const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 3u), 1u);
+    const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 7u), 1u);
     if ((old & 7u) == 7u) {
       fence_proxy_async_all();
       red_release_gpu_add(done_ctr, 1u);
@@ -160,21 +160,28 @@ __device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned i
   __syncwarp();
 }
 
-constexpr int kFusedBN = 256;
+// BN = columns of a work item's accumulator tile (256 rows x BN): 256 -> two TMEM accumulator stages, 128 -> four.  With
+// four the MMA issuer could run three items ahead of the epilogue warps and absorb the bursts of coefficient tiles (their
+// epilogue lasts ~2x their MMAs) -- but a 256 x 128 x 16 MMA reads 8 KB of operands per SM every 64 clocks, i.e. all of
+// the 128 B/clk of shared-memory bandwidth, before TMA writes and epilogue traffic: measured 5.9 vs 2.6 ms at 32768^2.
+// MMG_FUSED_BN=128 keeps the variant reachable; everything uses 256.
 using FusedGrad = EpiGradT<8>;
-using FusedSmem = GemmSmem<kFusedBN, 2, 8 * 4096, FusedGrad::kScratchBytes>;
+template <int BN>
+using FusedSmemT = GemmSmem<BN, 2, 8 * 4096, FusedGrad::kScratchBytes>;
 constexpr int kFusedThreads = 32 * (4 + 8);
 
+template <int BN>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
                          const __grid_constant__ CUtensorMap mGk, const __grid_constant__ CUtensorMap mGmn,
                          const __grid_constant__ CUtensorMap mGst, const __grid_constant__ CUtensorMap mdA,
                          const __grid_constant__ BwdOwnerMaps mdB, const BwdFusedParams p) {
-  using S = FusedSmem;
+  using S = FusedSmemT<BN>;
   constexpr int kStages = S::kStages;
-  constexpr int BN = kFusedBN;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr int kAcc = 512 / BN;          // accumulator stages: all 512 TMEM columns
+  constexpr uint32_t kTmemCols = 512;
+  constexpr int kBHalf = BN / 2;          // B-operand rows each CTA of the pair stages
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0u) {
@@ -190,9 +197,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  unsigned int* pub_cnt = reinterpret_cast<unsigned int*>(bars) + 96;  // [4] arrival counters of the publish slots
+  uint64_t* tempty_bar = bars + 2 * kStages + kAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAcc);
+  unsigned int* pub_cnt = reinterpret_cast<unsigned int*>(bars) + 96;  // [8] arrival counters of the publish slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,11 +218,11 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       mbar_init(&full_bar[i], 2);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8 * 2);
     }
-    for (int i = 0; i < 4; ++i) pub_cnt[i] = 0u;
+    for (int i = 0; i < 8; ++i) pub_cnt[i] = 0u;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg2(tmem_slot, kTmemCols);
@@ -242,7 +249,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         wait_counter(p.doneA + it.blk, wantA, lane);
         verified = it.blk;
       }
-      const int half_off = static_cast<int>(cta_rank) * kBM;
+      const int half_off = static_cast<int>(cta_rank) * kBM;     // this CTA's 128 of the tile's 256 rows (A operand)
+      const int n_half = static_cast<int>(cta_rank) * kBHalf;    // this CTA's half of the tile's BN columns (B operand)
       for (int kb = 0; kb < it.nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -253,23 +261,23 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           const int k0 = (it.kb0 + kb) * kBK;
           if (it.type == 0) {
             tma_load_2d_cg2(&mAk, &full_bar[stage], a_dst, k0, rb * p.Rb + it.tm * 256 + half_off, kEvictNormal);
-            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, cb * p.Cb + it.tn * 256 + half_off, kEvictNormal);
+            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, cb * p.Cb + it.tn * BN + n_half, kEvictNormal);
           } else if (it.type == 1) {
             // dA[rows] += g . b[cols]:  A = g (K-major, K = block columns),  B = b (MN-major: [K = column index][N = D])
             tma_load_2d_cg2(&mGk, &full_bar[stage], a_dst, k0, buf * p.Rb + it.tm * 256 + half_off, kEvictNormal);
-            const int n0 = it.tn * 256 + half_off;
+            const int n0 = it.tn * BN + n_half;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < kBHalf / 64; ++i)
               tma_load_2d_cg2(&mBmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, cb * p.Cb + k0, kEvictNormal);
           } else {
             // dB[cols] += g^T . a[rows]:  A = g (MN-major: [K = block row][M = block column]),  B = a (MN-major)
             const int m0 = it.tm * 256 + half_off;
-            const int n0 = it.tn * 256 + half_off;
+            const int n0 = it.tn * BN + n_half;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
               tma_load_2d_cg2(&mGmn, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, buf * p.Rb + k0, kEvictNormal);
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < kBHalf / 64; ++i)
               tma_load_2d_cg2(&mAmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, rb * p.Rb + k0, kEvictNormal);
           }
         }
@@ -284,8 +292,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       uint32_t phase = 0;
       int n = 0;
       while (cur.next(p, it)) {
-        const int acc_stage = n & 1;
-        const uint32_t acc_phase = (n >> 1) & 1;
+        const int acc_stage = n % kAcc;
+        const uint32_t acc_phase = (n / kAcc) & 1;
         ++n;
         mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -314,10 +322,10 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (n > 0) {
-        const int last = n - 1;
-        mbar_wait(&tempty_bar[last & 1], (last >> 1) & 1);  // the peer's remote arrivals have landed
-      }
+      // every outstanding accumulator stage has been released (the peer's remote arrivals have landed) before the
+      // leader's barriers die
+      for (int last = n - 1; last >= 0 && last > n - 1 - kAcc; --last)
+        mbar_wait(&tempty_bar[last % kAcc], (last / kAcc) & 1);
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs) =====================
@@ -341,8 +349,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         publish_tile(pub_cnt, a_seq++, p.doneA + pending, lane);
         pending = -1;
       }
-      const int acc_stage = n & 1;
-      const uint32_t acc_phase = (n >> 1) & 1;
+      const int acc_stage = n % kAcc;
+      const uint32_t acc_phase = (n / kAcc) & 1;
       ++n;
       const int rb = it.blk / p.nbc, cb = it.blk - rb * p.nbc;
       const int buf = it.blk % p.nbuf;
@@ -359,7 +367,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         gp.cinv = p.cinv + cb * p.Cb;
         gp.diag_offset = rb * p.Rb + p.diag_offset - cb * p.Cb;
         gp.g_row_off = buf * p.Rb;
-        FusedGrad::run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * 256, p.Rb, p.Cb, half, q, lane, ewarp,
+        FusedGrad::run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
                            epi_scratch + acc_stage * BN + half * (BN / 2), &mGst, staging, 0, carry);
         pending = it.blk;
       } else {
@@ -374,7 +382,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           m0 -= owner * p.owner_rows;
           cmap = &mdB.m[owner];
         }
-        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * 256, p.D, half, q, lane, cmap, staging + ewarp * 4096);
+        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * BN, p.D, half, q, lane, cmap, staging + ewarp * 4096);
       }
       tcgen05_fence_before();
       __syncwarp();

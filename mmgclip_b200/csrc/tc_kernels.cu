@@ -434,7 +434,8 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   p.nbc = cols / f.Cb;
   p.nblk = (rows / f.Rb) * p.nbc;
   p.nbuf = f.nbuf;
-  p.tAm = f.Rb / 256; p.tAn = f.Cb / 256; p.tDn = D / 256;
+  const int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
+  p.tAm = f.Rb / 256; p.tAn = f.Cb / BN; p.tDn = D / BN;
   p.kslI = f.kslI; p.kslT = f.kslT;
   p.sI = (f.Cb / kBK) / f.kslI;
   p.sT = (f.Rb / kBK) / f.kslT;
@@ -455,7 +456,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   int rc;
   const long long grow = (long long)f.nbuf * f.Rb;
   if ((rc = make_tmap(&mAk, a_hat, D, rows, D, kBM)) != 0) return rc;
-  if ((rc = make_tmap(&mBk, b_hat, D, cols, D, kBM)) != 0) return rc;
+  if ((rc = make_tmap(&mBk, b_hat, D, cols, D, BN / 2)) != 0) return rc;
   if ((rc = make_tmap(&mAmn, a_hat, D, rows, D, kBK)) != 0) return rc;
   if ((rc = make_tmap(&mBmn, b_hat, D, cols, D, kBK)) != 0) return rc;
   if ((rc = make_tmap(&mGk, workspace, f.Cb, grow, f.Cb, kBM)) != 0) return rc;
@@ -467,19 +468,20 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, cols / n_owners, D)) != 0) return rc;
   }
 
-  auto kern = infonce_bwd_fused_kernel;
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::kTotal);
+  auto kern = BN == 128 ? infonce_bwd_fused_kernel<128> : infonce_bwd_fused_kernel<256>;
+  const int smem_bytes = BN == 128 ? FusedSmemT<128>::kTotal : FusedSmemT<256>::kTotal;
+  static bool configured[2] = {false, false};
+  if (!configured[BN == 128]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
-    configured = true;
+    configured[BN == 128] = true;
   }
   const int pairs = sm_count() / 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pairs * 2);
   cfg.blockDim = dim3(kFusedThreads);
-  cfg.dynamicSmemBytes = FusedSmem::kTotal;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
