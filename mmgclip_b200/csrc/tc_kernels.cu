@@ -224,10 +224,16 @@ static int prefetch_distance() {
 using EpiLse = EpiLseT<8>;
 using EpiGrad = EpiGradT<8>;
 struct TileCfg { int BN, cg; };
-static TileCfg pick_tile(int M, int N) {
+static TileCfg pick_tile(int M, int N, int work_items_per_tile = 0) {
   TileCfg c;
   c.BN = N > 128 ? 256 : 128;
   c.cg = (pair_enabled() && c.BN == 256 && M > 128) ? 2 : 1;
+  if (c.cg == 2 && work_items_per_tile > 0) {
+    // under-filled single-problem launch (e.g. a 4096-row head projection: 32 pair tiles on 74 pairs): twice as many
+    // single-CTA tiles of half the work fill the SMs instead
+    const long long pair_tiles = (long long)((M + 2 * kBM - 1) / (2 * kBM)) * ((N + c.BN - 1) / c.BN);
+    if (pair_tiles * work_items_per_tile * 2 <= sm_count()) c.cg = 1;
+  }
   return c;
 }
 
@@ -254,7 +260,7 @@ int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand&
   if (nseg < 1 || nseg > 3) return set_error(-1, "tc_gemm: 1..3 K segments (got %d)", nseg);
   if (nseg > 1 && ((seg_a != 0 && A1 == nullptr) || (seg_b != 0 && B1 == nullptr)))
     return set_error(-1, "tc_gemm: a K segment refers to a missing operand");
-  const TileCfg tcfg = pick_tile(M, N);
+  const TileCfg tcfg = pick_tile(M, N, k_splits < 1 ? 1 : k_splits);
   CUtensorMap ma, mb, ma1, mb1;
   int rc;
   if ((rc = make_operand_map(&ma, A0, M, K, kBM)) != 0) return rc;
