@@ -84,3 +84,59 @@ def test_fused_backward_vs_float64():
     assert rel_err(dA.cpu(), g @ Bm) < 4e-3
     assert rel_err(dB.cpu(), g.T @ A) < 4e-3
     assert abs(dls.item() - float((g * cos).sum())) < 4e-3 * max(1.0, abs(float((g * cos).sum())))
+
+
+@pytest.mark.parametrize("world,rank", [(2, 1), (4, 2), (8, 5)])
+def test_owner_distributed_column_gradients(world, rank):
+    """mmg_infonce_bwd_owners on one GPU: the column-side gradient is spread over `world` separate buffers (what the ranks'
+    NVLink-mapped buffers are in the multi-GPU run); stitched together they equal the ordinary dB."""
+    from mmgclip_b200 import ops
+    rows, d = 512, 256
+    cols = rows * world
+    off = rank * rows
+    ops_, a, b, ab, bb, s, rs, cs, diag = _problem(rows, cols, d, off, seed=21)
+    one = torch.ones((), device="cuda")
+    b32 = b[off:off + rows].contiguous()
+    dA0, dB0, dl0 = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, off, "bf16", a32=a, b32=b32, diag=diag)
+    bufs = [torch.zeros((rows, d), device="cuda") for _ in range(world)]   # the other owners start from zero
+    events = []
+    dA1, own, dl1 = ops.infonce_backward_owners(ab, bb, s, rs, cs, one, 0.5 / cols, off, bufs[rank],
+                                                [t.data_ptr() for t in bufs], lambda: events.append("pre"),
+                                                lambda: events.append("post"), a32=a, b32=b32, diag=diag)
+    torch.cuda.synchronize()
+    assert events == ["pre", "post"] and own is bufs[rank]
+    assert rel_err(dA1.cpu(), dA0.cpu()) < 2e-4
+    assert rel_err(torch.cat(bufs).cpu(), dB0.cpu()) < 2e-4
+    assert abs(dl1.item() - dl0.item()) <= 2e-4 * max(abs(dl0.item()), 1e-3)
+
+
+def test_gemm_split_single_launch_matches_three_products():
+    """mmg_gemm_split: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in one contraction over three K segments (all four operand
+    layouts, bias + ReLU epilogue, split-K)."""
+    from mmgclip_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 300, 520, 200
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            if (a_mn and M % 8) or (b_mn and N % 8):
+                M2, N2 = 304, 520
+            else:
+                M2, N2 = M, N
+            A = torch.randn((K, M2) if a_mn else (M2, K), device="cuda", generator=gen)
+            B = torch.randn((K, N2) if b_mn else (N2, K), device="cuda", generator=gen)
+            Ao, Bo = ops._Operand(*ops.cast_bf16_split(A)), ops._Operand(*ops.cast_bf16_split(B))
+            bias = torch.randn(N2, device="cuda", generator=gen)
+            out = ops.gemm_heads(Ao, Bo, M2, N2, K, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=True)
+            f = lambda t, mn: (t.t() if mn else t).double()  # noqa: E731
+            ref = (f(Ao.hi, a_mn) @ f(Bo.hi, b_mn).t() + f(Ao.hi, a_mn) @ f(Bo.lo, b_mn).t()
+                   + f(Ao.lo, a_mn) @ f(Bo.hi, b_mn).t() + bias.double()).clamp_min(0)
+            assert rel_err(out.cpu(), ref.cpu()) < 2e-6
+            exact = (f(A, a_mn) @ f(B, b_mn).t() + bias.double()).clamp_min(0)
+            assert rel_err(out.cpu(), exact.cpu()) < 3e-5          # the split keeps ~16 mantissa bits per operand
+    # split-K over the concatenated range (the dW shape: short and wide, long K)
+    M, N, K = 256, 384, 4096
+    A = torch.randn(K, M, device="cuda", generator=gen)
+    B = torch.randn(K, N, device="cuda", generator=gen)
+    Ao, Bo = ops._Operand(*ops.cast_bf16_split(A)), ops._Operand(*ops.cast_bf16_split(B))
+    out = ops.gemm_heads(Ao, Bo, M, N, K, a_mn=True, b_mn=True, k_splits=12)
+    assert rel_err(out.cpu(), (A.double().t() @ B.double()).cpu()) < 3e-5
