@@ -129,11 +129,12 @@ __device__ __forceinline__ unsigned int atom_acq_rel_cta_add(unsigned int* smem_
 // shared-memory counter; whoever arrives last (acq_rel at CTA scope chains the others' completed stores in) pays for the
 // one gpu-scope release.  Nobody waits for anybody.  Eight slots: warps are never more than three tiles apart (at most
 // four TMEM accumulator stages), so a slot is never reused before all eight arrivals of its previous use.
+template <int kEW>
 __device__ __forceinline__ void publish_tile(unsigned int* pub_cnt, unsigned int seq, unsigned int* done_ctr, int lane) {
   if (lane == 0) {
     tma_store_wait_all();
     const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 7u), 1u);
-    if ((old & 7u) == 7u) {
+    if ((old & (kEW - 1)) == kEW - 1) {  // last of the CTA's epilogue warps
       fence_proxy_async_all();
       red_release_gpu_add(done_ctr, 1u);
     }
@@ -165,19 +166,22 @@ __device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned i
 // epilogue lasts ~2x their MMAs) -- but a 256 x 128 x 16 MMA reads 8 KB of operands per SM every 64 clocks, i.e. all of
 // the 128 B/clk of shared-memory bandwidth, before TMA writes and epilogue traffic: measured 5.9 vs 2.6 ms at 32768^2.
 // MMG_FUSED_BN=128 keeps the variant reachable; everything uses 256.
-using FusedGrad = EpiGradT<8>;
-template <int BN>
-using FusedSmemT = GemmSmem<BN, 2, 8 * 4096, FusedGrad::kScratchBytes>;
-constexpr int kFusedThreads = 32 * (4 + 8);
+// kEW = epilogue warps per CTA (8 or 16).  With 16 a coefficient tile's epilogue takes about as long as its MMAs, but
+// the staging boxes (16 x 4 KB) cost one operand-ring stage and every thread is held to 96 registers: measured 2.65 vs
+// 2.61 ms at 32768^2 and 0.358 vs 0.353 ms at 4096 x 32768, i.e. no gain -- MMG_FUSED_EPI_WARPS=16 keeps it reachable.
+template <int BN, int kEW>
+using FusedSmemT = GemmSmem<BN, 2, kEW * 4096, EpiGradT<kEW>::kScratchBytes>;
 
-template <int BN>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <int BN, int kEW>
+__global__ void __launch_bounds__(32 * (4 + kEW), 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
                          const __grid_constant__ CUtensorMap mGk, const __grid_constant__ CUtensorMap mGmn,
                          const __grid_constant__ CUtensorMap mGst, const __grid_constant__ CUtensorMap mdA,
                          const __grid_constant__ BwdOwnerMaps mdB, const BwdFusedParams p) {
-  using S = FusedSmemT<BN>;
+  using S = FusedSmemT<BN, kEW>;
+  using FusedGrad = EpiGradT<kEW>;
+  using FusedStore = EpiStoreF32T<kEW>;
   constexpr int kStages = S::kStages;
   constexpr int kAcc = 512 / BN;          // accumulator stages: all 512 TMEM columns
   constexpr uint32_t kTmemCols = 512;
@@ -192,8 +196,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::kABytes;
   uint8_t* staging = sB + kStages * S::kBBytes;
-  float* epi_scratch = reinterpret_cast<float*>(staging + 8 * 4096);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 8 * 4096 + S::kScratch);
+  float* epi_scratch = reinterpret_cast<float*>(staging + kEW * 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEW * 4096 + S::kScratch);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
@@ -220,7 +224,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     }
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8 * 2);
+      mbar_init(&tempty_bar[i], kEW * 2);
     }
     for (int i = 0; i < 8; ++i) pub_cnt[i] = 0u;
     fence_barrier_init();
@@ -337,16 +341,16 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int pending = -1;     // block whose coefficient-tile stores of this warp are not yet published in doneA
     unsigned int a_seq = 0;  // coefficient tiles this warp has finished (identical across the CTA's epilogue warps)
     int verified = -1;    // scratch buffers of blocks [0, verified + nbuf] are known to be free
-    FusedGrad::Params gp;
+    typename FusedGrad::Params gp;
     gp.scale_ptr = p.scale; gp.scal = p.scal; gp.dlogscale_acc = p.dlogscale_acc; gp.dbg = 0;
-    EpiStoreF32::Params sp;
+    typename FusedStore::Params sp;
     sp.C = nullptr; sp.ldc = 0; sp.bias = nullptr; sp.alpha = 1.f; sp.alpha_ptr = nullptr; sp.mode = 1; sp.relu = 0;
     sp.use_tma = 1;
     while (cur.next(p, it)) {
       if (pending >= 0) {
         // publish the previous coefficient tile (deferred to here so the stores' latency is off the critical path, and
         // done BEFORE blocking on the next accumulator so it never depends on this item's progress)
-        publish_tile(pub_cnt, a_seq++, p.doneA + pending, lane);
+        publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
         pending = -1;
       }
       const int acc_stage = n % kAcc;
@@ -367,8 +371,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         gp.cinv = p.cinv + cb * p.Cb;
         gp.diag_offset = rb * p.Rb + p.diag_offset - cb * p.Cb;
         gp.g_row_off = buf * p.Rb;
-        FusedGrad::run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
-                           epi_scratch + acc_stage * BN + half * (BN / 2), &mGst, staging, 0, carry);
+        FusedGrad::template run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
+                           epi_scratch + acc_stage * BN + half * (BN / (kEW / 4)), &mGst, staging, 0, carry);
         pending = it.blk;
       } else {
         // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
@@ -382,7 +386,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           m0 -= owner * p.owner_rows;
           cmap = &mdB.m[owner];
         }
-        EpiStoreF32::run_tma<BN>(sp, tacc, m0, it.tn * BN, p.D, half, q, lane, cmap, staging + ewarp * 4096);
+        FusedStore::template run_tma<BN>(sp, tacc, m0, it.tn * BN, p.D, half, q, lane, cmap, staging + ewarp * 4096);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -391,7 +395,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
       }
     }
-    if (pending >= 0) publish_tile(pub_cnt, a_seq++, p.doneA + pending, lane);
+    if (pending >= 0) publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
     FusedGrad::finish(gp, carry, lane);
   }
 

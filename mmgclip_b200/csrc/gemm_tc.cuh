@@ -120,7 +120,8 @@ __device__ __forceinline__ TileCoord decode_virtual(int t, const GemmProblem& p0
 // ---------------------------------------------------------------------------------------------------------
 
 // C = alpha * acc (+ bias[col]) (ReLU) stored / accumulated / atomically added to fp32 row-major C.
-struct EpiStoreF32 {
+template <int kW>
+struct EpiStoreF32T {
   struct Params {
     float* C;
     long long ldc;
@@ -131,7 +132,7 @@ struct EpiStoreF32 {
     int relu;
     int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
   };
-  static constexpr int kWarps = 8;
+  static constexpr int kWarps = kW;
   static constexpr int kScratchBytes = 0;
   // one [32 rows x 32 fp32] (4 KB, 128B-swizzled) staging box per epilogue warp
   template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kWarps * 4096; }
@@ -253,6 +254,8 @@ struct EpiStoreF32 {
     }
   }
 };
+
+using EpiStoreF32 = EpiStoreF32T<8>;
 
 // Forward InfoNCE epilogue: the accumulator holds cosines cos[r][c] of a logit tile.  With the fixed shift m = s
 // (|cos| <= 1 => logits in [-s, s]) E = exp(s*cos - s) feeds the row sums AND the column sums with a single exp per

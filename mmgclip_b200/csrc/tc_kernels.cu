@@ -474,19 +474,24 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, cols / n_owners, D)) != 0) return rc;
   }
 
-  auto kern = BN == 128 ? infonce_bwd_fused_kernel<128> : infonce_bwd_fused_kernel<256>;
-  const int smem_bytes = BN == 128 ? FusedSmemT<128>::kTotal : FusedSmemT<256>::kTotal;
-  static bool configured[2] = {false, false};
-  if (!configured[BN == 128]) {
+  const int ew = env_int("MMG_FUSED_EPI_WARPS", 8) == 16 ? 16 : 8;
+  const int variant = (BN == 128 ? 1 : 0) + (ew == 16 ? 2 : 0);
+  auto kern = infonce_bwd_fused_kernel<256, 8>;
+  int smem_bytes = FusedSmemT<256, 8>::kTotal;
+  if (variant == 1) { kern = infonce_bwd_fused_kernel<128, 8>; smem_bytes = FusedSmemT<128, 8>::kTotal; }
+  if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
+  if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
+  static bool configured[4] = {false, false, false, false};
+  if (!configured[variant]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
-    configured[BN == 128] = true;
+    configured[variant] = true;
   }
   const int pairs = sm_count() / 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pairs * 2);
-  cfg.blockDim = dim3(kFusedThreads);
+  cfg.blockDim = dim3(32 * (4 + ew));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -27,7 +27,7 @@ def timeit(fn, iters=5):
 
 def setenv(**kw):
     for k in ("MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF", "MMG_FUSED_KSL", "MMG_FUSED_KSL_T",
-              "MMG_FUSED_BN"):
+              "MMG_FUSED_BN", "MMG_FUSED_EPI_WARPS"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -59,8 +59,8 @@ def main():
     print(f"{rows}x{cols}: block loop {t_loop:.3f} ms ({3 * f / t_loop / 1e9:.0f} TF exec)", flush=True)
     cfgs = [dict()]
     if not quick:
-        cfgs += [dict(MMG_FUSED_BN=128), dict(MMG_FUSED_BN=128, MMG_FUSED_KSL=16), dict(MMG_FUSED_BN=128, MMG_FUSED_NBUF=3),
-                 dict(), dict(MMG_FUSED_BN=128)]
+        cfgs += [dict(MMG_FUSED_EPI_WARPS=16), dict(), dict(MMG_FUSED_EPI_WARPS=16), dict(MMG_FUSED_EPI_WARPS=16, MMG_FUSED_KSL=16),
+                 dict(MMG_FUSED_EPI_WARPS=16, MMG_FUSED_NBUF=3)]
     for c in cfgs:
         c = {k: v for k, v in c.items() if not (k == "MMG_FUSED_RB" and rows % v) and not (k == "MMG_FUSED_CB" and cols % v)}
         setenv(**c)
