@@ -160,11 +160,14 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
  * (NVLink peer memory, e.g. torch symmetric memory), so the gradient GEMM's TMA reduce-add IS the reduce-scatter: no
  * [cols, D] staging buffer and no separate collective.  The caller initialises the owners' buffers (zero, or the
  * matching-pair term via mmg_infonce_bwd_diag(init=1)) and synchronises the ranks before and after the call.
- * bf16 path only; runs as the one fused persistent launch or returns MMG_ERR_UNSUPPORTED_SHAPE. */
+ * The owners may also be slices of a local staging buffer that a reduce-scatter then sends home; with n_parts > 1 one
+ * call covers only part `part` (0-based) of EVERY owner's columns -- dB_owners[i] is then the [cols/n_owners/n_parts, D]
+ * buffer of that part, dA accumulates across the calls -- so the reduce-scatter of one part travels while the next part
+ * is computed.  bf16 path only; runs as the one fused persistent launch or returns MMG_ERR_UNSUPPORTED_SHAPE. */
 int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                            const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
-                           float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
-                           size_t workspace_bytes, mmg_stream_t stream);
+                           float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
+                           void* workspace, size_t workspace_bytes, mmg_stream_t stream);
 
 /* ---- literal cross-entropy on materialised logits (losses.py:28-44, 207-212) ----------------------------- */
 /* F.cross_entropy(logits[n, m], labels) pieces; labels: int64 DEVICE array [n] or NULL = arange(n) (needs n <= m).

@@ -47,13 +47,23 @@ struct BwdFusedParams {
   unsigned int* doneA;  // [nblk], zeroed by the host before the launch
   unsigned int* doneB;  // [nblk]
   int owner_rows;       // column-side gradient rows per owner: column c accumulates into dB map c / owner_rows at row
-                        // c % owner_rows (one owner = the whole of dB on a single GPU; in the row-sharded run every
-                        // rank owns cols / world rows and the maps point at the owners' buffers over NVLink)
+                        // c % owner_rows - part_row0 (one owner = the whole of dB on a single GPU; in the row-sharded
+                        // run every rank owns cols / world rows)
+  // Column parts: a launch may cover only the i-th of n equal parts of EVERY owner's columns (so that the reduce-scatter
+  // of one part can travel while the next part is computed).  Block column index cb of this launch -> global block:
+  int blocks_per_owner;   // column blocks per owner in the whole problem (owner_rows / Cb)
+  int blocks_per_part;    // blocks_per_owner / n_parts
+  int part;               // which part this launch covers
+  int part_row0;          // part * blocks_per_part * Cb: first row of the part inside an owner's gradient rows
+  __host__ __device__ int global_cb(int cb) const {
+    const int owner = cb / blocks_per_part;
+    return owner * blocks_per_owner + part * blocks_per_part + (cb - owner * blocks_per_part);
+  }
 };
 
 constexpr int kMaxOwners = 8;
 struct BwdOwnerMaps {
-  CUtensorMap m[kMaxOwners];  // fp32 [owner_rows, D] output maps (box 32 x 32), one per owner
+  CUtensorMap m[kMaxOwners];  // fp32 [owner_rows / n_parts, D] output maps (box 32 x 32), one per owner
 };
 
 struct BwdItem {
@@ -247,7 +257,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     uint32_t phase = 0;
     int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
     while (cur.next(p, it)) {
-      const int rb = it.blk / p.nbc, cb = it.blk - rb * p.nbc;
+      const int rb = it.blk / p.nbc;
+      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       if (it.type != 0 && it.blk > verified) {
         wait_counter(p.doneA + it.blk, wantA, lane);
@@ -265,14 +276,14 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           const int k0 = (it.kb0 + kb) * kBK;
           if (it.type == 0) {
             tma_load_2d_cg2(&mAk, &full_bar[stage], a_dst, k0, rb * p.Rb + it.tm * 256 + half_off, kEvictNormal);
-            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, cb * p.Cb + it.tn * BN + n_half, kEvictNormal);
+            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, col0 + it.tn * BN + n_half, kEvictNormal);
           } else if (it.type == 1) {
             // dA[rows] += g . b[cols]:  A = g (K-major, K = block columns),  B = b (MN-major: [K = column index][N = D])
             tma_load_2d_cg2(&mGk, &full_bar[stage], a_dst, k0, buf * p.Rb + it.tm * 256 + half_off, kEvictNormal);
             const int n0 = it.tn * BN + n_half;
 #pragma unroll
             for (int i = 0; i < kBHalf / 64; ++i)
-              tma_load_2d_cg2(&mBmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, cb * p.Cb + k0, kEvictNormal);
+              tma_load_2d_cg2(&mBmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, col0 + k0, kEvictNormal);
           } else {
             // dB[cols] += g^T . a[rows]:  A = g (MN-major: [K = block row][M = block column]),  B = a (MN-major)
             const int m0 = it.tm * 256 + half_off;
@@ -356,7 +367,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       const int acc_stage = n % kAcc;
       const uint32_t acc_phase = (n / kAcc) & 1;
       ++n;
-      const int rb = it.blk / p.nbc, cb = it.blk - rb * p.nbc;
+      const int rb = it.blk / p.nbc;
+      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tcgen05_fence_after();
@@ -368,8 +380,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           verified = it.blk - p.nbuf;
         }
         gp.rinv = p.rinv + rb * p.Rb;
-        gp.cinv = p.cinv + cb * p.Cb;
-        gp.diag_offset = rb * p.Rb + p.diag_offset - cb * p.Cb;
+        gp.cinv = p.cinv + col0;
+        gp.diag_offset = rb * p.Rb + p.diag_offset - col0;
         gp.g_row_off = buf * p.Rb;
         FusedGrad::template run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
                            epi_scratch + acc_stage * BN + half * (BN / (kEW / 4)), &mGst, staging, 0, carry);
@@ -377,13 +389,13 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       } else {
         // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
         if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
-        int m0 = (it.type == 1 ? rb * p.Rb : cb * p.Cb) + it.tm * 256 + half_off;
+        int m0 = (it.type == 1 ? rb * p.Rb : col0) + it.tm * 256 + half_off;
         const CUtensorMap* cmap = &mdA;
         if (it.type == 2) {
           // the owner of these 128 gradient rows (owner_rows is a multiple of 256: a tile never straddles owners); a
           // remote owner's buffer is reached by the same TMA reduce-add, over NVLink
           const int owner = m0 / p.owner_rows;
-          m0 -= owner * p.owner_rows;
+          m0 -= owner * p.owner_rows + p.part_row0;
           cmap = &mdB.m[owner];
         }
         FusedStore::template run_tma<BN>(sp, tacc, m0, it.tn * BN, p.D, half, q, lane, cmap, staging + ewarp * 4096);

@@ -384,7 +384,7 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   if (prec == MMG_PREC_BF16 && phases == 3 && block_rows <= 0 && block_cols <= 0) {
     int used = 0;
     float* owners[1] = {dB};
-    MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, owners, 1,
+    MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, owners, 1, 1, 0,
                                  dlogscale_acc, workspace, workspace_bytes, st, &used));
     if (used) return 0;
   }
@@ -423,8 +423,8 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
 
 int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                            const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
-                           float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
-                           size_t workspace_bytes, mmg_stream_t stream) {
+                           float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
+                           void* workspace, size_t workspace_bytes, mmg_stream_t stream) {
   MMG_TRY(check_infonce_args("mmg_infonce_bwd_owners", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
   MMG_REQ(rinv);
   MMG_REQ(cinv);
@@ -436,13 +436,16 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
   for (int i = 0; i < n_owners; ++i)
     if (dB_owners[i] == nullptr) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_owners: owner %d is NULL", i);
   int used = 0;
+  if (n_parts < 1 || part < 0 || part >= n_parts)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_owners: bad column part %d of %d", part, n_parts);
   MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, dB_owners,
-                               n_owners, dlogscale_acc, workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
-                               &used));
+                               n_owners, n_parts, part, dlogscale_acc, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream), &used));
   if (!used)
     return set_error(MMG_ERR_UNSUPPORTED_SHAPE,
-                     "mmg_infonce_bwd_owners: needs rows, cols / owners and D to be multiples of 256, 16-byte aligned "
-                     "outputs and a workspace of mmg_infonce_workspace_bytes() (use mmg_infonce_bwd + a reduce-scatter)");
+                     "mmg_infonce_bwd_owners: needs rows, cols / owners and D to be multiples of 256, column parts made of "
+                     "whole column blocks, 16-byte aligned outputs and a workspace of mmg_infonce_workspace_bytes() (use "
+                     "mmg_infonce_bwd + a reduce-scatter)");
   return 0;
 }
 

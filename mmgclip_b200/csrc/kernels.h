@@ -45,12 +45,14 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
 // not covered (rows / cols / D not multiples of 256, workspace too small, MMG_BWD_FUSED=0): the caller falls back to the
 // block loop.  tc_infonce_bwd_fused_workspace = bytes it needs (0 = not covered).
 size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D);
-// dB_owners[i] = fp32 [cols / n_owners, D] buffer that owns column-side rows [i * cols / n_owners, (i+1) * ...): one
-// owner = all of dB; in the row-sharded run the owners are the ranks and the pointers are NVLink peer mappings.
+// dB_owners[i] = fp32 buffer that owns column-side rows [i * cols / n_owners, (i+1) * ...): one owner = all of dB; in the
+// row-sharded run the owners are the ranks (pointers into a staging buffer, or NVLink peer mappings).  n_parts > 1: the
+// launch covers only part `part` of every owner's columns and dB_owners[i] is the [cols / n_owners / n_parts, D] buffer
+// of that part.
 int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
-                         float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
-                         size_t workspace_bytes, cudaStream_t st, int* used);
+                         float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used);
 
 // Zero-shot prompt scoring on the tensor pipe (zeroshot_tc.cu): 3xTF32, fp32-faithful, HBM-bound at large N.
 size_t tc_zeroshot_workspace_bytes(int C, int D);

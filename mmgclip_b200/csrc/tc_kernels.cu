@@ -391,14 +391,16 @@ static int largest_divisor(int n, int cap) {
   return 0;
 }
 
-static FusedPlan fused_plan(int rows, int cols, int D) {
+static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0) {
   FusedPlan f;
   memset(&f, 0, sizeof(f));
   if (env_int("MMG_BWD_FUSED", 1) == 0) return f;
   if (rows < 256 || cols < 256 || D < 256 || (D % 256) != 0) return f;
   int Rb = env_int("MMG_FUSED_RB", 0), Cb = env_int("MMG_FUSED_CB", 0);
   if (Rb <= 0) Rb = largest_divisor(rows, 4096);
-  if (Cb <= 0) Cb = largest_divisor(cols, 2048);
+  // col_unit > 0: column blocks must also divide col_unit (the columns of one part of one owner)
+  if (Cb <= 0) Cb = largest_divisor(col_unit > 0 ? col_unit : cols, 2048);
+  if (col_unit > 0 && Cb >= 256 && (col_unit % Cb) != 0) return f;
   if (Rb < 256 || Cb < 256 || (Rb % 256) || (Cb % 256) || (rows % Rb) || (cols % Cb)) return f;
   // K blocks (of 64) per gradient slice: every slice ends in a 256 x 256 fp32 reduce-add at L2, so slices are long
   int kslI = env_int("MMG_FUSED_KSL", 32), kslT = env_int("MMG_FUSED_KSL_T", env_int("MMG_FUSED_KSL", 32));
@@ -423,12 +425,15 @@ size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
 
 int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
-                         float* const* dB_owners, int n_owners, float* dlogscale_acc, void* workspace,
-                         size_t workspace_bytes, cudaStream_t st, int* used) {
+                         float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used) {
   *used = 0;
-  const FusedPlan f = fused_plan(rows, cols, D);
-  if (!f.ok || workspace_bytes < f.total_bytes) return 0;
   if (n_owners < 1 || n_owners > kMaxOwners || (cols % n_owners) != 0 || ((cols / n_owners) % 256) != 0) return 0;
+  if (n_parts < 1 || part < 0 || part >= n_parts) return 0;
+  const int owner_rows = cols / n_owners;
+  if (n_parts > 1 && ((owner_rows % n_parts) != 0 || ((owner_rows / n_parts) % 256) != 0)) return 0;
+  const FusedPlan f = fused_plan(rows, cols, D, n_parts > 1 ? owner_rows / n_parts : 0);  // parts = whole column blocks
+  if (!f.ok || workspace_bytes < f.total_bytes) return 0;
   if (!out_tma_ok(dA, D)) return 0;
   for (int i = 0; i < n_owners; ++i)
     if (dB_owners[i] == nullptr || !out_tma_ok(dB_owners[i], D)) return 0;
@@ -437,7 +442,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   memset(&p, 0, sizeof(p));
   p.rows = rows; p.cols = cols; p.D = D;
   p.Rb = f.Rb; p.Cb = f.Cb;
-  p.nbc = cols / f.Cb;
+  p.nbc = cols / f.Cb / n_parts;   // column blocks this launch covers
   p.nblk = (rows / f.Rb) * p.nbc;
   p.nbuf = f.nbuf;
   const int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
@@ -453,7 +458,16 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
   p.doneA = ctr;
   p.doneB = ctr + p.nblk;
-  p.owner_rows = cols / n_owners;
+  p.owner_rows = owner_rows;
+  if (n_parts > 1) {
+    p.blocks_per_owner = owner_rows / f.Cb;
+    p.blocks_per_part = p.blocks_per_owner / n_parts;
+  } else {
+    p.blocks_per_owner = p.blocks_per_part = p.nbc;  // one part: block index == global block index
+  }
+  p.part = part;
+  p.part_row0 = part * p.blocks_per_part * f.Cb;
+  if (p.nbuf > p.nblk) p.nbuf = p.nblk < 1 ? 1 : p.nblk;
   cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)2 * p.nblk * sizeof(unsigned int), st);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
 
@@ -471,7 +485,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   if ((rc = make_out_tmap_f32(&mdA, dA, D, rows, D)) != 0) return rc;
   for (int i = 0; i < kMaxOwners; ++i) {
     const int o = i < n_owners ? i : 0;  // unused slots repeat owner 0 (never selected)
-    if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, cols / n_owners, D)) != 0) return rc;
+    if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, owner_rows / n_parts, D)) != 0) return rc;
   }
 
   const int ew = env_int("MMG_FUSED_EPI_WARPS", 8) == 16 ? 16 : 8;

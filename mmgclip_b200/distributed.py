@@ -230,10 +230,10 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             peer = _peer_buffers(bl, D, a_op.device, group)
         if peer is not None:
             # gradient GEMM + reduce-scatter in one kernel: the slices add into their owners' buffers over NVLink
-            dA, own, dls = ops.infonce_backward_owners(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off,
-                                                       peer.own, peer.ptrs, peer.pre_sync, peer.post_sync, a32=a32,
-                                                       b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2])
-            dB = own.clone()  # the symmetric buffer is reused by the next step
+            dA, owns, dls = ops.infonce_backward_owners(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off,
+                                                        [(peer.own, peer.ptrs)], peer.pre_sync, peer.post_sync, a32=a32,
+                                                        b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2])
+            dB = owns[0].clone()  # the symmetric buffer is reused by the next step
             dscale = None
             if ctx.needs_input_grad[2]:
                 dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)

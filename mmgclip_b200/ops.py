@@ -327,19 +327,28 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     return dA, dB, dls
 
 
-def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, own: torch.Tensor,
-                            owner_ptrs, pre_sync, post_sync, a32=None, b32=None, diag=None, need_dscale: bool = True):
+def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, parts,
+                            pre_sync=None, post_sync=None, after_part=None, a32=None, b32=None, diag=None,
+                            need_dscale: bool = True):
     """Row-sharded backward whose column-side gradient goes straight to its owners (mmg_infonce_bwd_owners).
 
-    ``own`` is this rank's fp32 [cols/world, D] gradient buffer, ``owner_ptrs`` the device pointers of every rank's buffer
-    as mapped into this process (NVLink peer memory), in rank order.  ``pre_sync`` / ``post_sync`` are stream-ordered
-    cross-rank barriers: every owner's buffer is initialised before anybody adds into it, and all adds have landed before
-    anybody reads its own.  Returns (dA [rows, D], own, sum g*cos or None)."""
+    ``parts`` is a list of ``(own, owner_ptrs)``, one entry per column part (usually one): ``own`` is this rank's fp32
+    ``[cols/world/n_parts, D]`` gradient buffer for that part of its columns and ``owner_ptrs`` the device pointers of
+    every rank's buffer for the part, in rank order (NVLink peer mappings, or slices of a local staging buffer that a
+    reduce-scatter sends home).  ``pre_sync`` / ``post_sync``: stream-ordered cross-rank barriers for the peer-memory
+    case (every owner's buffer is initialised before anybody adds into it; all adds have landed before anybody reads its
+    own).  ``after_part(i)`` runs right after part i has been launched (e.g. to start its reduce-scatter).
+    Returns (dA [rows, D], [own buffers], sum g*cos or None)."""
     rows, D = a.shape
     cols = b.shape[0]
-    world = len(owner_ptrs)
-    if rows * world != cols or diag_offset % rows != 0 or tuple(own.shape) != (rows, D) or own.dtype != torch.float32:
+    n_parts = len(parts)
+    world = len(parts[0][1])
+    rp = rows // n_parts
+    if rows * world != cols or diag_offset % rows != 0 or rp * n_parts != rows:
         raise ValueError("infonce_backward_owners: every rank must own cols/world rows paired with its local rows")
+    for own, ptrs in parts:
+        if tuple(own.shape) != (rp, D) or own.dtype != torch.float32 or len(ptrs) != world:
+            raise ValueError("infonce_backward_owners: each part needs an fp32 [rows/n_parts, D] buffer per owner")
     dev = a.device
     lib = _lib.load()
     rinv = torch.empty(rows, dtype=torch.float32, device=dev)
@@ -351,22 +360,33 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
                                    int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
     if diag_fp32:
+        # the matching-pair term is the first writer of dA and of this rank's own buffers (part i = local rows
+        # [i*rp, (i+1)*rp), whose partners are rows [0, rp) of the part's buffer)
         dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
-        cinvm = cinv[diag_offset:diag_offset + rows]
-        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
-                                       _p(dA), _p(own), _p(dls), 1, _stream()), "mmg_infonce_bwd_diag")
+        for i, (own, _) in enumerate(parts):
+            r0 = i * rp
+            cinvm = cinv[diag_offset + r0:diag_offset + r0 + rp]
+            check(lib.mmg_infonce_bwd_diag(_p(a32[r0:r0 + rp]), _p(b32[r0:r0 + rp]), rp, D, _p(diag[r0:r0 + rp]), _p(scale),
+                                           _p(rinv[r0:r0 + rp]), _p(cinvm), _p(scal), _p(dA[r0:r0 + rp]), _p(own), _p(dls),
+                                           1, _stream()), "mmg_infonce_bwd_diag")
     else:
         dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
-        own.zero_()
+        for own, _ in parts:
+            own.zero_()
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC["bf16"], rows, cols, D)
     ws = _workspace(dev, nbytes)
-    ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
-    pre_sync()
-    check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv), _p(scal),
-                                     _p(dA), ptrs, world, _p(dls), _p(ws), ws.numel(), _stream()),
-          "mmg_infonce_bwd_owners")
-    post_sync()
-    return dA, own, dls
+    if pre_sync is not None:
+        pre_sync()
+    for i, (_, owner_ptrs) in enumerate(parts):
+        ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
+        check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+                                         _p(scal), _p(dA), ptrs, world, n_parts, i, _p(dls), _p(ws), ws.numel(),
+                                         _stream()), "mmg_infonce_bwd_owners")
+        if after_part is not None:
+            after_part(i)
+    if post_sync is not None:
+        post_sync()
+    return dA, [own for own, _ in parts], dls
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -86,10 +86,11 @@ def test_fused_backward_vs_float64():
     assert abs(dls.item() - float((g * cos).sum())) < 4e-3 * max(1.0, abs(float((g * cos).sum())))
 
 
-@pytest.mark.parametrize("world,rank", [(2, 1), (4, 2), (8, 5)])
-def test_owner_distributed_column_gradients(world, rank):
+@pytest.mark.parametrize("world,rank,n_parts", [(2, 1, 1), (4, 2, 1), (8, 5, 1), (2, 0, 2), (4, 3, 2)])
+def test_owner_distributed_column_gradients(world, rank, n_parts):
     """mmg_infonce_bwd_owners on one GPU: the column-side gradient is spread over `world` separate buffers (what the ranks'
-    NVLink-mapped buffers are in the multi-GPU run); stitched together they equal the ordinary dB."""
+    NVLink-mapped buffers are in the multi-GPU run), optionally in `n_parts` launches that each cover one part of every
+    owner's columns; stitched together they equal the ordinary dB."""
     from mmgclip_b200 import ops
     rows, d = 512, 256
     cols = rows * world
@@ -98,15 +99,23 @@ def test_owner_distributed_column_gradients(world, rank):
     one = torch.ones((), device="cuda")
     b32 = b[off:off + rows].contiguous()
     dA0, dB0, dl0 = ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, off, "bf16", a32=a, b32=b32, diag=diag)
-    bufs = [torch.zeros((rows, d), device="cuda") for _ in range(world)]   # the other owners start from zero
+    rp = rows // n_parts
+    # bufs[part][owner]: the other owners start from zero, this rank's own buffers are initialised by the call
+    bufs = [[torch.zeros((rp, d), device="cuda") for _ in range(world)] for _ in range(n_parts)]
     events = []
-    dA1, own, dl1 = ops.infonce_backward_owners(ab, bb, s, rs, cs, one, 0.5 / cols, off, bufs[rank],
-                                                [t.data_ptr() for t in bufs], lambda: events.append("pre"),
-                                                lambda: events.append("post"), a32=a, b32=b32, diag=diag)
-    torch.cuda.synchronize()
-    assert events == ["pre", "post"] and own is bufs[rank]
+    try:
+        dA1, owns, dl1 = ops.infonce_backward_owners(
+            ab, bb, s, rs, cs, one, 0.5 / cols, off,
+            [(bufs[i][rank], [t.data_ptr() for t in bufs[i]]) for i in range(n_parts)],
+            lambda: events.append("pre"), lambda: events.append("post"), lambda i: events.append(i), a32=a, b32=b32,
+            diag=diag)
+        torch.cuda.synchronize()
+    finally:
+        _setenv()
+    assert events == ["pre"] + list(range(n_parts)) + ["post"] and owns[0] is bufs[0][rank]
     assert rel_err(dA1.cpu(), dA0.cpu()) < 2e-4
-    assert rel_err(torch.cat(bufs).cpu(), dB0.cpu()) < 2e-4
+    stitched = torch.cat([torch.cat([bufs[i][o] for i in range(n_parts)]) for o in range(world)])
+    assert rel_err(stitched.cpu(), dB0.cpu()) < 2e-4
     assert abs(dl1.item() - dl0.item()) <= 2e-4 * max(abs(dl0.item()), 1e-3)
 
 
