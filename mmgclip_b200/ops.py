@@ -64,6 +64,18 @@ def num_sms() -> int:
 
 _workspaces = {}
 
+# Optional timing probe around the dominant launch (the InfoNCE backward contraction): a pair of CUDA events recorded on
+# the launching stream right before / after it.  With `torch.cuda.Event(enable_timing=True, external=True)` the records are
+# captured into CUDA graphs as well, so a replayed step can be timed per kernel without a profiler (bench.py's live
+# roofline).
+_bwd_probe = None
+
+
+def set_backward_probe(events) -> None:
+    """events: (start, end) CUDA events or None."""
+    global _bwd_probe
+    _bwd_probe = events
+
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Grow-only scratch per device (the L2-resident gradient-coefficient block lives here)."""
@@ -321,9 +333,13 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
         bc = (min(cols, block_cols or 4096) + 63) // 64 * 64
         nbytes = max(nbytes, br * bc * esz + 256)
     ws = _workspace(dev, nbytes)
+    if _bwd_probe is not None:
+        _bwd_probe[0].record()
     check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
                               _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
                               _stream()), "mmg_infonce_bwd")
+    if _bwd_probe is not None:
+        _bwd_probe[1].record()
     return dA, dB, dls
 
 
