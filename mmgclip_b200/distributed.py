@@ -28,10 +28,12 @@ from . import ops
 # ---------------------------------------------------------------------------------------------------------------------
 # Column-side gradients over NVLink peer memory: every rank owns one [B/R, D] fp32 buffer in torch symmetric memory; the
 # fused backward's gradient slices TMA-reduce-add straight into the owner's buffer (mmg_infonce_bwd_owners), so the
-# gradient GEMM *is* the reduce-scatter.  Opt-in (MMGCLIP_B200_PEER_REDUCE=1): results are identical (tests/
-# gpu_dist_check.py, eager and graph) but on 8 x B200 the step measured 0.996 ms against 0.933 ms with the default path
-# -- a [B, D] staging buffer + asynchronous NCCL reduce-scatter overlapped with the row-side head backward -- because the
-# remote 128-byte reduce-adds lengthen the gradient-slice epilogues (2 GPUs: 2.108 vs 2.131 ms, a wash).
+# gradient GEMM *is* the reduce-scatter.  Results are identical to the staging-buffer + NCCL reduce-scatter path
+# (tests/gpu_dist_check.py, eager and graph).  What makes it pay is that the kernel takes whole-K dB slices when the
+# owners are remote, so every gradient element crosses NVLink once per row block: 8 x B200 0.775 ms per step against
+# 0.817 ms with the asynchronous NCCL reduce-scatter (and 0.945 ms with the 32-block slices of the single-GPU schedule,
+# whose remote 128-byte reduce-adds lengthen the slice epilogues).  MMGCLIP_B200_PEER_REDUCE=0, a non-NCCL backend or a
+# failed set-up (a collective decision) select the NCCL path.
 # ---------------------------------------------------------------------------------------------------------------------
 _peer_cache = {}
 
@@ -56,7 +58,7 @@ def peer_reduce_active() -> bool:
 
 
 def _peer_buffers(rows, D, device, group):
-    if os.environ.get("MMGCLIP_B200_PEER_REDUCE", "0") != "1":
+    if os.environ.get("MMGCLIP_B200_PEER_REDUCE", "1") == "0":
         return None
     world = dist.get_world_size(group)
     if dist.get_backend(group) != "nccl" or world > 8 or rows % 256 != 0 or D % 256 != 0 or D < 256:
