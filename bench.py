@@ -8,8 +8,10 @@ A *step* is one pass of the hot path over one global batch of synthetic encoder 
     LinearProjectionLayer heads (768 -> 512, image and text) -> L2 normalise -> exp(logit_scale) -> symmetric InfoNCE
     (CLIPLoss) forward -> backward down to the head-weight gradients            (reference: mmgclip_model.py:124-136,
     losses.py:36-44, ClassifierExperiment.py:109-115; optimizer step excluded, as in the metric's definition)
-Rows are sharded across ranks (strong scaling: the global batch is fixed at 32768); text embeddings are all-gathered,
-column sums all-reduced, text-side gradients reduce-scattered, head gradients all-reduced (NCCL over NVLink).
+Rows are sharded across ranks (strong scaling: the global batch is fixed at 32768); text embeddings are all-gathered
+(NCCL), column sums / loss / head gradients all-reduced (symmetric-memory kernels over NVLink), and the text-side gradients
+reach their owner ranks inside the fused backward kernel (TMA reduce-add into NVLink peer memory; NCCL reduce-scatter
+as the fallback).  The step is replayed as one CUDA graph.
 
 `value`  : inputs already resident in HBM (fp32 features), timed with CUDA events on the launching stream, max over ranks.
 `e2e`    : same call with features in pinned HOST memory: each step's host->device copy (prefetched on a copy stream one
