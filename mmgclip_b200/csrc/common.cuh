@@ -107,6 +107,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    // (a __nanosleep back-off between polls was measured on 150-step soak runs: no effect on time, clock or power)
     if (clock64() - t0 > MMG_HANG_GUARD_CYCLES) {
       printf("[mmgclip_b200] mbarrier wait timed out: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
