@@ -169,6 +169,13 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
                            float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream);
 
+/* Introspection (host only, no GPU): the static work-item schedule of the fused backward for CTA pair `pair` of `pairs`
+ * -- rows of items[] are {type (0 coefficient tile, 1 dA slice, 2 dB slice), block, tm, tn, kb0, nkb, global column
+ * block}; info[8] = {Rb, Cb, nbuf, nA, nB, nblk, kslI, kslT}.  Returns the pair's item count (0 = shape not covered).
+ * tests/test_fused_schedule_cpu.py uses it to check the schedule's ordering / dead-lock-freedom invariants. */
+int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
+                           int max_items, int* info);
+
 /* ---- literal cross-entropy on materialised logits (losses.py:28-44, 207-212) ----------------------------- */
 /* F.cross_entropy(logits[n, m], labels) pieces; labels: int64 DEVICE array [n] or NULL = arange(n) (needs n <= m).
  * lse[n] is kept for the backward.   loss_out[0] += coef * sum_r (lse[r] - logits[r, labels[r]]). */

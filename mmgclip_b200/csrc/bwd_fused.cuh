@@ -76,12 +76,12 @@ struct BwdItem {
 // Merged, key-ordered walk over the items one CTA pair owns.
 struct BwdCursor {
   int a, b, na_total, nb_total, step;
-  __device__ __forceinline__ void init(const BwdFusedParams& p, int pair, int pairs) {
+  __host__ __device__ __forceinline__ void init(const BwdFusedParams& p, int pair, int pairs) {
     a = pair; b = pair; step = pairs;
     na_total = p.nblk * p.nA;
     nb_total = p.nblk * p.nB;
   }
-  __device__ __forceinline__ bool next(const BwdFusedParams& p, BwdItem& it) {
+  __host__ __device__ __forceinline__ bool next(const BwdFusedParams& p, BwdItem& it) {
     const bool have_a = a < na_total, have_b = b < nb_total;
     if (!have_a && !have_b) return false;
     bool take_a;

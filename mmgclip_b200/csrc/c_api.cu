@@ -449,6 +449,11 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
   return 0;
 }
 
+int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
+                           int max_items, int* info) {
+  return tc_fused_bwd_schedule(rows, cols, D, n_owners, n_parts, part, pairs, pair, items, max_items, info);
+}
+
 int mmg_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
                float* loss_out, mmg_stream_t stream) {
   if (n <= 0 || m <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_fwd: bad shape %dx%d", n, m);

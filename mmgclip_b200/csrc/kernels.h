@@ -61,6 +61,9 @@ int tc_zeroshot(const float* img, const float* txt, int N, int C, int D, const f
                 float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
 
+int tc_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
+                          int max_items, int* info);
+
 // ---- SIMT (fp32) launchers: simt_kernels.cu ----
 int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C, long long ldc,
               int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,

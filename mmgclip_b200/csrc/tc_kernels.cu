@@ -421,6 +421,71 @@ static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0, bool re
   return f;
 }
 
+// Everything of BwdFusedParams that defines the work-item schedule (no pointers).
+static void fill_schedule(BwdFusedParams* pp, const FusedPlan& f, int rows, int cols, int D, int n_owners, int n_parts,
+                          int part, int BN) {
+  BwdFusedParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  const int owner_rows = cols / n_owners;
+  p.rows = rows; p.cols = cols; p.D = D;
+  p.Rb = f.Rb; p.Cb = f.Cb;
+  p.nbc = cols / f.Cb / n_parts;   // column blocks this launch covers
+  p.nblk = (rows / f.Rb) * p.nbc;
+  p.nbuf = f.nbuf;
+  p.tAm = f.Rb / 256; p.tAn = f.Cb / BN; p.tDn = D / BN;
+  p.kslI = f.kslI; p.kslT = f.kslT;
+  p.sI = (f.Cb / kBK) / f.kslI;
+  p.sT = (f.Rb / kBK) / f.kslT;
+  p.nA = p.tAm * p.tAn;
+  p.nBI = p.tAm * p.tDn * p.sI;
+  p.nB = p.nBI + p.tAn * p.tDn * p.sT;
+  p.owner_rows = owner_rows;
+  if (n_parts > 1) {
+    p.blocks_per_owner = owner_rows / f.Cb;
+    p.blocks_per_part = p.blocks_per_owner / n_parts;
+  } else {
+    p.blocks_per_owner = p.blocks_per_part = p.nbc;  // one part: block index == global block index
+  }
+  p.part = part;
+  p.part_row0 = part * p.blocks_per_part * f.Cb;
+  if (p.nbuf > p.nblk) p.nbuf = p.nblk < 1 ? 1 : p.nblk;
+}
+
+// Host-side enumeration of the fused backward's static schedule (no GPU needed): the items CTA pair `pair` of `pairs`
+// walks, in order, as rows of {type, block, tm, tn, kb0, nkb, global column block}.  info[8] = {Rb, Cb, nbuf, nA, nB,
+// nblk, kslI, kslT}.  Returns the pair's item count (items beyond max_items are counted but not written), 0 when the
+// shape is not covered by the fused kernel.  Used by tests/test_fused_schedule_cpu.py to check the dead-lock freedom
+// argument of bwd_fused.cuh for arbitrary shapes.
+int tc_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
+                          int max_items, int* info) {
+  if (n_owners < 1 || n_parts < 1 || part < 0 || part >= n_parts || pairs < 1 || pair < 0 || pair >= pairs) return 0;
+  if ((cols % n_owners) != 0) return 0;
+  const int owner_rows = cols / n_owners;
+  if (n_parts > 1 && ((owner_rows % n_parts) != 0 || ((owner_rows / n_parts) % 256) != 0)) return 0;
+  const FusedPlan f = fused_plan(rows, cols, D, n_parts > 1 ? owner_rows / n_parts : 0, n_owners > 1);
+  if (!f.ok) return 0;
+  BwdFusedParams p;
+  fill_schedule(&p, f, rows, cols, D, n_owners, n_parts, part, 256);
+  if (info != nullptr) {
+    info[0] = p.Rb; info[1] = p.Cb; info[2] = p.nbuf; info[3] = p.nA; info[4] = p.nB; info[5] = p.nblk;
+    info[6] = p.kslI; info[7] = p.kslT;
+  }
+  BwdCursor cur;
+  cur.init(p, pair, pairs);
+  BwdItem it;
+  int n = 0;
+  while (cur.next(p, it)) {
+    if (items != nullptr && n < max_items) {
+      int* o = items + 7 * n;
+      const int rb = it.blk / p.nbc;
+      o[0] = it.type; o[1] = it.blk; o[2] = it.tm; o[3] = it.tn; o[4] = it.kb0; o[5] = it.nkb;
+      o[6] = p.global_cb(it.blk - rb * p.nbc);
+    }
+    ++n;
+  }
+  return n;
+}
+
 size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
   const FusedPlan f = fused_plan(rows, cols, D);
   return f.ok ? f.total_bytes : 0;
@@ -441,36 +506,14 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   for (int i = 0; i < n_owners; ++i)
     if (dB_owners[i] == nullptr || !out_tma_ok(dB_owners[i], D)) return 0;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return 0;
-  BwdFusedParams p;
-  memset(&p, 0, sizeof(p));
-  p.rows = rows; p.cols = cols; p.D = D;
-  p.Rb = f.Rb; p.Cb = f.Cb;
-  p.nbc = cols / f.Cb / n_parts;   // column blocks this launch covers
-  p.nblk = (rows / f.Rb) * p.nbc;
-  p.nbuf = f.nbuf;
   const int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
-  p.tAm = f.Rb / 256; p.tAn = f.Cb / BN; p.tDn = D / BN;
-  p.kslI = f.kslI; p.kslT = f.kslT;
-  p.sI = (f.Cb / kBK) / f.kslI;
-  p.sT = (f.Rb / kBK) / f.kslT;
-  p.nA = p.tAm * p.tAn;
-  p.nBI = p.tAm * p.tDn * p.sI;
-  p.nB = p.nBI + p.tAn * p.tDn * p.sT;
+  BwdFusedParams p;
+  fill_schedule(&p, f, rows, cols, D, n_owners, n_parts, part, BN);
   p.diag_offset = diag_offset;
   p.rinv = rinv; p.cinv = cinv; p.scale = scale; p.scal = scal; p.dlogscale_acc = dlogscale_acc;
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
   p.doneA = ctr;
   p.doneB = ctr + p.nblk;
-  p.owner_rows = owner_rows;
-  if (n_parts > 1) {
-    p.blocks_per_owner = owner_rows / f.Cb;
-    p.blocks_per_part = p.blocks_per_owner / n_parts;
-  } else {
-    p.blocks_per_owner = p.blocks_per_part = p.nbc;  // one part: block index == global block index
-  }
-  p.part = part;
-  p.part_row0 = part * p.blocks_per_part * f.Cb;
-  if (p.nbuf > p.nblk) p.nbuf = p.nblk < 1 ? 1 : p.nblk;
   cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)2 * p.nblk * sizeof(unsigned int), st);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
 

@@ -1,0 +1,121 @@
+"""Host-only checks of the fused backward's static work-item schedule (mmgclip_b200/csrc/bwd_fused.cuh).
+
+The kernel hands every CTA pair a fixed, key-ordered list of items: coefficient tiles ("A", type 0) of a block, and the
+dA / dB K-slices ("B", types 1 / 2) that consume the block's coefficients.  B items of block s spin on doneA[s] == nA, A
+items of block s spin on doneB[s - nbuf] == nB (the coefficient buffer they overwrite).  Nothing here needs a GPU:
+`mmg_fused_bwd_schedule` enumerates the same cursor on the host, and the test replays all pairs against the counters to
+prove that every item runs exactly once and that the spin-waits cannot dead-lock for any number of resident pairs.
+"""
+import ctypes
+
+import pytest
+
+from mmgclip_b200 import _lib
+
+MAX_ITEMS = 1 << 16
+
+
+def _schedule(rows, cols, D, n_owners, n_parts, part, pairs):
+    lib = _lib.load()
+    info = (ctypes.c_int * 8)()
+    per_pair = []
+    for pair in range(pairs):
+        buf = (ctypes.c_int * (7 * MAX_ITEMS))()
+        n = lib.mmg_fused_bwd_schedule(rows, cols, D, n_owners, n_parts, part, pairs, pair, buf, MAX_ITEMS, info)
+        assert 0 <= n <= MAX_ITEMS
+        per_pair.append([tuple(buf[7 * i:7 * i + 7]) for i in range(n)])
+    keys = ("Rb", "Cb", "nbuf", "nA", "nB", "nblk", "kslI", "kslT")
+    return per_pair, dict(zip(keys, info))
+
+
+SHAPES = [
+    # rows, cols, D, n_owners, n_parts, part
+    (32768, 32768, 512, 1, 1, 0),      # BASELINE configs[1], one GPU
+    (4096, 4096, 512, 1, 1, 0),        # configs[2]
+    (4096, 32768, 512, 8, 1, 0),       # one rank of 8, rows sharded
+    (4096, 32768, 512, 8, 2, 1),       # ... in two column parts (peer-reduce pipelining)
+    (16384, 32768, 512, 2, 1, 0),
+    (8192, 8192, 256, 1, 1, 0),
+    (2048, 131072, 1024, 8, 1, 0),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("pairs", [1, 3, 74])
+def test_schedule_is_complete_and_deadlock_free(shape, pairs):
+    rows, cols, D, n_owners, n_parts, part = shape
+    per_pair, info = _schedule(rows, cols, D, n_owners, n_parts, part, pairs)
+    if info["nblk"] == 0 or not any(per_pair):
+        pytest.skip("shape not covered by the fused backward (block loop takes it)")
+    nA, nB, nblk, nbuf = info["nA"], info["nB"], info["nblk"], info["nbuf"]
+
+    # every item exactly once over all pairs
+    seen = set()
+    for items in per_pair:
+        for it in items:
+            key = it[:5]
+            assert key not in seen, f"item {it} scheduled twice"
+            seen.add(key)
+    a_items = [k for k in seen if k[0] == 0]
+    b_items = [k for k in seen if k[0] != 0]
+    assert len(a_items) == nA * nblk
+    assert len(b_items) == nB * nblk
+    assert {k[1] for k in seen} == set(range(nblk))
+
+    # K-slices tile the contraction: per (type, block, tm, tn) the [kb0, kb0+nkb) ranges are disjoint and contiguous
+    slices = {}
+    for items in per_pair:
+        for t, blk, tm, tn, kb0, nkb, _ in items:
+            if t != 0:
+                slices.setdefault((t, blk, tm, tn), []).append((kb0, nkb))
+    for (t, blk, tm, tn), sl in slices.items():
+        sl.sort()
+        want = (info["Cb"] if t == 1 else info["Rb"]) // 64
+        pos = 0
+        for kb0, nkb in sl:
+            assert kb0 == pos
+            pos += nkb
+        assert pos == want
+
+    # replay: a pair runs its items in order and blocks on the counters exactly as the kernel does
+    doneA = [0] * nblk
+    doneB = [0] * nblk
+    pos = [0] * pairs
+    total = sum(len(x) for x in per_pair)
+    done = 0
+    while done < total:
+        progressed = False
+        for p in range(pairs):
+            while pos[p] < len(per_pair[p]):
+                t, blk = per_pair[p][pos[p]][:2]
+                if t == 0:
+                    if blk >= nbuf and doneB[blk - nbuf] != nB:
+                        break
+                    doneA[blk] += 1
+                else:
+                    if doneA[blk] != nA:
+                        break
+                    doneB[blk] += 1
+                pos[p] += 1
+                done += 1
+                progressed = True
+        assert progressed, f"dead-lock with {pairs} pairs at positions {pos}"
+    assert doneA == [nA] * nblk and doneB == [nB] * nblk
+
+
+def test_global_column_block_mapping_of_parts():
+    """Two parts of an 8-owner launch cover disjoint halves of every owner's rows, together all column blocks."""
+    rows, cols, D = 4096, 32768, 512
+    cover = []
+    for part in range(2):
+        per_pair, info = _schedule(rows, cols, D, 8, 2, part, 4)
+        if not any(per_pair):
+            pytest.skip("shape not covered")
+        cover.append({it[6] for items in per_pair for it in items})
+    assert not (cover[0] & cover[1])
+    assert cover[0] | cover[1] == set(range(cols // info["Cb"]))
+
+
+def test_unsupported_shape_reports_zero():
+    per_pair, _ = _schedule(100, 100, 64, 1, 1, 0, 2)
+    assert per_pair == [[], []]
