@@ -169,6 +169,27 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
                            float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream);
 
+/* ---- SURVEY s8(f) "next" rows: the callers either side of the path ---- */
+
+/* 'eos' text pooling, mmgclip/networks/mmgclip_model.py:108-111: idx[r] = attention_mask[r,:].sum() - 1 (negative wraps
+ * to seq-1 like Python indexing); out[r,:] = hidden[r, idx[r], :].  hidden [n, seq, H] fp32, attention_mask [n, seq]
+ * int64, out [n, H] fp32, idx_out [n] int64 or NULL (needed by the backward). */
+int mmg_eos_pool(const float* hidden, const long long* attention_mask, int n, int seq, int H, float* out,
+                 long long* idx_out, mmg_stream_t stream);
+/* dhidden [n, seq, H] = 0 except dhidden[r, idx[r], :] = dout[r, :]. */
+int mmg_eos_pool_bwd(const float* dout, const long long* idx, int n, int seq, int H, float* dhidden,
+                     mmg_stream_t stream);
+
+/* Multi-tensor AdamW step, replacing `self.optimizer.step()` of mmgclip/experiments/ClassifierExperiment.py:74,118
+ * (torch.optim.AdamW(model.parameters(), lr, weight_decay); betas (0.9, 0.999), eps 1e-8 by default):
+ *   p *= 1 - lr*wd;  m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * params/grads/exp_avg/exp_avg_sq/numel are HOST arrays of n_tensors device pointers / element counts (fp32 tensors).
+ * step_state: device int64[2] = {t (steps taken so far), 0}; the launch reads t+1 and stores it back, so a captured
+ * CUDA graph advances it on every replay.  lr_dev: device fp32 scalar read at run time (NULL: use `lr`). */
+int mmg_adamw_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
+                   float eps, float weight_decay, long long* step_state, mmg_stream_t stream);
+
 /* Introspection (host only, no GPU): the static work-item schedule of the fused backward for CTA pair `pair` of `pairs`
  * -- rows of items[] are {type (0 coefficient tile, 1 dA slice, 2 dB slice), block, tm, tn, kb0, nkb, global column
  * block}; info[8] = {Rb, Cb, nbuf, nA, nB, nblk, kslI, kslT}.  Returns the pair's item count (0 = shape not covered).

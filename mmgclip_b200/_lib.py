@@ -58,6 +58,11 @@ SIGNATURES = {
     "mmg_infonce_bwd_owners": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_size_t, c_void_p]),
+    "mmg_eos_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmg_eos_pool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mmg_adamw_step": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                               POINTER(c_longlong), c_int, c_float, c_void_p, c_float, c_float, c_float, c_float,
+                               c_void_p, c_void_p]),
     "mmg_fused_bwd_schedule": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int,
                                        POINTER(c_int)]),
     "mmg_ce_fwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),

@@ -454,6 +454,52 @@ int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts,
   return tc_fused_bwd_schedule(rows, cols, D, n_owners, n_parts, part, pairs, pair, items, max_items, info);
 }
 
+int mmg_eos_pool(const float* hidden, const long long* attention_mask, int n, int seq, int H, float* out,
+                 long long* idx_out, mmg_stream_t stream) {
+  if (n < 0 || seq <= 0 || H <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_eos_pool: bad shape %d x %d x %d", n, seq, H);
+  if (n == 0) return 0;
+  MMG_REQ(hidden);
+  MMG_REQ(attention_mask);
+  MMG_REQ(out);
+  if (idx_out != nullptr) MMG_REQ(idx_out);
+  return simt_eos_pool(hidden, attention_mask, n, seq, H, out, idx_out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_eos_pool_bwd(const float* dout, const long long* idx, int n, int seq, int H, float* dhidden,
+                     mmg_stream_t stream) {
+  if (n < 0 || seq <= 0 || H <= 0)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_eos_pool_bwd: bad shape %d x %d x %d", n, seq, H);
+  if (n == 0) return 0;
+  MMG_REQ(dout);
+  MMG_REQ(idx);
+  MMG_REQ(dhidden);
+  return simt_eos_pool_bwd(dout, idx, n, seq, H, dhidden, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_adamw_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
+                   float eps, float weight_decay, long long* step_state, mmg_stream_t stream) {
+  if (n_tensors < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_adamw_step: n_tensors < 0");
+  if (n_tensors == 0) return 0;
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || numel == nullptr)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_adamw_step: NULL pointer table");
+  if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f) || !(weight_decay >= 0.f) ||
+      (lr_dev == nullptr && !(lr >= 0.f)))
+    return set_error(MMG_ERR_BAD_ARG, "mmg_adamw_step: invalid hyper-parameter");
+  MMG_REQ(step_state);
+  if (lr_dev != nullptr) MMG_REQ(lr_dev);
+  for (int i = 0; i < n_tensors; ++i) {
+    if (numel[i] < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_adamw_step: numel[%d] < 0", i);
+    if (numel[i] == 0) continue;
+    MMG_REQ(params[i]);
+    MMG_REQ(grads[i]);
+    MMG_REQ(exp_avg[i]);
+    MMG_REQ(exp_avg_sq[i]);
+  }
+  return simt_adamw(params, grads, exp_avg, exp_avg_sq, numel, n_tensors, lr, lr_dev, beta1, beta2, eps, weight_decay,
+                    step_state, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
                float* loss_out, mmg_stream_t stream) {
   if (n <= 0 || m <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_ce_fwd: bad shape %dx%d", n, m);

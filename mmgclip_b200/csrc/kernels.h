@@ -85,6 +85,14 @@ int simt_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
 int simt_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        int rows, int cols, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
 
+int simt_eos_pool(const float* hidden, const long long* mask, int n, int seq, int H, float* out, long long* idx_out,
+                  cudaStream_t st);
+int simt_eos_pool_bwd(const float* dout, const long long* idx, int n, int seq, int H, float* dhidden, cudaStream_t st);
+constexpr int kAdamwMaxTensors = 64;  // tensors per launch (pointers travel as kernel parameters)
+int simt_adamw(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+               const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
+               float eps, float weight_decay, long long* state, cudaStream_t st);
+
 // fp32 InfoNCE block helpers operating on an fp32 cosine block S[rb, cb] (pitch lds) in scratch
 int simt_lse_block(float* S, long long lds, int rb, int cb, int row0, int col0, int diag_offset, const float* scale,
                    float* rowsum, float* colsum, float* diag, cudaStream_t st);

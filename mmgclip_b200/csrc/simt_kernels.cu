@@ -920,4 +920,210 @@ int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const
   return 0;
 }
 
+// =====================================================================================================
+// 'eos' text pooling (mmgclip_model.py:108-111): the hidden state of the last attended token of every sequence,
+//   idx[r] = attention_mask[r, :].sum() - 1  (a negative index wraps like Python's: an all-zero mask picks seq - 1),
+//   out[r, :] = hidden[r, idx[r], :].
+// One CTA per sequence: mask row reduction, then a float4 row copy (the only HBM traffic that matters: 2*H*4 B per row;
+// the other seq-1 hidden states of the sequence are never touched).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) eos_pool_kernel(const float* __restrict__ hidden,
+                                                       const long long* __restrict__ mask, int seq, int H,
+                                                       float* __restrict__ out, long long* __restrict__ idx_out) {
+  __shared__ long long s_part[8];
+  __shared__ long long s_idx;
+  const int r = blockIdx.x;
+  long long acc = 0;
+  for (int t = threadIdx.x; t < seq; t += blockDim.x) acc += mask[(long long)r * seq + t];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+    long long idx = tot - 1;
+    if (idx < 0) idx += seq;
+    if (idx < 0 || idx >= seq) idx = -1;  // out of range: torch would raise; rows are written as NaN and idx = -1
+    s_idx = idx;
+    if (idx_out != nullptr) idx_out[r] = idx;
+  }
+  __syncthreads();
+  const long long idx = s_idx;
+  float* o = out + (long long)r * H;
+  if (idx < 0) {
+    for (int c = threadIdx.x; c < H; c += blockDim.x) o[c] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const float* src = hidden + ((long long)r * seq + idx) * H;
+  if ((H & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int c = threadIdx.x; c < H / 4; c += blockDim.x) o4[c] = __ldg(s4 + c);
+  } else {
+    for (int c = threadIdx.x; c < H; c += blockDim.x) o[c] = src[c];
+  }
+}
+// backward: dhidden (already zero-filled) [r, idx[r], :] = dout[r, :]
+__global__ void __launch_bounds__(256) eos_pool_bwd_kernel(const float* __restrict__ dout,
+                                                           const long long* __restrict__ idx, int seq, int H,
+                                                           float* __restrict__ dhidden) {
+  const int r = blockIdx.x;
+  const long long i = idx[r];
+  if (i < 0 || i >= seq) return;
+  float* dst = dhidden + ((long long)r * seq + i) * H;
+  const float* src = dout + (long long)r * H;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) dst[c] = src[c];
+}
+int simt_eos_pool(const float* hidden, const long long* mask, int n, int seq, int H, float* out, long long* idx_out,
+                  cudaStream_t st) {
+  if (n <= 0) return 0;
+  eos_pool_kernel<<<n, 256, 0, st>>>(hidden, mask, seq, H, out, idx_out);
+  MMG_LAUNCH_CHECK("eos_pool_kernel");
+  return 0;
+}
+int simt_eos_pool_bwd(const float* dout, const long long* idx, int n, int seq, int H, float* dhidden, cudaStream_t st) {
+  if (n <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(dhidden, 0, (size_t)n * seq * H * sizeof(float), st);
+  if (e != cudaSuccess) return check_cuda(e, "eos_pool_bwd memset");
+  eos_pool_bwd_kernel<<<n, 256, 0, st>>>(dout, idx, seq, H, dhidden);
+  MMG_LAUNCH_CHECK("eos_pool_bwd_kernel");
+  return 0;
+}
+
+// =====================================================================================================
+// Multi-tensor AdamW (ClassifierExperiment.py:74,118: torch.optim.AdamW over model.parameters(), i.e. the head weights).
+// Decoupled weight decay, bias-corrected moments, the operation order of torch's implementation:
+//   p *= 1 - lr*wd;  m += (1-b1)*(g - m);  v = b2*v + (1-b2)*g*g;
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// All tensors of a launch travel in the kernel parameters (no descriptor table in HBM, so a CUDA graph node owns its
+// own pointers -- GraphedStep re-points the gradients per recorded graph).  The step counter lives on the device:
+// every CTA reads t = state[0] + 1; the last CTA to retire (ticket in state[1]) publishes it, so the update is one launch
+// and replays correctly inside a CUDA graph.  `lr_dev` (optional) is read at run time for the same reason (schedulers).
+// =====================================================================================================
+struct AdamwTensors {
+  float* p[kAdamwMaxTensors];
+  const float* g[kAdamwMaxTensors];
+  float* m[kAdamwMaxTensors];
+  float* v[kAdamwMaxTensors];
+  int chunk0[kAdamwMaxTensors + 1];  // prefix sum of per-tensor chunk counts
+  long long numel[kAdamwMaxTensors];
+  int n;
+};
+constexpr int kAdamwChunk = 256 * 4 * 2;  // elements per CTA iteration: 256 threads x 2 float4
+
+__global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ AdamwTensors T, float lr_host,
+                                                    const float* __restrict__ lr_dev, float beta1, float beta2,
+                                                    float eps, float weight_decay, long long* __restrict__ state,
+                                                    int advance) {
+  __shared__ float s_coef[3];
+  __shared__ long long s_t;
+  if (threadIdx.x == 0) {
+    const long long t0 = state[0] + 1;
+    const float lr0 = lr_dev != nullptr ? *lr_dev : lr_host;
+    // bias corrections in double, as torch's Python-scalar path does
+    const double bc1 = 1.0 - pow((double)beta1, (double)t0);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t0);
+    s_coef[0] = (float)(1.0 - (double)lr0 * (double)weight_decay);
+    s_coef[1] = (float)((double)lr0 / bc1);
+    s_coef[2] = (float)(1.0 / sqrt(bc2));
+    s_t = t0;
+  }
+  __syncthreads();
+  const long long t = s_t;
+  const float decay = s_coef[0], step_size = s_coef[1], rsqrt_bc2 = s_coef[2];
+  const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+  const int total = T.chunk0[T.n];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int ti = 0;
+    while (ti + 1 < T.n && c >= T.chunk0[ti + 1]) ++ti;
+    const long long base = (long long)(c - T.chunk0[ti]) * kAdamwChunk;
+    const long long n = T.numel[ti];
+    float* __restrict__ p = T.p[ti];
+    const float* __restrict__ g = T.g[ti];
+    float* __restrict__ m = T.m[ti];
+    float* __restrict__ v = T.v[ti];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i0 = base + ((long long)u * 256 + threadIdx.x) * 4;
+      if (i0 >= n) continue;
+      const bool vec = (i0 + 4 <= n) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+      float pv[4], gv[4], mv[4], vv[4];
+      if (vec) {
+        *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(p + i0);
+        *reinterpret_cast<float4*>(gv) = *reinterpret_cast<const float4*>(g + i0);
+        *reinterpret_cast<float4*>(mv) = *reinterpret_cast<const float4*>(m + i0);
+        *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = i0 + j < n;
+          pv[j] = ok ? p[i0 + j] : 0.f; gv[j] = ok ? g[i0 + j] : 0.f;
+          mv[j] = ok ? m[i0 + j] : 0.f; vv[j] = ok ? v[i0 + j] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gj = gv[j];
+        float pj = pv[j] * decay;
+        const float mj = mv[j] + w1 * (gj - mv[j]);
+        const float vj = vv[j] * beta2 + w2 * gj * gj;
+        const float denom = sqrtf(vj) * rsqrt_bc2 + eps;
+        pj -= step_size * (mj / denom);
+        pv[j] = pj; mv[j] = mj; vv[j] = vj;
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(p + i0) = *reinterpret_cast<float4*>(pv);
+        *reinterpret_cast<float4*>(m + i0) = *reinterpret_cast<float4*>(mv);
+        *reinterpret_cast<float4*>(v + i0) = *reinterpret_cast<float4*>(vv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j < n) { p[i0 + j] = pv[j]; m[i0 + j] = mv[j]; v[i0 + j] = vv[j]; }
+      }
+    }
+  }
+  // last CTA out publishes the new step count (every CTA has read state[0] before it takes a ticket)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(state + 1), 1ull);
+    if (ticket == (unsigned long long)gridDim.x - 1) {
+      state[1] = 0;
+      if (advance) state[0] = t;
+      __threadfence();
+    }
+  }
+}
+
+int simt_adamw(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+               const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
+               float eps, float weight_decay, long long* state, cudaStream_t st) {
+  int done = 0;
+  while (done < n_tensors) {
+    AdamwTensors T;
+    memset(&T, 0, sizeof(T));
+    int k = 0;
+    long long chunks = 0;
+    while (done + k < n_tensors && k < kAdamwMaxTensors) {
+      const long long n = numel[done + k];
+      const long long c = (n + kAdamwChunk - 1) / kAdamwChunk;
+      if (chunks + c > 0x7fffffffLL) break;
+      T.p[k] = params[done + k]; T.g[k] = grads[done + k];
+      T.m[k] = exp_avg[done + k]; T.v[k] = exp_avg_sq[done + k];
+      T.numel[k] = n;
+      T.chunk0[k] = (int)chunks;
+      chunks += c;
+      ++k;
+    }
+    if (k == 0) return set_error(-1, "adamw: tensor %d too large", done);
+    T.chunk0[k] = (int)chunks;
+    T.n = k;
+    done += k;
+    int grid = (int)(chunks < 148 * 8 ? (chunks < 1 ? 1 : chunks) : 148 * 8);
+    adamw_kernel<<<grid, 256, 0, st>>>(T, lr, lr_dev, beta1, beta2, eps, weight_decay, state, done == n_tensors ? 1 : 0);
+    MMG_LAUNCH_CHECK("adamw_kernel");
+  }
+  return 0;
+}
+
 }  // namespace mmg

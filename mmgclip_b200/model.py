@@ -122,8 +122,7 @@ class MMGCLIP(nn.Module):
         hidden = self.text_encoder(tokens)
         if text_pooling != 'eos':
             raise NotImplementedError(f"{text_pooling} method is not implemented...")
-        last = tokens['attention_mask'].sum(dim=-1) - 1
-        return hidden[torch.arange(hidden.shape[0], device=hidden.device), last]
+        return ops.eos_pool(hidden.to(torch.float32), tokens['attention_mask'])
 
     # -- the hot path ------------------------------------------------------------------------------------------
     def _embed(self, head, features):

@@ -849,3 +849,42 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
         check(lib.mmg_zeroshot_score(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
                                      _p(tkv), _stream()), "mmg_zeroshot_score")
     return {"logits": logits, "probs": probs, "argmax": amax, "topk_idx": tki, "topk_val": tkv}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# 'eos' text pooling: hidden state of the last attended token, mmgclip_model.py:108-111
+# -------------------------------------------------------------------------------------------------------------------
+class _EosPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, attention_mask):
+        _need_cuda(hidden, attention_mask)
+        if hidden.dim() != 3 or attention_mask.dim() != 2 or attention_mask.shape != hidden.shape[:2]:
+            raise ValueError("eos_pool expects hidden [n, seq, H] and attention_mask [n, seq]")
+        if hidden.dtype != torch.float32:
+            raise ValueError("eos_pool expects fp32 hidden states (the reference encoders run in fp32)")
+        hidden = hidden.contiguous()
+        mask = attention_mask.to(torch.int64).contiguous()
+        n, seq, H = hidden.shape
+        out = torch.empty((n, H), dtype=torch.float32, device=hidden.device)
+        idx = torch.empty((n,), dtype=torch.int64, device=hidden.device)
+        check(_lib.load().mmg_eos_pool(_p(hidden), _p(mask), n, seq, H, _p(out), _p(idx), _stream()), "mmg_eos_pool")
+        ctx.save_for_backward(idx)
+        ctx.shape = (n, seq, H)
+        ctx.mark_non_differentiable(idx)
+        return out, idx
+
+    @staticmethod
+    def backward(ctx, g, _g_idx):
+        (idx,) = ctx.saved_tensors
+        n, seq, H = ctx.shape
+        dh = torch.empty((n, seq, H), dtype=torch.float32, device=g.device)
+        check(_lib.load().mmg_eos_pool_bwd(_p(g.contiguous()), _p(idx), n, seq, H, _p(dh), _stream()),
+              "mmg_eos_pool_bwd")
+        return dh, None
+
+
+def eos_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, return_index: bool = False):
+    """``hidden[arange(n), attention_mask.sum(-1) - 1]`` (mmgclip_model.py:108-111) in one launch that touches only the
+    pooled rows.  An all-zero mask row wraps to the last position, as Python's ``-1`` index does in the reference."""
+    out, idx = _EosPoolFn.apply(hidden, attention_mask)
+    return (out, idx) if return_index else out

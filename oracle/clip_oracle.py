@@ -135,6 +135,31 @@ def torch_zeroshot(image_embeddings, text_embeddings, logit_scale):
     return logits, probs, torch.argmax(probs, dim=-1)
 
 
+def torch_eos_pool(hidden: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    """'eos' text pooling, statement for statement (mmgclip/networks/mmgclip_model.py:108-111): the hidden state at
+    index ``attention_mask.sum(-1) - 1`` of every sequence (an all-zero mask yields -1, i.e. the last position)."""
+    eos_token_indices = attention_mask.sum(dim=-1) - 1
+    return hidden[torch.arange(hidden.shape[0]), eos_token_indices]
+
+
+def torch_adamw_steps(params: Sequence[torch.Tensor], grads_per_step: Sequence[Sequence[torch.Tensor]], lr,
+                      weight_decay: float, betas=(0.9, 0.999), eps: float = 1e-8) -> List[torch.Tensor]:
+    """The reference's optimiser, by the same library call: ``torch.optim.AdamW(model.parameters(), lr=..., weight_decay=...)``
+    followed by ``optimizer.step()`` per iteration (mmgclip/experiments/ClassifierExperiment.py:74,118), single-tensor
+    implementation on the CPU.  ``lr`` may be a float or one value per step (scheduler)."""
+    ps = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    lr0 = lr if isinstance(lr, (int, float)) else lr[0]
+    opt = torch.optim.AdamW(ps, lr=lr0, weight_decay=weight_decay, betas=betas, eps=eps, foreach=False)
+    for t, grads in enumerate(grads_per_step):
+        if not isinstance(lr, (int, float)):
+            for g in opt.param_groups:
+                g["lr"] = lr[t]
+        for p, g in zip(ps, grads):
+            p.grad = g.detach().clone()
+        opt.step()
+    return [p.detach() for p in ps]
+
+
 def torch_train_step(image_features, text_features, w_image, w_text, logit_scale_log) -> Dict[str, torch.Tensor]:
     """One step of the reference hot path with LinearProjectionLayer heads and CLIPLoss, forward and backward:
     heads -> normalise -> exp -> two logit GEMMs -> CLIPLoss -> backward (ClassifierExperiment.py:109-115).
@@ -208,6 +233,26 @@ def closed_form_zeroshot(img: np.ndarray, txt: np.ndarray, s: float, k: int = 0)
         order = np.lexsort((np.broadcast_to(np.arange(logits.shape[1]), logits.shape), -logits), axis=1)
         out["topk_idx"] = order[:, :k]
     return out
+
+
+def closed_form_adamw_steps(params, grads_per_step, lr, weight_decay: float, betas=(0.9, 0.999), eps: float = 1e-8):
+    """float64 AdamW (Loshchilov & Hutter; the algorithm box of torch.optim.AdamW's documentation), independent of
+    torch's implementation: theta <- theta(1 - lr*wd); m, v moments; theta <- theta - lr * m_hat / (sqrt(v_hat) + eps)."""
+    th = [np.asarray(p, np.float64).copy() for p in params]
+    m = [np.zeros_like(x) for x in th]
+    v = [np.zeros_like(x) for x in th]
+    b1, b2 = betas
+    for t, grads in enumerate(grads_per_step, start=1):
+        lr_t = lr if isinstance(lr, (int, float)) else lr[t - 1]
+        for i, g in enumerate(grads):
+            g = np.asarray(g, np.float64)
+            th[i] *= 1.0 - lr_t * weight_decay
+            m[i] = b1 * m[i] + (1.0 - b1) * g
+            v[i] = b2 * v[i] + (1.0 - b2) * g * g
+            m_hat = m[i] / (1.0 - b1 ** t)
+            v_hat = v[i] / (1.0 - b2 ** t)
+            th[i] -= lr_t * m_hat / (np.sqrt(v_hat) + eps)
+    return th
 
 
 def _logsumexp(x: np.ndarray, axis: int) -> np.ndarray:

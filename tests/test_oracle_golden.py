@@ -122,3 +122,25 @@ def test_zeroshot(golden):
     assert np.array_equal(c["argmax"], g["argmax"])            # duplicated prompt 2 == 5: first index wins
     assert fro_err(c["probs"], g["probs"]) < 1e-6
     assert not np.any(c["argmax"] == 5)
+
+
+def test_eos_pool_and_adamw_statements():
+    """The two 'next'-row helpers of the oracle: pooling is an index expression (checked on hand-made masks incl. the
+    all-zero wrap-around); the float64 AdamW closed form is pinned against torch.optim.AdamW itself on the CPU."""
+    g = torch.Generator().manual_seed(7)
+    hidden = torch.randn(5, 9, 12, generator=g)
+    mask = torch.zeros(5, 9, dtype=torch.int64)
+    lens = [9, 1, 4, 0, 7]
+    for r, n in enumerate(lens):
+        mask[r, :n] = 1
+    pooled = oc.torch_eos_pool(hidden, mask)
+    for r, n in enumerate(lens):
+        assert torch.equal(pooled[r], hidden[r, n - 1])  # n = 0 -> index -1 -> last position
+
+    params = [torch.randn(33, 17, generator=g), torch.randn(17, generator=g)]
+    grads = [[torch.randn(33, 17, generator=g) * 0.1, torch.randn(17, generator=g) * 0.1] for _ in range(6)]
+    lrs = [1e-3, 2e-3, 3e-3, 2e-3, 1e-3, 5e-4]
+    got = oc.torch_adamw_steps(params, grads, lrs, weight_decay=1e-2)
+    want = oc.closed_form_adamw_steps([p.numpy() for p in params], [[x.numpy() for x in gs] for gs in grads], lrs, 1e-2)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a.numpy(), b, rtol=2e-5, atol=2e-6)
