@@ -64,6 +64,28 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# synthetic inputs, generated here so that the measured arm touches nothing under oracle/:
+# image features ~ clamp(1 + 0.35 N(0,1), min=0) (ConvNeXt avg-pool-like), text features ~ 0.5 N(0,1) (BERT-like), head
+# weights ~ nn.Linear's default U(-1/sqrt(E), 1/sqrt(E)).  tests/test_boundary_cpu.py checks that the oracle's recipe
+# (used by the CPU arm) yields the same arrays, so both arms see identical data.
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_features(batch, e_image=768, e_text=768, seed=42):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    xi = np.maximum(1.0 + 0.35 * rng.standard_normal((batch, e_image)), 0.0).astype(np.float32)
+    xt = (0.5 * rng.standard_normal((batch, e_text))).astype(np.float32)
+    return xi, xt
+
+
+def synthetic_head_weights(d, e_image=768, e_text=768, seed=43):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    wi = rng.uniform(-1.0, 1.0, (d, e_image)).astype(np.float32) / np.float32(math.sqrt(e_image))
+    wt = rng.uniform(-1.0, 1.0, (d, e_text)).astype(np.float32) / np.float32(math.sqrt(e_text))
+    return wi, wt
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference step on the host cores
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference(sample_batch, steps, warmup):
@@ -92,7 +114,7 @@ def run_reference(args):
     sample = args.cpu_sample_batch
     r = cpu_reference(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
     desc = (f"oracle port (fp32 eager PyTorch on CPU) of the reference step at batch {sample} of {GLOBAL_BATCH}, "
-            f"{r['threads']} threads; cost per pair grows ~linearly with the batch, so the full 32768 batch would be "
+            f"{r['threads']} threads; cost per pair grows ~linearly with the batch, so the full {GLOBAL_BATCH} batch would be "
             f"~{GLOBAL_BATCH // sample}x slower per pair")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": "pairs/s", "n_gpus": args.gpus,
@@ -217,7 +239,6 @@ def run_gpu(args):
     from mmgclip_b200.distributed import (allreduce_gradients, gather_columns_async, peer_reduce_active,
                                           sharded_info_nce, symm_allreduce_active)
     from mmgclip_b200.projection import LinearProjectionLayer
-    from oracle import clip_oracle as oc  # only for the synthetic-input recipe and the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,8 +261,8 @@ def run_gpu(args):
     prec = args.precision
 
     # identical global tensors on every rank, contiguous row shard per rank
-    xi_g, xt_g = oc.synthetic_features(B, E_IMG, E_TXT, seed=42)
-    wi, wt = oc.synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
+    xi_g, xt_g = synthetic_features(B, E_IMG, E_TXT, seed=42)
+    wi, wt = synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
     xi_h = torch.from_numpy(xi_g[rank * bl:(rank + 1) * bl].copy())
     xt_h = torch.from_numpy(xt_g[rank * bl:(rank + 1) * bl].copy())
     del xi_g, xt_g
@@ -580,12 +601,15 @@ def run_zeroshot(args):
 
 
 def main():
+    global D_PROJ, GLOBAL_BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: the metric's 32768)")
+    ap.add_argument("--dim", type=int, default=D_PROJ,
+                    help="projection dimension D (default: the metric's 512; BASELINE config 5 uses 1024)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -603,6 +627,8 @@ def main():
     ap.add_argument("--zeroshot-rows", type=int, default=1 << 20)
     ap.add_argument("--zeroshot-impl", default="auto", choices=["auto", "tc", "ffma"])
     args = ap.parse_args()
+    D_PROJ = args.dim
+    GLOBAL_BATCH = args.batch  # the config block of the JSON line names the batch that was actually run
     if args.workload == "zeroshot":
         return run_zeroshot(args)
     if args.impl == "reference":

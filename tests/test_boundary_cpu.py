@@ -92,3 +92,19 @@ def test_assign_labels_host_logic(golden):
     loss = AveragedMedicalCLIPLoss()
     assert loss._assign_labels(k["doc_cosine"].tolist(), threshold=0.65) == [0, 1, 0, 1, 0, 1, 0, 1]
     assert loss._assign_labels(torch.from_numpy(k["doc_cosine"]), threshold=0.65) == k["doc_labels"].tolist()
+
+
+def test_bench_synthetic_recipe_matches_oracle():
+    """bench.py generates the measured arm's inputs itself (nothing under oracle/ on the product path); the CPU arm uses
+    the oracle's generator.  Both must produce the same arrays so that the two arms see identical data."""
+    import importlib.util
+    import os
+    import numpy as np
+    from oracle import clip_oracle as oc
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a, b = bench.synthetic_features(64, 48, 40, seed=42), oc.synthetic_features(64, 48, 40, seed=42)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    a, b = bench.synthetic_head_weights(32, 48, 40, seed=43), oc.synthetic_head_weights(32, 48, 40, seed=43)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
