@@ -126,6 +126,23 @@ def set_split_heads(flag: bool) -> None:
     _split_heads = bool(flag)
 
 
+# The head-weight gradient dW = du^T x can drop the lo terms independently of the forward: du already carries the bf16
+# rounding of the InfoNCE coefficients, so hi.hi alone is inside the bf16 gradient bar (tests/gpu_dw_probe.py measures
+# both).  MMGCLIP_B200_SPLIT_DW: "1" = three K segments, "0" = one.
+_split_dw = os.environ.get("MMGCLIP_B200_SPLIT_DW", "1") != "0"
+
+
+def set_split_dw(flag: bool) -> None:
+    global _split_dw
+    _split_dw = bool(flag)
+
+
+def _dw_operands(dz: "_Operand", xo: "_Operand"):
+    if _split_dw:
+        return dz, xo
+    return _Operand(dz.hi), _Operand(xo.hi)
+
+
 class _Operand:
     """A contraction operand for a given precision: fp32 tensor, bf16 tensor, or a (hi, lo) bf16 pair."""
 
@@ -460,8 +477,9 @@ class _LinearFn(torch.autograd.Function):
         dzo = _Operand.of(dz, prec)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
-            ks = _split_k_for(D, E, Bn * _n_segments(dzo, xo)) if prec == "bf16" else 1
-            dw = gemm_heads(dzo, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
+            da, xa = _dw_operands(dzo, xo)
+            ks = _split_k_for(D, E, Bn * _n_segments(da, xa)) if prec == "bf16" else 1
+            dw = gemm_heads(da, xa, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(D, dtype=torch.float32, device=dy.device)
             check(_lib.load().mmg_colsum(_p(dz), Bn, D, _p(db), _stream()), "mmg_colsum")
@@ -545,15 +563,16 @@ class _ProjNormFn(torch.autograd.Function):
         Bn, E, D = ctx.shape
         need_dx = ctx.needs_input_grad[0]
         if prec == "bf16":
-            split = xo.lo is not None
+            split = xo.lo is not None and (_split_dw or need_dx)
             res = l2norm_bwd(dy, y, inv, False, True, want_lo=split)
             dz = _Operand(res[1], res[2] if split else None)
         else:
             dz = _Operand(l2norm_bwd(dy, y, inv, True, False)[0])
         dw = dx = None
         if ctx.needs_input_grad[1]:
-            ks = _split_k_for(D, E, Bn * _n_segments(dz, xo)) if prec == "bf16" else 1
-            dw = gemm_heads(dz, xo, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
+            da, xa = _dw_operands(dz, xo)
+            ks = _split_k_for(D, E, Bn * _n_segments(da, xa)) if prec == "bf16" else 1
+            dw = gemm_heads(da, xa, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
         if need_dx:
             dx = gemm_heads(dz, wo, Bn, E, D, b_mn=True, prec=prec)
         return dx, dw, None
