@@ -14,8 +14,9 @@ reach their owner ranks inside the fused backward kernel (TMA reduce-add into NV
 as the fallback).  The step is replayed as one CUDA graph.
 
 `value`  : inputs already resident in HBM (fp32 features), timed with CUDA events on the launching stream, max over ranks.
-`e2e`    : same call with features in pinned HOST memory: each step's host->device copy (prefetched on a copy stream one
-           step ahead) and a device->host read of the loss are inside the timed region.
+`e2e`    : same call with features in pinned HOST memory, as a steady-state pipeline: every timed iteration issues one
+           host->device batch upload (the next step's, on a copy stream), the step, and a device->host read of the loss;
+           K uploads, K steps and K read-backs complete inside the timed region.
 `roofline`: algorithmic FLOPs (6 B^2 D + 4 B (E_i+E_t) D, SURVEY s8d / DESIGN.md) / step time / GPUs vs the measured
            bf16 tensor peak in MEASURED_PEAKS.json (sustained figure: the kernels are timed inside a long step).
 `cpu_baseline`: the oracle port of the reference step timed on this box's host cores on a bounded sample (rank 0, N=1).
@@ -398,28 +399,33 @@ def run_gpu(args):
             stage[s][1].copy_(ht, non_blocking=True)
             ready[s].record(copy_stream)
 
-    def e2e_loop(n_steps, base):
-        prefetch(base)
+    def e2e_loop(n_steps, base, first_in_flight):
+        """n_steps steps of the steady-state pipeline: while step i computes, the copy stream uploads batch i+1.  Every
+        iteration issues exactly one H2D batch copy (the NEXT step's) and one loss D2H; the batch of the first step is
+        already in flight when `first_in_flight` (it was issued by the previous loop's last iteration)."""
+        if not first_in_flight:
+            prefetch(base)
         for i in range(n_steps):
             s = (base + i) % 2
-            if i + 1 < n_steps:
-                prefetch(base + i + 1)
+            prefetch(base + i + 1)
             compute.wait_event(ready[s])
             l = run_stage_step(s)
             consumed[s].record(compute)
             loss_host[base + i].copy_(l.detach(), non_blocking=True)
+        # the upload issued by the last iteration belongs to this loop's bytes: its completion is inside the region
+        compute.wait_event(ready[(base + n_steps) % 2])
 
     for s in range(2):
         consumed[s].record(compute)
-    e2e_loop(W, 0)
+    W2 = W + (W % 2)  # keep the double-buffer parity aligned
+    e2e_loop(W2, 0, False)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    W2 = W + (W % 2)  # keep the double-buffer parity aligned
     barrier()
     if sampler is not None:
         sampler.begin()
     e2.record()
-    e2e_loop(K, W2)
+    e2e_loop(K, W2, True)
     e3.record()
     barrier()
     if sampler is not None:
@@ -469,7 +475,10 @@ def run_gpu(args):
         "loss": loss_value,
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": step_bytes * world, "d2h_bytes_per_step": 4 * world},
+                "h2d_bytes_per_step": step_bytes * world, "d2h_bytes_per_step": 4 * world,
+                "how": "steady-state pipeline through the public modules: K iterations, each issuing one pinned-host -> "
+                       "device batch upload (the next step's, on a copy stream) + the step + the loss read-back; K "
+                       "uploads complete inside the timed region (CUDA events, max over ranks)"},
         "gpu_launches": int(launches),
         # dominant kernel = the fused persistent backward launch (~65% of the step): algorithmic FLOPs per launch (dI + dT;
         # the recomputed cosines are not counted) / live CUDA-event launch duration, against the sustained bf16 peak (it
