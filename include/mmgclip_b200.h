@@ -169,6 +169,21 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
                            float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream);
 
+/* ---- stored-E variant of the fused InfoNCE (bf16 path): trade 2*rows*cols bytes of HBM for a third of the backward ----
+ * The forward additionally keeps E = exp(logit - s) as bf16 [rows, lde] (same reference lines as mmg_infonce_fwd:
+ * losses.py:28-44 via mmgclip_model.py:135-136); the backward then turns E into the gradient coefficients with a streaming
+ * transform instead of recomputing the cosines on the tensor cores (4 instead of 6 rows*cols*D FLOPs).  No
+ * d/d logit_scale in this mode (use mmg_infonce_bwd when logit_scale is trained).  mmg_infonce_stored_supported tells
+ * whether mmg_infonce_bwd_stored covers a shape (rows, cols/owners/parts and D multiples of 256). */
+int mmg_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts);
+int mmg_infonce_fwd_store(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                          const float* scale, float* rowsum, float* colsum, float* diag, void* e_out, long long lde,
+                          mmg_stream_t stream);
+int mmg_infonce_bwd_stored(const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows, int cols,
+                           int D, int diag_offset, const float* scale, const float* rinv, const float* cinv,
+                           const float* scal, float* dA, float* const* dB_owners, int n_owners, int n_parts, int part,
+                           void* workspace, size_t workspace_bytes, mmg_stream_t stream);
+
 /* ---- SURVEY s8(f) "next" rows: the callers either side of the path ---- */
 
 /* 'eos' text pooling, mmgclip/networks/mmgclip_model.py:108-111: idx[r] = attention_mask[r,:].sum() - 1 (negative wraps

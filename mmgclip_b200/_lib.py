@@ -58,6 +58,12 @@ SIGNATURES = {
     "mmg_infonce_bwd_owners": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_size_t, c_void_p]),
+    "mmg_infonce_stored_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "mmg_infonce_fwd_store": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_longlong, c_void_p]),
+    "mmg_infonce_bwd_stored": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
+                                       c_void_p, c_size_t, c_void_p]),
     "mmg_eos_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mmg_eos_pool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mmg_adamw_step": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),

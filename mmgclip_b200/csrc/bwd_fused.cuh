@@ -21,6 +21,13 @@
 //     doneA[s] : (CTA, coefficient tile) pairs of block s whose stores are complete   (gradient loads of s wait for all)
 //     doneB[s] : gradient slices of block s whose MMAs have completed               (block s + nbuf may then overwrite
 //                                                                                    the scratch buffer)
+// Stored-E mode (template flag kStoredE).  When the forward kept E = exp(logit - s) (bf16, rows x cols) the coefficient
+// tiles need no tensor-core work at all: g = E * (rinv[r] + cinv[c]) is a pure streaming transform.  (A) items are then
+// skipped by the TMA producer and the MMA issuer (they take no operand-ring slot and no accumulator stage); the
+// epilogue warps read their 32 x 128 piece of E straight from global memory (16 independent 16-byte loads per thread),
+// scale it and store the bf16 coefficients into the scratch buffer, meet at a named barrier and publish doneA.  The
+// backward executes 4 B^2 D FLOPs instead of 6 B^2 D, at the price of 2 B^2 bytes of HBM.
+//
 // An item only ever waits for items with a strictly smaller key and every pair processes its items in key order, so the
 // unfinished item with the smallest key can always run: no dead-lock as long as all CTAs are resident (grid <= #SMs).
 #pragma once
@@ -55,6 +62,11 @@ struct BwdFusedParams {
   int blocks_per_part;    // blocks_per_owner / n_parts
   int part;               // which part this launch covers
   int part_row0;          // part * blocks_per_part * Cb: first row of the part inside an owner's gradient rows
+  // stored-E mode (kStoredE): E = exp(logit - s) of the local rows x all columns, bf16 row-major, written by the forward
+  // (EpiLseT<.., true>); the coefficient tiles are then a transform of E instead of a recomputation of the cosines
+  const void* E;
+  long long ldE;
+  void* G;                // coefficient scratch [nbuf * Rb, Cb] bf16 (the stored-E transform writes it with plain stores)
   __host__ __device__ int global_cb(int cb) const {
     const int owner = cb / blocks_per_part;
     return owner * blocks_per_owner + part * blocks_per_part + (cb - owner * blocks_per_part);
@@ -182,13 +194,70 @@ __device__ __forceinline__ void wait_counter(const unsigned int* ctr, unsigned i
 template <int BN, int kEW>
 using FusedSmemT = GemmSmem<BN, 2, kEW * 4096, EpiGradT<kEW>::kScratchBytes>;
 
-template <int BN, int kEW>
-__global__ void __launch_bounds__(32 * (4 + kEW), 1)
+// Stored-E coefficient tile, one transform warp's share: kRows rows x 256 columns of the CTA's 128 x 256 half tile.  A warp
+// load covers one whole row (32 lanes x 16 bytes = 256 bf16); eight independent 16-byte loads per thread are in flight
+// before the first use.  g = E * (rinv[row] + cinv[col]); the matching pair gets the EpiGrad treatment.
+template <int kRows>
+__device__ __forceinline__ void stored_e_rows(const BwdFusedParams& p, const uint8_t* e_rows, long long e_pitch,
+                                              uint8_t* g_rows, long long g_pitch, const float* rinv_rows,
+                                              const float* cinv_cols, int row_g0, int col_g0, int lane) {
+  // e_rows / g_rows: first row of the share at the tile's first column; pitches in bytes
+  // row_g0: global column paired with the share's first row; col_g0: global column of the tile's first column
+  static_assert(kRows % 8 == 0, "rows are processed eight at a time");
+  float cv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cv[j] = __ldg(cinv_cols + lane * 8 + j);
+  const bool has_diag = (row_g0 < col_g0 + 256) && (row_g0 + kRows > col_g0);  // warp-uniform
+  float dcoef = 0.f;
+  bool zero_diag = false;
+  if (has_diag) {
+    dcoef = __ldg(p.scal);
+    zero_diag = __ldg(p.scal + 2) != 0.f;
+  }
+#pragma unroll 1
+  for (int r0 = 0; r0 < kRows; r0 += 8) {
+    uint4 ev[8];
+    float ri[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ev[i] = __ldcs(reinterpret_cast<const uint4*>(e_rows + (r0 + i) * e_pitch + lane * 16));
+      ri[i] = __ldg(rinv_rows + r0 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t w[4] = {ev[i].x, ev[i].y, ev[i].z, ev[i].w};
+      float g[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[2 * k] = __uint_as_float(w[k] << 16) * (ri[i] + cv[2 * k]);
+        g[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u) * (ri[i] + cv[2 * k + 1]);
+      }
+      if (has_diag) {
+        const int dj = row_g0 + r0 + i - (col_g0 + lane * 8);  // index of the matching column among this thread's 8
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j == dj) g[j] = zero_diag ? 0.f : g[j] - dcoef;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]);
+      o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]);
+      o.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(g_rows + (r0 + i) * g_pitch + lane * 16) = o;
+    }
+  }
+}
+
+// kTW = transform warps of the stored-E mode (0 = recompute mode): warps 4 + kEW .. 4 + kEW + kTW - 1.
+template <int BN, int kEW, int kTW>
+__global__ void __launch_bounds__(32 * (4 + kEW + kTW), 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
                          const __grid_constant__ CUtensorMap mGk, const __grid_constant__ CUtensorMap mGmn,
                          const __grid_constant__ CUtensorMap mGst, const __grid_constant__ CUtensorMap mdA,
                          const __grid_constant__ BwdOwnerMaps mdB, const BwdFusedParams p) {
+  constexpr bool kStoredE = kTW > 0;
+  static_assert(!kStoredE || BN == 256, "the stored-E transform is written for 256-column tiles");
   using S = FusedSmemT<BN, kEW>;
   using FusedGrad = EpiGradT<kEW>;
   using FusedStore = EpiStoreF32T<kEW>;
@@ -257,6 +326,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     uint32_t phase = 0;
     int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
     while (cur.next(p, it)) {
+      if (kStoredE && it.type == 0) continue;  // no tensor-core work: the epilogue warps transform E
       const int rb = it.blk / p.nbc;
       const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
@@ -307,6 +377,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       uint32_t phase = 0;
       int n = 0;
       while (cur.next(p, it)) {
+        if (kStoredE && it.type == 0) continue;
         const int acc_stage = n % kAcc;
         const uint32_t acc_phase = (n / kAcc) & 1;
         ++n;
@@ -342,7 +413,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       for (int last = n - 1; last >= 0 && last > n - 1 - kAcc; --last)
         mbar_wait(&tempty_bar[last % kAcc], (last / kAcc) & 1);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEW) {
     // ===================== epilogue warps (both CTAs) =====================
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -364,6 +435,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
         pending = -1;
       }
+      if (kStoredE && it.type == 0) continue;  // the transform warps own the coefficient tiles
       const int acc_stage = n % kAcc;
       const uint32_t acc_phase = (n / kAcc) & 1;
       ++n;
@@ -409,6 +481,37 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     }
     if (pending >= 0) publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
     FusedGrad::finish(gp, carry, lane);
+  } else if (kStoredE && warp >= 4 + kEW) {
+    // ===================== transform warps (stored-E mode, both CTAs) =====================
+    constexpr int kRowsPerWarp = kBM / (kTW > 0 ? kTW : 1);
+    const int tw = warp - (4 + kEW);
+    int verified = -1;  // scratch buffers of blocks [0, verified + nbuf] are known to be free
+    uint8_t* g_base = static_cast<uint8_t*>(p.G);
+    while (cur.next(p, it)) {
+      if (it.type != 0) continue;
+      const int rb = it.blk / p.nbc;
+      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;
+      const int buf = it.blk % p.nbuf;
+      if (it.blk >= p.nbuf && it.blk - p.nbuf > verified) {
+        wait_counter(p.doneB + (it.blk - p.nbuf), wantB, lane);  // the buffer's previous block has been consumed
+        verified = it.blk - p.nbuf;
+      }
+      const int r0 = it.tm * 256 + static_cast<int>(cta_rank) * kBM + tw * kRowsPerWarp;  // first row inside the block
+      const int c0 = it.tn * BN;                                                          // first column inside the block
+      const long long grow0 = static_cast<long long>(rb) * p.Rb + r0;                     // local row
+      stored_e_rows<kRowsPerWarp>(p, static_cast<const uint8_t*>(p.E) + (grow0 * p.ldE + col0 + c0) * 2, p.ldE * 2,
+                                  g_base + ((static_cast<long long>(buf) * p.Rb + r0) * p.Cb + c0) * 2,
+                                  static_cast<long long>(p.Cb) * 2, p.rinv + grow0, p.cinv + col0 + c0,
+                                  static_cast<int>(grow0) + p.diag_offset, col0 + c0, lane);
+      // all transform warps' stores -> one gpu-scope release per CTA (the consumers read the scratch through TMA)
+      fence_proxy_async_all();
+      asm volatile("bar.sync 1, %0;" ::"n"((kTW > 0 ? kTW : 1) * 32) : "memory");
+      if (tw == 0 && lane == 0) {
+        __threadfence();
+        fence_proxy_async_all();
+        red_release_gpu_add(p.doneA + it.blk, 1u);
+      }
+    }
   }
 
   tcgen05_fence_before();

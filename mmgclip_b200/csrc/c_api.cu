@@ -280,7 +280,7 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (prec == MMG_PREC_BF16) {
     // One persistent launch over all logit tiles; the tile lives only in TMEM.
-    return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, st);
+    return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, nullptr, 0, st);
   }
   if (workspace_bytes < mmg_infonce_workspace_bytes(prec, rows, cols, D))
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_fwd: workspace too small");
@@ -300,6 +300,54 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
       MMG_TRY(simt_lse_block(S, lds, rb, cb, r0, c0, diag_offset, scale, rowsum, colsum, diag, st));
     }
   }
+  return 0;
+}
+
+int mmg_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts) {
+  if (rows <= 0 || cols <= 0 || D <= 0) return 0;
+  return tc_infonce_stored_supported(rows, cols, D, n_owners, n_parts);
+}
+
+int mmg_infonce_fwd_store(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+                          const float* scale, float* rowsum, float* colsum, float* diag, void* e_out, long long lde,
+                          mmg_stream_t stream) {
+  MMG_TRY(check_infonce_args("mmg_infonce_fwd_store", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  MMG_REQ(rowsum);
+  MMG_REQ(colsum);
+  MMG_REQ(diag);
+  MMG_REQ(e_out);
+  if (lde < cols || (lde & 7) != 0 || (reinterpret_cast<uintptr_t>(e_out) & 15) != 0)
+    return set_error(MMG_ERR_BAD_ALIGN, "mmg_infonce_fwd_store: E needs a pitch >= cols that is a multiple of 8 and a "
+                                        "16-byte aligned base");
+  return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, e_out, lde,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_bwd_stored(const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows, int cols,
+                           int D, int diag_offset, const float* scale, const float* rinv, const float* cinv,
+                           const float* scal, float* dA, float* const* dB_owners, int n_owners, int n_parts, int part,
+                           void* workspace, size_t workspace_bytes, mmg_stream_t stream) {
+  MMG_TRY(check_infonce_args("mmg_infonce_bwd_stored", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  MMG_REQ(e_stored);
+  MMG_REQ(rinv);
+  MMG_REQ(cinv);
+  MMG_REQ(scal);
+  MMG_REQ(dA);
+  MMG_REQ(workspace);
+  if (dB_owners == nullptr || n_owners < 1 || n_owners > 8)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_stored: 1..8 owners (got %d)", n_owners);
+  for (int i = 0; i < n_owners; ++i)
+    if (dB_owners[i] == nullptr) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_stored: owner %d is NULL", i);
+  if (n_parts < 1 || part < 0 || part >= n_parts)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_stored: bad column part %d of %d", part, n_parts);
+  int used = 0;
+  MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, dB_owners,
+                               n_owners, n_parts, part, nullptr, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream), &used, e_stored, lde));
+  if (!used)
+    return set_error(MMG_ERR_UNSUPPORTED_SHAPE,
+                     "mmg_infonce_bwd_stored: shape not covered (see mmg_infonce_stored_supported), misaligned E or "
+                     "outputs, or workspace smaller than mmg_infonce_workspace_bytes()");
   return 0;
 }
 

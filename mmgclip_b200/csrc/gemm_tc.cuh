@@ -265,7 +265,11 @@ using EpiStoreF32 = EpiStoreF32T<8>;
 // accumulate in registers for the whole tile, column sums are pre-reduced over the thread's 4 rows and finished with a
 // 3-stage / 7-shuffle transposing butterfly.  Interior tiles take a mask-free path; the diagonal is looked at only in
 // tiles that contain it.
-template <int kW>
+// kStoreE: additionally keep E (bf16, row-major [M, N]) for a backward that transforms it into the gradient coefficients
+// instead of recomputing the cosines (bwd_fused.cuh, stored-E mode).  Each warp packs its 32 x 64 block of E into a
+// 128B-swizzled staging box (conflict-free 4-byte stores straight from the 16x256b fragments) and ships it with a TMA
+// bulk-tensor store, like EpiGrad does for g.
+template <int kW, bool kStoreE = false>
 struct EpiLseT {
   struct Params {
     float* rowsum;            // [M]   (atomic accumulate; zero-initialised by the caller)
@@ -275,13 +279,17 @@ struct EpiLseT {
     int diag_offset;          // global column index of local row 0 (rank offset in the sharded case)
   };
   static constexpr int kWarps = kW;
-  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return 0; }
+  // kStoreE: one [32 rows x 64 bf16] (4 KB, 128B-swizzled) staging box per epilogue warp
+  template <int BN> __host__ __device__ static constexpr int staging_bytes() { return kStoreE ? kWarps * 4096 : 0; }
   static constexpr int kScratchBytes = 0;
-  static __device__ __forceinline__ void finish(const Params&, float, int) {}
+  static __device__ __forceinline__ void finish(const Params&, float, int lane) {
+    if (kStoreE && lane == 0) tma_store_wait_all();
+  }
 
   template <int BN, bool kMasked, bool kDiag>
   static __device__ __forceinline__ void tile(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
-                                              int q, int lane, float s, float sl2) {
+                                              int q, int lane, float s, float sl2, const CUtensorMap* cmap,
+                                              uint8_t* box) {
     constexpr int kCols = BN / (kWarps / 4);
     const int lr = lane >> 2;          // row within an 8-row group
     const int lc = (lane & 3) * 2;     // first of this thread's two columns within an 8-column group
@@ -296,9 +304,14 @@ struct EpiLseT {
       tmem_ld_16x256b_x4(tacc + cl, va);                  // lanes 32q + 0..15  -> rows i = 0, 1
       tmem_ld_16x256b_x4(tacc + (16u << 16) + cl, vb);    // lanes 32q + 16..31 -> rows i = 2, 3
       tmem_ld_wait();
+      if (kStoreE && (ch & 1) == 0) {
+        if (lane == 0) tma_store_wait_read();  // this warp's previous box has left shared memory
+        __syncwarp();
+      }
       float cp[8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        float evs[2][4];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = c0 + 8 * g + lc + e;
@@ -314,8 +327,27 @@ struct EpiLseT {
             if (kMasked) ev = (rbase + 8 * i < M && col < N) ? ev : 0.f;
             racc[i] += ev;
             csum += ev;
+            evs[e][i] = ev;
           }
           cp[2 * g + e] = csum;
+        }
+        if (kStoreE) {
+          // rows lr + 8i (row & 7 == lr), columns 8g + lc, +1 of this 32-column chunk: 16-byte unit (ch & 1) * 4 + g of
+          // the box row, 4 bytes at (lane & 3) * 4 inside it -- 32 distinct banks per store instruction
+          const uint32_t unit = static_cast<uint32_t>((ch & 1) * 4 + g) ^ static_cast<uint32_t>(lr);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint32_t*>(box + (lr + 8 * i) * 128 + (unit << 4) + (lane & 3) * 4) =
+                pack_bf16x2(evs[0][i], evs[1][i]);
+        }
+      }
+      if (kStoreE && ((ch & 1) == 1 || ch + 1 == kCols / 32 || (kMasked && c0 + 32 >= N))) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          // columns / rows beyond the matrix are clipped by the hardware
+          tma_store_2d(cmap, box, n0 + half * kCols + (ch & ~1) * 32, m0 + q * 32);
+          tma_store_commit();
         }
       }
       // transposing butterfly over the 8 lanes that share lane%4: afterwards this lane holds the full 32-row sum of
@@ -365,15 +397,16 @@ struct EpiLseT {
   static __device__ __forceinline__ void run(const Params& P, uint32_t tacc, int m0, int n0, int M, int N, int half,
                                              int q, int lane, int ewarp, float* smem, const CUtensorMap* cmap,
                                              uint8_t* staging, int force_atomic, float& carry) {
-    (void)ewarp; (void)smem; (void)cmap; (void)staging; (void)force_atomic; (void)carry;
+    (void)smem; (void)force_atomic; (void)carry;
     const float s = __ldg(P.scale_ptr);
     const float sl2 = s * 1.4426950408889634f;
     const bool interior = (m0 + kBM <= M) && (n0 + BN <= N);
     // does this tile contain matching pairs?  columns of rows [m0, m0+128) are [m0+off, m0+off+128)
     const bool has_diag = (m0 + P.diag_offset < n0 + BN) && (m0 + P.diag_offset + kBM > n0);
-    if (interior && !has_diag) tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
-    else if (interior) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
-    else tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2);
+    uint8_t* box = staging + ewarp * 4096;
+    if (interior && !has_diag) tile<BN, false, false>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2, cmap, box);
+    else if (interior) tile<BN, false, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2, cmap, box);
+    else tile<BN, true, true>(P, tacc, m0, n0, M, N, half, q, lane, s, sl2, cmap, box);
   }
 };
 

@@ -35,7 +35,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
                             cudaStream_t st);
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
-                   float* rowsum, float* colsum, float* diag, cudaStream_t st);
+                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st);
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
                           const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
@@ -52,7 +52,9 @@ size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D);
 int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                          float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used);
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used,
+                         const void* e_stored = nullptr, long long lde = 0);
+int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts);
 
 // Zero-shot prompt scoring on the tensor pipe (zeroshot_tc.cu): 3xTF32, fp32-faithful, HBM-bound at large N.
 size_t tc_zeroshot_workspace_bytes(int C, int D);

@@ -222,6 +222,7 @@ static int prefetch_distance() {
 // measured slower on B200 at 32768^2 x 512 (forward 0.754 vs 0.723 ms, coefficient launches 1.095 vs 1.019 ms): the
 // staging boxes of 16 warps cost an operand-ring stage, which matters more than the extra latency hiding.
 using EpiLse = EpiLseT<8>;
+using EpiLseStore = EpiLseT<8, true>;
 using EpiGrad = EpiGradT<8>;
 struct TileCfg { int BN, cg; };
 static TileCfg pick_tile(int M, int N, int work_items_per_tile = 0) {
@@ -335,7 +336,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
-                   float* rowsum, float* colsum, float* diag, cudaStream_t st) {
+                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st) {
   const TileCfg tcfg = pick_tile(rows, cols);
   TcOperand A{a_hat, D, 0}, B{b_hat, D, 0};
   CUtensorMap ma, mb;
@@ -346,6 +347,14 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
   GemmProblem p1 = empty_problem();
   EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
+  if (e_out != nullptr) {
+    // also keep E = exp(logit - s) as bf16 [rows, cols] for the stored-E backward: box = one epilogue warp's 32 x 64 block
+    CUtensorMap mc;
+    if ((rc = make_tmap(&mc, e_out, cols, rows, lde, 32)) != 0) return rc;
+    EpiLseStore::Params es;
+    es.rowsum = rowsum; es.colsum = colsum; es.diag = diag; es.scale_ptr = scale; es.diag_offset = diag_offset;
+    MMG_DISPATCH(EpiLseStore, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, es, es, st);
+  }
   MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
 
@@ -486,6 +495,17 @@ int tc_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, 
   return n;
 }
 
+// Can the stored-E backward take this shape?  (Same conditions as the fused launch; the forward must then have been
+// asked to keep E.)
+int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts) {
+  if (n_owners < 1 || n_owners > kMaxOwners || (cols % n_owners) != 0 || ((cols / n_owners) % 256) != 0) return 0;
+  if (n_parts < 1) return 0;
+  const int owner_rows = cols / n_owners;
+  if (n_parts > 1 && ((owner_rows % n_parts) != 0 || ((owner_rows / n_parts) % 256) != 0)) return 0;
+  const FusedPlan f = fused_plan(rows, cols, D, n_parts > 1 ? owner_rows / n_parts : 0, n_owners > 1);
+  return f.ok && pick_tile(rows, cols).BN == 256 ? 1 : 0;
+}
+
 size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
   const FusedPlan f = fused_plan(rows, cols, D);
   return f.ok ? f.total_bytes : 0;
@@ -494,8 +514,12 @@ size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
 int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                          float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, int* used, const void* e_stored,
+                         long long lde) {
   *used = 0;
+  if (e_stored != nullptr && (dlogscale_acc != nullptr || (reinterpret_cast<uintptr_t>(e_stored) & 15) != 0 ||
+                              (lde & 7) != 0 || lde < cols))
+    return 0;  // stored-E mode has no sum g*cos (the cosines are gone) and needs 16-byte aligned rows
   if (n_owners < 1 || n_owners > kMaxOwners || (cols % n_owners) != 0 || ((cols / n_owners) % 256) != 0) return 0;
   if (n_parts < 1 || part < 0 || part >= n_parts) return 0;
   const int owner_rows = cols / n_owners;
@@ -506,9 +530,11 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   for (int i = 0; i < n_owners; ++i)
     if (dB_owners[i] == nullptr || !out_tma_ok(dB_owners[i], D)) return 0;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return 0;
-  const int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
+  int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
+  if (e_stored != nullptr) BN = 256;
   BwdFusedParams p;
   fill_schedule(&p, f, rows, cols, D, n_owners, n_parts, part, BN);
+  p.E = e_stored; p.ldE = lde; p.G = workspace;
   p.diag_offset = diag_offset;
   p.rinv = rinv; p.cinv = cinv; p.scale = scale; p.scal = scal; p.dlogscale_acc = dlogscale_acc;
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
@@ -534,14 +560,17 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     if ((rc = make_out_tmap_f32(&mdB.m[i], dB_owners[o], D, owner_rows / n_parts, D)) != 0) return rc;
   }
 
-  const int ew = env_int("MMG_FUSED_EPI_WARPS", 8) == 16 ? 16 : 8;
-  const int variant = (BN == 128 ? 1 : 0) + (ew == 16 ? 2 : 0);
-  auto kern = infonce_bwd_fused_kernel<256, 8>;
+  constexpr int kStoredTW = 8;  // transform warps of the stored-E kernel
+  int ew = env_int("MMG_FUSED_EPI_WARPS", 8) == 16 ? 16 : 8;
+  if (e_stored != nullptr) ew = 8;
+  const int variant = e_stored != nullptr ? 4 : (BN == 128 ? 1 : 0) + (ew == 16 ? 2 : 0);
+  auto kern = infonce_bwd_fused_kernel<256, 8, 0>;
   int smem_bytes = FusedSmemT<256, 8>::kTotal;
-  if (variant == 1) { kern = infonce_bwd_fused_kernel<128, 8>; smem_bytes = FusedSmemT<128, 8>::kTotal; }
-  if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
-  if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
-  static bool configured[4] = {false, false, false, false};
+  if (variant == 1) { kern = infonce_bwd_fused_kernel<128, 8, 0>; smem_bytes = FusedSmemT<128, 8>::kTotal; }
+  if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16, 0>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
+  if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16, 0>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
+  if (variant == 4) { kern = infonce_bwd_fused_kernel<256, 8, kStoredTW>; smem_bytes = FusedSmemT<256, 8>::kTotal; }
+  static bool configured[5] = {false, false, false, false, false};
   if (!configured[variant]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
@@ -551,7 +580,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pairs * 2);
-  cfg.blockDim = dim3(32 * (4 + ew));
+  cfg.blockDim = dim3(32 * (4 + ew + (variant == 4 ? kStoredTW : 0)));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -277,9 +277,29 @@ def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: b
     return du, dub
 
 
-def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, colsum=None):
-    """Accumulate row/column sums of exp(s*cos - s) for local rows `a` against all columns `b`."""
-    _need_cuda(a, b, scale)
+# Stored-E mode of the bf16 InfoNCE: the forward keeps E = exp(logit - s) as bf16 [rows, cols] and the backward transforms
+# it into the gradient coefficients instead of recomputing the cosines on the tensor cores (4 instead of 6 B^2 D FLOPs in
+# the backward) -- at the price of 2*rows*cols bytes of HBM, i.e. the O(B*D) memory bound is given up on purpose.  Used
+# when E fits the budget below (MiB; 0 = never), the shape is covered by the fused backward and logit_scale carries no
+# gradient (the cosines are gone, so sum g*cos cannot be formed).
+_store_e_mb = int(os.environ.get("MMGCLIP_B200_STORE_E_MB", "0"))
+
+
+def set_store_e_budget_mb(mb: int) -> None:
+    global _store_e_mb
+    _store_e_mb = int(mb)
+
+
+def want_store_e(rows: int, cols: int, D: int, prec: str, need_dscale: bool, n_owners: int = 1, n_parts: int = 1) -> bool:
+    if prec != "bf16" or need_dscale or _store_e_mb <= 0 or rows * cols * 2 > (_store_e_mb << 20):
+        return False
+    return bool(_lib.load().mmg_infonce_stored_supported(rows, cols, D, n_owners, n_parts))
+
+
+def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, colsum=None, e_out=None):
+    """Accumulate row/column sums of exp(s*cos - s) for local rows `a` against all columns `b`.
+    ``e_out`` (bf16 [rows, cols], bf16 path only): also keep E for the stored-E backward."""
+    _need_cuda(a, b, scale, e_out)
     rows, D = a.shape
     cols = b.shape[0]
     dev = a.device
@@ -289,6 +309,12 @@ def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, c
         colsum = torch.zeros(cols, dtype=torch.float32, device=dev)
     diag = torch.empty(rows, dtype=torch.float32, device=dev)
     lib = _lib.load()
+    if e_out is not None:
+        if prec != "bf16" or e_out.dtype != torch.bfloat16 or tuple(e_out.shape) != (rows, cols) or e_out.stride(1) != 1:
+            raise ValueError("e_out must be a bf16 [rows, cols] tensor with contiguous rows (bf16 path only)")
+        check(lib.mmg_infonce_fwd_store(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum), _p(colsum),
+                                        _p(diag), _p(e_out), e_out.stride(0), _stream()), "mmg_infonce_fwd_store")
+        return rowsum, colsum, diag
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
     ws = _workspace(dev, nbytes)
     check(lib.mmg_infonce_fwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum), _p(colsum),
@@ -305,7 +331,7 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
 
 def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, prec: str,
                          block_rows: int = 0, block_cols: int = 0, a32=None, b32=None, diag=None,
-                         need_dscale: bool = True):
+                         need_dscale: bool = True, e_stored=None):
     """Returns (dA [rows,D], dB_partial [cols,D], sum g*cos) -- see mmg_infonce_bwd in the header.
 
     ``need_dscale=False`` (the scale carries no gradient -- the reference's CUDA behaviour) skips the
@@ -313,7 +339,11 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
 
     When the fp32 embeddings (a32 [rows,D]; b32 [rows,D] = the column-side rows paired with the local rows) are supplied
     to the bf16 path, the matching-pair term of the
-    gradient is applied from them in fp32 (mmg_infonce_bwd_diag) instead of through the bf16 contraction."""
+    gradient is applied from them in fp32 (mmg_infonce_bwd_diag) instead of through the bf16 contraction.
+
+    ``e_stored`` (bf16 [rows, cols] written by ``infonce_forward_raw(e_out=...)``): stored-E backward, no ``sum g*cos``."""
+    if e_stored is not None and need_dscale:
+        raise ValueError("the stored-E backward cannot produce d/d logit_scale")
     rows, D = a.shape
     cols = b.shape[0]
     dev = a.device
@@ -352,9 +382,15 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     ws = _workspace(dev, nbytes)
     if _bwd_probe is not None:
         _bwd_probe[0].record()
-    check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
-                              _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
-                              _stream()), "mmg_infonce_bwd")
+    if e_stored is not None:
+        owners = (ctypes.c_void_p * 1)(dB.data_ptr())
+        check(lib.mmg_infonce_bwd_stored(_p(a), _p(b), _p(e_stored), e_stored.stride(0), rows, cols, D, diag_offset,
+                                         _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), owners, 1, 1, 0, _p(ws),
+                                         ws.numel(), _stream()), "mmg_infonce_bwd_stored")
+    else:
+        check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+                                  _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
+                                  _stream()), "mmg_infonce_bwd")
     if _bwd_probe is not None:
         _bwd_probe[1].record()
     return dA, dB, dls
@@ -609,9 +645,13 @@ class _InfoNCEFn(torch.autograd.Function):
         if b_hat.shape != a_hat.shape:
             raise ValueError(f"paired InfoNCE needs equal shapes, got {tuple(a_hat.shape)} and {tuple(b_hat.shape)}")
         s = scale.detach().reshape(()).to(device=a_hat.device, dtype=torch.float32).contiguous()
-        rowsum, colsum, diag = infonce_forward_raw(a_op, b_op, s, 0, prec)
+        e_mat = None
+        if want_store_e(n, n, D, prec, ctx.needs_input_grad[2]) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            e_mat = torch.empty((n, n), dtype=torch.bfloat16, device=a_hat.device)
+        rowsum, colsum, diag = infonce_forward_raw(a_op, b_op, s, 0, prec, e_out=e_mat)
         loss = infonce_loss_raw(rowsum, colsum, diag, s, 0.5 / n)
         ctx.prec = prec
+        ctx.e_mat = e_mat  # not an input or output of the function: kept on the ctx
         # fp32 embeddings (when that is what the caller holds) serve the matching-pair term of the backward
         keep32 = prec == "bf16" and a_hat.dtype == torch.float32 and b_hat.dtype == torch.float32
         ctx.keep32 = keep32
@@ -632,7 +672,9 @@ class _InfoNCEFn(torch.autograd.Function):
             a32 = b32 = diag = None
         n = a_op.shape[0]
         dA, dB, dls = infonce_backward_raw(a_op, b_op, s, rowsum, colsum, grad_loss, 0.5 / n, 0, ctx.prec,
-                                           a32=a32, b32=b32, diag=diag, need_dscale=ctx.needs_input_grad[2])
+                                           a32=a32, b32=b32, diag=diag, need_dscale=ctx.needs_input_grad[2],
+                                           e_stored=ctx.e_mat)
+        ctx.e_mat = None
         dscale = None
         if ctx.needs_input_grad[2]:
             dscale = (dls / s).reshape(ctx.scale_shape)  # d loss / d s ; sum g*cos = s * dloss/ds
