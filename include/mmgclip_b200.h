@@ -206,8 +206,8 @@ int mmg_adamw_step(float* const* params, const float* const* grads, float* const
                    float eps, float weight_decay, long long* step_state, mmg_stream_t stream);
 
 /* Introspection (host only, no GPU): the static work-item schedule of the fused backward for CTA pair `pair` of `pairs`
- * -- rows of items[] are {type (0 coefficient tile, 1 dA slice, 2 dB slice), block, tm, tn, kb0, nkb, global column
- * block}; info[8] = {Rb, Cb, nbuf, nA, nB, nblk, kslI, kslT}.  Returns the pair's item count (0 = shape not covered).
+ * -- rows of items[] are 8 ints {type (0 coefficient tile, 1 dA slice, 2 dB slice), block, tm, tn, kb0, nkb, global
+ * column block, row block}; info[8] = {Rb, Cb, nbuf, nA, nB, nblk, kslI, kslT}.  Returns the pair's item count (0 = shape not covered).
  * tests/test_fused_schedule_cpu.py uses it to check the schedule's ordering / dead-lock-freedom invariants. */
 int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
                            int max_items, int* info);

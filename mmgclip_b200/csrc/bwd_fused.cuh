@@ -67,6 +67,20 @@ struct BwdFusedParams {
   const void* E;
   long long ldE;
   void* G;                // coefficient scratch [nbuf * Rb, Cb] bf16 (the stored-E transform writes it with plain stores)
+  // Block order.  Block index blk (the order the blocks are walked in) -> (row block, column block of this launch).
+  // Blocks are visited super-tile by super-tile (sr x sc blocks, row-major inside and across super-tiles) so that the
+  // gradient rows a super-tile accumulates into and its operand rows can stay in L2.  sr = sc = 1 (the default: measured
+  // no better with larger super-tiles, see fill_schedule) is plain row-major.
+  int sr, sc;
+  __host__ __device__ void block_rc(int blk, int& rb, int& cb) const {
+    const int per = sr * sc;
+    const int sidx = blk / per, w = blk - sidx * per;
+    const int scols = nbc / sc;
+    const int srow = sidx / scols, scol = sidx - srow * scols;
+    const int wr = w / sc;
+    rb = srow * sr + wr;
+    cb = scol * sc + (w - wr * sc);
+  }
   __host__ __device__ int global_cb(int cb) const {
     const int owner = cb / blocks_per_part;
     return owner * blocks_per_owner + part * blocks_per_part + (cb - owner * blocks_per_part);
@@ -327,8 +341,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
     while (cur.next(p, it)) {
       if (kStoredE && it.type == 0) continue;  // no tensor-core work: the epilogue warps transform E
-      const int rb = it.blk / p.nbc;
-      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;  // first global column of the block
+      int rb, cbl;
+      p.block_rc(it.blk, rb, cbl);
+      const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       if (it.type != 0 && it.blk > verified) {
         wait_counter(p.doneA + it.blk, wantA, lane);
@@ -439,8 +454,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       const int acc_stage = n % kAcc;
       const uint32_t acc_phase = (n / kAcc) & 1;
       ++n;
-      const int rb = it.blk / p.nbc;
-      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;  // first global column of the block
+      int rb, cbl;
+      p.block_rc(it.blk, rb, cbl);
+      const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tcgen05_fence_after();
@@ -489,8 +505,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     uint8_t* g_base = static_cast<uint8_t*>(p.G);
     while (cur.next(p, it)) {
       if (it.type != 0) continue;
-      const int rb = it.blk / p.nbc;
-      const int col0 = p.global_cb(it.blk - rb * p.nbc) * p.Cb;
+      int rb, cbl;
+      p.block_rc(it.blk, rb, cbl);
+      const int col0 = p.global_cb(cbl) * p.Cb;
       const int buf = it.blk % p.nbuf;
       if (it.blk >= p.nbuf && it.blk - p.nbuf > verified) {
         wait_counter(p.doneB + (it.blk - p.nbuf), wantB, lane);  // the buffer's previous block has been consumed

@@ -458,10 +458,22 @@ static void fill_schedule(BwdFusedParams* pp, const FusedPlan& f, int rows, int 
   p.part = part;
   p.part_row0 = part * p.blocks_per_part * f.Cb;
   if (p.nbuf > p.nblk) p.nbuf = p.nblk < 1 ? 1 : p.nblk;
+  // super-tile of the block order (BwdFusedParams::block_rc).  Default 1 x 1 = row-major: at 32768^2 x 512 super-tiles
+  // of 2x2 .. 4x4 blocks measured the same or slightly slower (2.52 -> 2.54 ms; stored-E 2.16 -> 2.20 ms) -- the launch is
+  // bound by the block-level doneA / doneB dependencies, not by L2 capacity.  MMG_FUSED_SR / MMG_FUSED_SC select others.
+  int sr = env_int("MMG_FUSED_SR", 1), sc = env_int("MMG_FUSED_SC", 1);
+  const int nbr = rows / f.Rb;
+  if (sr <= 0) sr = 1;
+  if (sc <= 0) sc = 1;
+  while (sr > 1 && (nbr % sr) != 0) sr >>= 1;
+  while (sc > 1 && (p.nbc % sc) != 0) sc >>= 1;
+  if (sr < 1 || (nbr % sr) != 0) sr = 1;
+  if (sc < 1 || (p.nbc % sc) != 0) sc = 1;
+  p.sr = sr; p.sc = sc;
 }
 
 // Host-side enumeration of the fused backward's static schedule (no GPU needed): the items CTA pair `pair` of `pairs`
-// walks, in order, as rows of {type, block, tm, tn, kb0, nkb, global column block}.  info[8] = {Rb, Cb, nbuf, nA, nB,
+// walks, in order, as rows of {type, block, tm, tn, kb0, nkb, global column block, row block}.  info[8] = {Rb, Cb, nbuf, nA, nB,
 // nblk, kslI, kslT}.  Returns the pair's item count (items beyond max_items are counted but not written), 0 when the
 // shape is not covered by the fused kernel.  Used by tests/test_fused_schedule_cpu.py to check the dead-lock freedom
 // argument of bwd_fused.cuh for arbitrary shapes.
@@ -485,10 +497,11 @@ int tc_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, 
   int n = 0;
   while (cur.next(p, it)) {
     if (items != nullptr && n < max_items) {
-      int* o = items + 7 * n;
-      const int rb = it.blk / p.nbc;
+      int* o = items + 8 * n;
+      int rb, cbl;
+      p.block_rc(it.blk, rb, cbl);
       o[0] = it.type; o[1] = it.blk; o[2] = it.tm; o[3] = it.tn; o[4] = it.kb0; o[5] = it.nkb;
-      o[6] = p.global_cb(it.blk - rb * p.nbc);
+      o[6] = p.global_cb(cbl); o[7] = rb;
     }
     ++n;
   }

@@ -82,7 +82,7 @@ def time_(B, D):
         for stored in order:
             e = E if stored else None
             tf, tb = [], []
-            for _ in range(8):
+            for _ in range(int(os.environ.get("PROBE_REPS", "8"))):
                 ev[0].record()
                 r = ops.infonce_forward_raw(ab, bb, s, 0, "bf16", e_out=e)
                 ev[1].record()

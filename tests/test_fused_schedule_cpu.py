@@ -20,10 +20,10 @@ def _schedule(rows, cols, D, n_owners, n_parts, part, pairs):
     info = (ctypes.c_int * 8)()
     per_pair = []
     for pair in range(pairs):
-        buf = (ctypes.c_int * (7 * MAX_ITEMS))()
+        buf = (ctypes.c_int * (8 * MAX_ITEMS))()
         n = lib.mmg_fused_bwd_schedule(rows, cols, D, n_owners, n_parts, part, pairs, pair, buf, MAX_ITEMS, info)
         assert 0 <= n <= MAX_ITEMS
-        per_pair.append([tuple(buf[7 * i:7 * i + 7]) for i in range(n)])
+        per_pair.append([tuple(buf[8 * i:8 * i + 8]) for i in range(n)])
     keys = ("Rb", "Cb", "nbuf", "nA", "nB", "nblk", "kslI", "kslT")
     return per_pair, dict(zip(keys, info))
 
@@ -62,10 +62,20 @@ def test_schedule_is_complete_and_deadlock_free(shape, pairs):
     assert len(b_items) == nB * nblk
     assert {k[1] for k in seen} == set(range(nblk))
 
+    # the block order is a bijection between block indices and (row block, global column block) cells of the grid
+    cell = {}
+    for items in per_pair:
+        for it in items:
+            cell.setdefault(it[1], set()).add((it[7], it[6]))
+    assert all(len(c) == 1 for c in cell.values())
+    cells = {next(iter(c)) for c in cell.values()}
+    assert len(cells) == nblk
+    assert {c[0] for c in cells} == set(range(rows // info["Rb"]))
+
     # K-slices tile the contraction: per (type, block, tm, tn) the [kb0, kb0+nkb) ranges are disjoint and contiguous
     slices = {}
     for items in per_pair:
-        for t, blk, tm, tn, kb0, nkb, _ in items:
+        for t, blk, tm, tn, kb0, nkb, _, _ in items:
             if t != 0:
                 slices.setdefault((t, blk, tm, tn), []).append((kb0, nkb))
     for (t, blk, tm, tn), sl in slices.items():
@@ -119,3 +129,12 @@ def test_global_column_block_mapping_of_parts():
 def test_unsupported_shape_reports_zero():
     per_pair, _ = _schedule(100, 100, 64, 1, 1, 0, 2)
     assert per_pair == [[], []]
+
+
+@pytest.mark.parametrize("sr,sc", [(1, 1), (2, 4), (4, 2), (8, 16), (3, 5)])
+def test_block_order_super_tiles(monkeypatch, sr, sc):
+    """Any super-tile shape (non-dividing requests fall back to a dividing one) keeps the schedule complete and live."""
+    monkeypatch.setenv("MMG_FUSED_SR", str(sr))
+    monkeypatch.setenv("MMG_FUSED_SC", str(sc))
+    test_schedule_is_complete_and_deadlock_free((32768, 32768, 512, 1, 1, 0), 74)
+    test_schedule_is_complete_and_deadlock_free((4096, 32768, 512, 8, 2, 1), 74)
