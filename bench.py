@@ -43,12 +43,13 @@ def alg_flops(b, e_i, e_t, d):
     return 6.0 * b * b * d + 4.0 * b * (e_i + e_t) * d
 
 
-def ncu_traffic_bytes():
+def ncu_traffic_bytes(stored_e=False):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/r01_ncu_top_kernels.md); None if the summary is missing."""
+    captures (profiles/r01c_ncu_top_kernels.md, r01d_ncu_stored_e_bwd.md); None if the summary is missing."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["dominant_kernel_dram_bytes_per_launch"])
+            key = "dominant_kernel_dram_bytes_per_launch" + ("_stored_e" if stored_e else "")
+            return float(json.load(f)[key])
     except Exception:  # noqa: BLE001
         return None
 
@@ -129,7 +130,7 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None, symm=None):
+def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None, symm=None, stored_e=None):
     cfg = {"workload": f"mmg-clip hot path: LinearProjectionLayer heads {E_IMG}->{D_PROJ} (image, text) + L2 normalise + "
                        f"symmetric CLIPLoss fwd+bwd to head-weight grads, global batch {GLOBAL_BATCH}, synthetic "
                        f"ConvNeXt-like / BERT-like features",
@@ -146,6 +147,10 @@ def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=Non
     if graph is not None:
         cfg["launch"] = ("one CUDA graph replay per step (mmgclip_b200.graph.GraphedStep)" if graph
                          else "eager (one host launch per kernel)")
+    if stored_e is not None:
+        cfg["backward"] = ("stored-E: the forward keeps exp(logit - s) as bf16 [rows, cols] (2*rows*cols bytes of HBM) and "
+                           "the fused backward transforms it into the gradient coefficients" if stored_e else
+                           "recompute: the fused backward recomputes the cosines on the tensor cores (O(B*D) memory)")
     if sample_batch is not None:
         cfg["cpu_sample_batch"] = sample_batch
     return cfg
@@ -459,11 +464,16 @@ def run_gpu(args):
     fl = alg_flops(B, E_IMG, E_TXT, D_PROJ)
     ach = fl / (ms_value * 1e-3) / world / 1e12
     dom = kernels["backward_fused"] if kernels else None
+    # stored-E mode (ops.want_store_e): the single-GPU loss keeps E in the forward and the backward does no recomputation
+    stored_e = world == 1 and ops.want_store_e(bl, B, D_PROJ, prec, False)
     if live_bwd_ms is not None and live_bwd_ms > 0:
         f_bwd = 4.0 * bl * B * D_PROJ  # dI + dT of this rank's rows (the recomputed cosines are not counted)
-        dom = {"kernel": "infonce_bwd_fused_kernel (one persistent launch = the whole InfoNCE backward of the step)",
+        dom = {"kernel": "infonce_bwd_fused_kernel (one persistent launch = the whole InfoNCE backward of the step"
+                         + ("; stored-E mode: coefficients transformed from the forward's bf16 E, no recomputation)"
+                            if stored_e else ")"),
                "tflops": f_bwd / (live_bwd_ms * 1e-3) / 1e12, "ms_per_launch": live_bwd_ms,
-               "flops_per_launch": f_bwd, "tflops_executed": 1.5 * f_bwd / (live_bwd_ms * 1e-3) / 1e12,
+               "flops_per_launch": f_bwd,
+               "tflops_executed": (1.0 if stored_e else 1.5) * f_bwd / (live_bwd_ms * 1e-3) / 1e12,
                "how": "CUDA events recorded around the launch on its own stream inside the timed region (captured into "
                       "the replayed graph as external event-record nodes); value of the last timed step"}
     line = {
@@ -471,7 +481,7 @@ def run_gpu(args):
         "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active(),
-                                  symm=symm_allreduce_active()),
+                                  symm=symm_allreduce_active(), stored_e=stored_e),
         "loss": loss_value,
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
@@ -490,7 +500,7 @@ def run_gpu(args):
                      "frac": (dom["tflops"] if dom else ach) / peaks["sustained"],
                      "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained; burst = "
                                     + str(peaks["burst"]) + ")",
-                     "traffic": ncu_traffic_bytes(),
+                     "traffic": ncu_traffic_bytes(stored_e),
                      "dominant_kernel_live": dom if (live_bwd_ms is not None and live_bwd_ms > 0) else None,
                      "whole_step": {"algorithmic_flops_per_step": fl, "achieved": ach, "frac": ach / peaks["sustained"],
                                     "frac_of_burst_peak": ach / peaks["burst"]},

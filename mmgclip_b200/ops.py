@@ -281,8 +281,14 @@ def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: b
 # it into the gradient coefficients instead of recomputing the cosines on the tensor cores (4 instead of 6 B^2 D FLOPs in
 # the backward) -- at the price of 2*rows*cols bytes of HBM, i.e. the O(B*D) memory bound is given up on purpose.  Used
 # when E fits the budget below (MiB; 0 = never), the shape is covered by the fused backward and logit_scale carries no
-# gradient (the cosines are gone, so sum g*cos cannot be formed).
-_store_e_mb = int(os.environ.get("MMGCLIP_B200_STORE_E_MB", "0"))
+# gradient (the cosines are gone, so sum g*cos cannot be formed).  Default 4 GiB: a paired batch of up to 46340 rows per
+# GPU (2 GiB at the benchmark's 32768); larger problems -- BASELINE config 5's 131072 rows -- keep the O(B*D) recompute
+# path.  Same box, whole step at B = 32768: 3.74 vs 4.01 ms.
+_store_e_mb = int(os.environ.get("MMGCLIP_B200_STORE_E_MB", "4096"))
+
+
+def get_store_e_budget_mb() -> int:
+    return _store_e_mb
 
 
 def set_store_e_budget_mb(mb: int) -> None:
