@@ -205,6 +205,14 @@ int mmg_adamw_step(float* const* params, const float* const* grads, float* const
                    const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
                    float eps, float weight_decay, long long* step_state, mmg_stream_t stream);
 
+/* Debug timeline of the fused backward (environment MMG_FUSED_TRACE=1 at launch time; mmg_infonce_workspace_bytes then
+ * includes the region): per CTA and role (0 TMA producer, 1 MMA issuer, 2 epilogue warp 0, 3 transform warp 0)
+ * `records_per_role` records {globaltimer ns, tag} of 16 bytes at workspace + *offset; tag = role<<60 | event<<56 |
+ * type<<52 | block<<32 | tm<<16 | tn (events: 0 item picked up, 1 dependency wait over, 2 item finished).  Returns 1 when
+ * tracing is enabled and the shape is covered by the fused launch, else 0. */
+int mmg_debug_fused_trace_region(int rows, int cols, int D, size_t* offset, size_t* bytes, int* records_per_role,
+                                 int* roles);
+
 /* Introspection (host only, no GPU): the static work-item schedule of the fused backward for CTA pair `pair` of `pairs`
  * -- rows of items[] are 8 ints {type (0 coefficient tile, 1 dA slice, 2 dB slice), block, tm, tn, kb0, nkb, global
  * column block, row block}; info[8] = {Rb, Cb, nbuf, nA, nB, nblk, kslI, kslT}.  Returns the pair's item count (0 = shape not covered).

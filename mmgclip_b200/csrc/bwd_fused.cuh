@@ -67,6 +67,9 @@ struct BwdFusedParams {
   const void* E;
   long long ldE;
   void* G;                // coefficient scratch [nbuf * Rb, Cb] bf16 (the stored-E transform writes it with plain stores)
+  // Debug timeline (MMG_FUSED_TRACE=1; NULL otherwise): per CTA and role kTraceCap records {globaltimer ns, tag}, see
+  // trace_event().  Read back by tests/gpu_stored_e_probe.py trace.
+  unsigned long long* trace;
   // Block order.  Block index blk (the order the blocks are walked in) -> (row block, column block of this launch).
   // Blocks are visited super-tile by super-tile (sr x sc blocks, row-major inside and across super-tiles) so that the
   // gradient rows a super-tile accumulates into and its operand rows can stay in L2.  sr = sc = 1 (the default: measured
@@ -86,6 +89,25 @@ struct BwdFusedParams {
     return owner * blocks_per_owner + part * blocks_per_part + (cb - owner * blocks_per_part);
   }
 };
+
+constexpr int kTraceCap = 1024;   // records per (CTA, role)
+constexpr int kTraceRoles = 4;    // 0 TMA producer, 1 MMA issuer, 2 epilogue warp 0, 3 transform warp 0
+
+// tag = role << 60 | event << 56 | item type << 52 | block << 32 | tm << 16 | tn;  events: 0 item picked up, 1 its
+// dependency wait is over, 2 item finished (producer: loads issued; MMA: last commit issued; epilogue: stores issued;
+// transform: published)
+__device__ __forceinline__ void trace_event(unsigned long long* trace, int role, int& n, int event, int type, int blk,
+                                            int tm, int tn) {
+  if (trace == nullptr || n >= kTraceCap) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  unsigned long long* rec = trace + (static_cast<size_t>(blockIdx.x * kTraceRoles + role) * kTraceCap + n) * 2;
+  rec[0] = t;
+  rec[1] = (static_cast<unsigned long long>(role) << 60) | (static_cast<unsigned long long>(event) << 56) |
+           (static_cast<unsigned long long>(type) << 52) | (static_cast<unsigned long long>(blk & 0xfffff) << 32) |
+           (static_cast<unsigned long long>(tm & 0xffff) << 16) | static_cast<unsigned long long>(tn & 0xffff);
+  ++n;
+}
 
 constexpr int kMaxOwners = 8;
 struct BwdOwnerMaps {
@@ -263,7 +285,9 @@ __device__ __forceinline__ void stored_e_rows(const BwdFusedParams& p, const uin
 }
 
 // kTW = transform warps of the stored-E mode (0 = recompute mode): warps 4 + kEW .. 4 + kEW + kTW - 1.
-template <int BN, int kEW, int kTW>
+// kTrace compiles the debug timeline in (MMG_FUSED_TRACE=1 selects those instantiations; the production kernels carry none
+// of it).
+template <int BN, int kEW, int kTW, bool kTrace = false>
 __global__ void __launch_bounds__(32 * (4 + kEW + kTW), 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
@@ -339,16 +363,19 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
+    int ntr = 0;
     while (cur.next(p, it)) {
       if (kStoredE && it.type == 0) continue;  // no tensor-core work: the epilogue warps transform E
       int rb, cbl;
       p.block_rc(it.blk, rb, cbl);
       const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
+      if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 0, ntr, 0, it.type, it.blk, it.tm, it.tn);
       if (it.type != 0 && it.blk > verified) {
         wait_counter(p.doneA + it.blk, wantA, lane);
         verified = it.blk;
       }
+      if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 0, ntr, 1, it.type, it.blk, it.tm, it.tn);
       const int half_off = static_cast<int>(cta_rank) * kBM;     // this CTA's 128 of the tile's 256 rows (A operand)
       const int n_half = static_cast<int>(cta_rank) * kBHalf;    // this CTA's half of the tile's BN columns (B operand)
       for (int kb = 0; kb < it.nkb; ++kb) {
@@ -384,6 +411,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 0, ntr, 2, it.type, it.blk, it.tm, it.tn);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -391,11 +419,13 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int n = 0;
+      int ntr = 0;
       while (cur.next(p, it)) {
         if (kStoredE && it.type == 0) continue;
         const int acc_stage = n % kAcc;
         const uint32_t acc_phase = (n / kAcc) & 1;
         ++n;
+        if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 1, ntr, 0, it.type, it.blk, it.tm, it.tn);
         mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t a_mn = it.type == 2 ? 1u : 0u, b_mn = it.type != 0 ? 1u : 0u;
@@ -407,6 +437,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         for (int kb = 0; kb < it.nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if constexpr (kTrace) if (kb == 0 && lane == 0) trace_event(p.trace, 1, ntr, 1, it.type, it.blk, it.tm, it.tn);
           if (elect_one_sync()) {
             const uint32_t a_addr = smem_u32(sA + stage * S::kABytes);
             const uint32_t b_addr = smem_u32(sB + stage * S::kBBytes);
@@ -422,6 +453,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 1, ntr, 2, it.type, it.blk, it.tm, it.tn);
       }
       // every outstanding accumulator stage has been released (the peer's remote arrivals have landed) before the
       // leader's barriers die
@@ -438,6 +470,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int pending = -1;     // block whose coefficient-tile stores of this warp are not yet published in doneA
     unsigned int a_seq = 0;  // coefficient tiles this warp has finished (identical across the CTA's epilogue warps)
     int verified = -1;    // scratch buffers of blocks [0, verified + nbuf] are known to be free
+    int ntr = 0;
     typename FusedGrad::Params gp;
     gp.scale_ptr = p.scale; gp.scal = p.scal; gp.dlogscale_acc = p.dlogscale_acc; gp.dbg = 0;
     typename FusedStore::Params sp;
@@ -458,8 +491,10 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       p.block_rc(it.blk, rb, cbl);
       const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
+      if constexpr (kTrace) if (ewarp == 0 && lane == 0) trace_event(p.trace, 2, ntr, 0, it.type, it.blk, it.tm, it.tn);
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tcgen05_fence_after();
+      if constexpr (kTrace) if (ewarp == 0 && lane == 0) trace_event(p.trace, 2, ntr, 1, it.type, it.blk, it.tm, it.tn);
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
       const int half_off = static_cast<int>(cta_rank) * kBM;
       if (it.type == 0) {
@@ -494,6 +529,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         if (leader) mbar_arrive(&tempty_bar[acc_stage]);
         else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
       }
+      if constexpr (kTrace) if (ewarp == 0 && lane == 0) trace_event(p.trace, 2, ntr, 2, it.type, it.blk, it.tm, it.tn);
     }
     if (pending >= 0) publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
     FusedGrad::finish(gp, carry, lane);
@@ -502,6 +538,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     constexpr int kRowsPerWarp = kBM / (kTW > 0 ? kTW : 1);
     const int tw = warp - (4 + kEW);
     int verified = -1;  // scratch buffers of blocks [0, verified + nbuf] are known to be free
+    int ntr = 0;
     uint8_t* g_base = static_cast<uint8_t*>(p.G);
     while (cur.next(p, it)) {
       if (it.type != 0) continue;
@@ -509,10 +546,12 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       p.block_rc(it.blk, rb, cbl);
       const int col0 = p.global_cb(cbl) * p.Cb;
       const int buf = it.blk % p.nbuf;
+      if constexpr (kTrace) if (tw == 0 && lane == 0) trace_event(p.trace, 3, ntr, 0, it.type, it.blk, it.tm, it.tn);
       if (it.blk >= p.nbuf && it.blk - p.nbuf > verified) {
         wait_counter(p.doneB + (it.blk - p.nbuf), wantB, lane);  // the buffer's previous block has been consumed
         verified = it.blk - p.nbuf;
       }
+      if constexpr (kTrace) if (tw == 0 && lane == 0) trace_event(p.trace, 3, ntr, 1, it.type, it.blk, it.tm, it.tn);
       const int r0 = it.tm * 256 + static_cast<int>(cta_rank) * kBM + tw * kRowsPerWarp;  // first row inside the block
       const int c0 = it.tn * BN;                                                          // first column inside the block
       const long long grow0 = static_cast<long long>(rb) * p.Rb + r0;                     // local row
@@ -527,6 +566,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         __threadfence();
         fence_proxy_async_all();
         red_release_gpu_add(p.doneA + it.blk, 1u);
+        if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, it.type, it.blk, it.tm, it.tn);
       }
     }
   }

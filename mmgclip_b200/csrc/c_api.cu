@@ -497,6 +497,12 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
   return 0;
 }
 
+int mmg_debug_fused_trace_region(int rows, int cols, int D, size_t* offset, size_t* bytes, int* records_per_role,
+                                 int* roles) {
+  if (offset == nullptr || bytes == nullptr || records_per_role == nullptr || roles == nullptr) return 0;
+  return tc_fused_trace_region(rows, cols, D, offset, bytes, records_per_role, roles);
+}
+
 int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
                            int max_items, int* info) {
   return tc_fused_bwd_schedule(rows, cols, D, n_owners, n_parts, part, pairs, pair, items, max_items, info);

@@ -55,6 +55,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
                          void* workspace, size_t workspace_bytes, cudaStream_t st, int* used,
                          const void* e_stored = nullptr, long long lde = 0);
 int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts);
+int tc_fused_trace_region(int rows, int cols, int D, size_t* off, size_t* bytes, int* per_role, int* roles);
 
 // Zero-shot prompt scoring on the tensor pipe (zeroshot_tc.cu): 3xTF32, fp32-faithful, HBM-bound at large N.
 size_t tc_zeroshot_workspace_bytes(int C, int D);

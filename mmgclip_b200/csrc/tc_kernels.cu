@@ -392,6 +392,7 @@ static int env_int(const char* name, int dflt) {
 struct FusedPlan {
   int ok, Rb, Cb, nbuf, kslI, kslT;
   size_t g_bytes, total_bytes;
+  size_t trace_off, trace_bytes;  // MMG_FUSED_TRACE=1: debug timeline region at the end of the workspace
 };
 
 static int largest_divisor(int n, int cap) {
@@ -426,6 +427,11 @@ static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0, bool re
   f.Rb = Rb; f.Cb = Cb; f.nbuf = nbuf; f.kslI = kslI; f.kslT = kslT;
   f.g_bytes = ((size_t)nbuf * Rb * Cb * 2 + 255) / 256 * 256;
   f.total_bytes = f.g_bytes + (size_t)2 * nblk * sizeof(unsigned int) + 256;
+  if (env_int("MMG_FUSED_TRACE", 0) != 0) {
+    f.trace_off = (f.total_bytes + 255) / 256 * 256;
+    f.trace_bytes = (size_t)sm_count() * kTraceRoles * kTraceCap * 16;
+    f.total_bytes = f.trace_off + f.trace_bytes;
+  }
   f.ok = 1;
   return f;
 }
@@ -519,6 +525,14 @@ int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_p
   return f.ok && pick_tile(rows, cols).BN == 256 ? 1 : 0;
 }
 
+// Debug: where the MMG_FUSED_TRACE=1 timeline of the last fused launch of this shape lives inside the workspace.
+int tc_fused_trace_region(int rows, int cols, int D, size_t* off, size_t* bytes, int* per_role, int* roles) {
+  const FusedPlan f = fused_plan(rows, cols, D);
+  if (!f.ok || f.trace_bytes == 0) return 0;
+  *off = f.trace_off; *bytes = f.trace_bytes; *per_role = kTraceCap; *roles = kTraceRoles;
+  return 1;
+}
+
 size_t tc_infonce_bwd_fused_workspace(int rows, int cols, int D) {
   const FusedPlan f = fused_plan(rows, cols, D);
   return f.ok ? f.total_bytes : 0;
@@ -548,6 +562,12 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   BwdFusedParams p;
   fill_schedule(&p, f, rows, cols, D, n_owners, n_parts, part, BN);
   p.E = e_stored; p.ldE = lde; p.G = workspace;
+  p.trace = nullptr;
+  if (f.trace_bytes > 0) {
+    p.trace = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + f.trace_off);
+    cudaError_t te = cudaMemsetAsync(p.trace, 0, f.trace_bytes, st);
+    if (te != cudaSuccess) return check_cuda(te, "cudaMemsetAsync(fused backward trace)");
+  }
   p.diag_offset = diag_offset;
   p.rinv = rinv; p.cinv = cinv; p.scale = scale; p.scal = scal; p.dlogscale_acc = dlogscale_acc;
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
@@ -583,11 +603,19 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16, 0>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
   if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16, 0>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
   if (variant == 4) { kern = infonce_bwd_fused_kernel<256, 8, kStoredTW>; smem_bytes = FusedSmemT<256, 8>::kTotal; }
-  static bool configured[5] = {false, false, false, false, false};
-  if (!configured[variant]) {
+  int slot = variant;
+  if (p.trace != nullptr && (variant == 0 || variant == 4)) {  // debug timeline: separate instantiations
+    if (variant == 0) kern = infonce_bwd_fused_kernel<256, 8, 0, true>;
+    else kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, true>;
+    slot = variant == 0 ? 5 : 6;
+  } else {
+    p.trace = nullptr;
+  }
+  static bool configured[7] = {false, false, false, false, false, false, false};
+  if (!configured[slot]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
-    configured[variant] = true;
+    configured[slot] = true;
   }
   const int pairs = sm_count() / 2;
   cudaLaunchConfig_t cfg;

@@ -94,8 +94,43 @@ def time_(B, D):
                   + " ".join(f"{x:.3f}" for x in tb), flush=True)
 
 
+def trace(B, D, out_prefix):
+    """MMG_FUSED_TRACE=1 timelines of one fused backward launch per mode -> <out_prefix>_{stored,recompute}.npy
+    (int64 [CTAs, roles, records, 2] = {globaltimer ns, tag}; see mmg_debug_fused_trace_region in the header)."""
+    import ctypes
+    import os
+    os.environ["MMG_FUSED_TRACE"] = "1"
+    lib = ops._lib.load()
+    s = torch.tensor(math.log(1 / 0.07), device="cuda").exp()
+    a, b = embeddings(B, D, seed=1)
+    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    gl = torch.ones((), device="cuda")
+    E = torch.empty((B, B), dtype=torch.bfloat16, device="cuda")
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    per, roles = ctypes.c_int(), ctypes.c_int()
+    assert lib.mmg_debug_fused_trace_region(B, B, D, ctypes.byref(off), ctypes.byref(nb), ctypes.byref(per),
+                                            ctypes.byref(roles)) == 1
+    nbytes = lib.mmg_infonce_workspace_bytes(ops._PREC["bf16"], B, B, D)
+    for mode, e in (("stored", E), ("recompute", None)):
+        for _ in range(3):
+            r = ops.infonce_forward_raw(ab, bb, s, 0, "bf16", e_out=e)
+            ops.infonce_backward_raw(ab, bb, s, r[0], r[1], gl, 0.5 / B, 0, "bf16", a32=a, b32=b, diag=r[2],
+                                     need_dscale=False, e_stored=e)
+        torch.cuda.synchronize()
+        ws = ops._workspace(a.device, nbytes)
+        raw = ws[off.value:off.value + nb.value].clone().view(torch.int64).cpu().numpy()
+        raw = raw.reshape(-1, roles.value, per.value, 2)
+        np.save(f"{out_prefix}_{mode}.npy", raw)
+        used = (raw[..., 0] != 0).sum(axis=2)
+        t = raw[..., 0][raw[..., 0] != 0]
+        print(f"{mode}: CTAs {raw.shape[0]}, records per role (max) {used.max(axis=0).tolist()}, span "
+              f"{(t.max() - t.min()) / 1e6:.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "time":
+    if len(sys.argv) > 1 and sys.argv[1] == "trace":
+        trace(int(sys.argv[2]) if len(sys.argv) > 2 else 32768, 512, sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/trace")
+    elif len(sys.argv) > 1 and sys.argv[1] == "time":
         time_(int(sys.argv[2]) if len(sys.argv) > 2 else 32768, int(sys.argv[3]) if len(sys.argv) > 3 else 512)
     else:
         check()
