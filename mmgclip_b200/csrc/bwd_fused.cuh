@@ -23,10 +23,14 @@
 //                                                                                    the scratch buffer)
 // Stored-E mode (template flag kStoredE).  When the forward kept E = exp(logit - s) (bf16, rows x cols) the coefficient
 // tiles need no tensor-core work at all: g = E * (rinv[r] + cinv[c]) is a pure streaming transform.  (A) items are then
-// skipped by the TMA producer and the MMA issuer (they take no operand-ring slot and no accumulator stage); the
-// epilogue warps read their 32 x 128 piece of E straight from global memory (16 independent 16-byte loads per thread),
-// scale it and store the bf16 coefficients into the scratch buffer, meet at a named barrier and publish doneA.  The
-// backward executes 4 B^2 D FLOPs instead of 6 B^2 D, at the price of 2 B^2 bytes of HBM.
+// skipped by the TMA producer, the MMA issuer and the epilogue warps (they take no operand-ring slot and no accumulator
+// stage); kTW extra *transform warps* per CTA read their 16 rows x 256 columns of E straight from global memory (eight
+// independent 16-byte loads per thread in flight), scale them and store the bf16 coefficients into the scratch buffer,
+// meet at a named barrier and publish doneA.  The
+// backward executes 4 B^2 D FLOPs instead of 6 B^2 D, at the price of 2 B^2 bytes of HBM.  (Timeline, MMG_FUSED_TRACE=1
+// at 32768^2 x 512: the transform warps are busy 76 % of the launch, ~7.6 us per tile, and the producers still wait
+// ~0.46 ms for doneA.  Prefetching the next tile's E rows into L2 from the transform warps measured no gain -- 2.32 vs
+// 2.62 ms recompute on that box, the same ratio as without -- and was not kept.)
 //
 // An item only ever waits for items with a strictly smaller key and every pair processes its items in key order, so the
 // unfinished item with the smallest key can always run: no dead-lock as long as all CTAs are resident (grid <= #SMs).
