@@ -603,15 +603,30 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16, 0>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
   if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16, 0>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
   if (variant == 4) { kern = infonce_bwd_fused_kernel<256, 8, kStoredTW>; smem_bytes = FusedSmemT<256, 8>::kTotal; }
+  // MMG_STORED_TW=16: sixteen transform warps (8 rows each, twice the E bytes in flight per SM; 896 threads -> 72 registers
+  // per thread).  Compiles without spills; not yet measured -- opt-in.
+  int stored_tw = kStoredTW;
+  if (variant == 4 && env_int("MMG_STORED_TW", kStoredTW) == 16) {
+    kern = infonce_bwd_fused_kernel<256, 8, 16>;
+    stored_tw = 16;
+  }
   int slot = variant;
   if (p.trace != nullptr && (variant == 0 || variant == 4)) {  // debug timeline: separate instantiations
     if (variant == 0) kern = infonce_bwd_fused_kernel<256, 8, 0, true>;
     else kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, true>;
     slot = variant == 0 ? 5 : 6;
+    stored_tw = kStoredTW;
   } else {
     p.trace = nullptr;
   }
-  static bool configured[7] = {false, false, false, false, false, false, false};
+  if (variant == 4 && stored_tw == 16) slot = 7;
+  // MMG_STORED_DEFER=1: deferred publish of the stored-E coefficient tiles (kDefer in bwd_fused.cuh) -- compiled, covered
+  // at schedule level on the CPU, NOT yet run on a GPU; opt-in for the next measurement session
+  if (variant == 4 && slot == 4 && p.nbuf >= 3 && env_int("MMG_STORED_DEFER", 0) != 0) {
+    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, true>;
+    slot = 8;
+  }
+  static bool configured[9] = {false, false, false, false, false, false, false, false, false};
   if (!configured[slot]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
@@ -621,7 +636,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pairs * 2);
-  cfg.blockDim = dim3(32 * (4 + ew + (variant == 4 ? kStoredTW : 0)));
+  cfg.blockDim = dim3(32 * (4 + ew + (variant == 4 ? stored_tw : 0)));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -78,7 +78,13 @@ def time_(B, D):
         orders = ((True,),)
     elif os.environ.get("PROBE_ONLY") == "recompute":
         orders = ((False,),)
-    for order in orders:
+    elif os.environ.get("PROBE_ONLY") == "tw":  # stored-E with 8, then 16, then 8 transform warps (env is read per launch)
+        orders = ((True,), (True,), (True,))
+    tw_cycle = ["8", "16", "8"]
+    for oi, order in enumerate(orders):
+        if os.environ.get("PROBE_ONLY") == "tw":
+            os.environ["MMG_STORED_TW"] = tw_cycle[oi]
+            print("MMG_STORED_TW=" + tw_cycle[oi], flush=True)
         for stored in order:
             e = E if stored else None
             tf, tb = [], []

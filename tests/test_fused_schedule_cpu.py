@@ -138,3 +138,55 @@ def test_block_order_super_tiles(monkeypatch, sr, sc):
     monkeypatch.setenv("MMG_FUSED_SC", str(sc))
     test_schedule_is_complete_and_deadlock_free((32768, 32768, 512, 1, 1, 0), 74)
     test_schedule_is_complete_and_deadlock_free((4096, 32768, 512, 8, 2, 1), 74)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("pairs", [1, 5, 74])
+@pytest.mark.parametrize("defer", [False, True])
+def test_stored_e_two_stream_replay(shape, pairs, defer):
+    """Stored-E mode runs two independent streams per CTA pair: the transform warps walk the coefficient tiles (waiting
+    for doneB of the block whose buffer they overwrite), the producer / MMA / epilogue warps walk the gradient slices
+    (waiting for doneA of their block).  ``defer``: a tile is published only once the NEXT tile of the pair has passed its
+    wait (kDefer kernels, MMG_STORED_DEFER=1), the last one immediately.  Both must run to completion."""
+    rows, cols, D, n_owners, n_parts, part = shape
+    per_pair, info = _schedule(rows, cols, D, n_owners, n_parts, part, pairs)
+    if not any(per_pair):
+        pytest.skip("shape not covered by the fused backward")
+    nA, nB, nblk, nbuf = info["nA"], info["nB"], info["nblk"], info["nbuf"]
+    if defer and nbuf < 3:
+        pytest.skip("the launcher only selects the deferred kernel with at least three buffers")
+    t_items = [[it for it in items if it[0] == 0] for items in per_pair]
+    m_items = [[it for it in items if it[0] != 0] for items in per_pair]
+    doneA, doneB = [0] * nblk, [0] * nblk
+    tpos, mpos = [0] * pairs, [0] * pairs
+    pending = [None] * pairs
+    remaining = sum(len(x) for x in t_items) + sum(len(x) for x in m_items)
+    while remaining:
+        progressed = False
+        for p in range(pairs):
+            while tpos[p] < len(t_items[p]):
+                blk = t_items[p][tpos[p]][1]
+                if blk >= nbuf and doneB[blk - nbuf] != nB:
+                    break
+                if defer:
+                    if pending[p] is not None:
+                        doneA[pending[p]] += 1
+                    pending[p] = blk
+                    if tpos[p] + 1 == len(t_items[p]):
+                        doneA[blk] += 1
+                        pending[p] = None
+                else:
+                    doneA[blk] += 1
+                tpos[p] += 1
+                remaining -= 1
+                progressed = True
+            while mpos[p] < len(m_items[p]):
+                blk = m_items[p][mpos[p]][1]
+                if doneA[blk] != nA:
+                    break
+                doneB[blk] += 1
+                mpos[p] += 1
+                remaining -= 1
+                progressed = True
+        assert progressed, f"dead-lock (defer={defer}) with {pairs} pairs: transform at {tpos}, slices at {mpos}"
+    assert doneA == [nA] * nblk and doneB == [nB] * nblk
