@@ -441,7 +441,8 @@ def run_gpu(args):
     # ---- per-launch timing of the dominant kernels (informational; outside the timed regions) ----
     kernels = None
     if rank == 0 and args.kernel_breakdown:
-        kernels = kernel_breakdown(torch, ops, dev, bl, B, D_PROJ)
+        kernels = kernel_breakdown(torch, ops, dev, bl, B, D_PROJ,
+                                   stored_e=world == 1 and ops.want_store_e(bl, B, D_PROJ, prec, False))
 
     def finish(code=0):
         # Multi-GPU teardown: NCCL communicators that were captured into CUDA graphs do not always unwind cleanly
@@ -516,7 +517,7 @@ def run_gpu(args):
     return finish(0)
 
 
-def kernel_breakdown(torch, ops, dev, rows, cols, d):
+def kernel_breakdown(torch, ops, dev, rows, cols, d, stored_e=False):
     """Live CUDA-event timing (no profiler) of each tcgen05 kernel family at the bench shape (local rows x global
     columns), outside the timed regions.  The backward phases are separated with the library's MMG_BWD_PHASES hook."""
     gen = torch.Generator(device=dev).manual_seed(7)
@@ -553,6 +554,27 @@ def kernel_breakdown(torch, ops, dev, rows, cols, d):
                            "note": "algorithmic = dI + dT (4 rows cols D); executed adds the recomputed cosines; the "
                                    "timing includes the prep kernel and the zero fills of the call"},
     }
+    if stored_e:
+        # the step itself ran in stored-E mode (ops.want_store_e): the two entries above are the recompute kernels, kept
+        # for comparison; these are the kernels of the step
+        out["forward_lse"]["mode"] = out["backward_fused"]["mode"] = "recompute (not what the timed step ran)"
+        try:
+            e_mat = torch.empty((rows, cols), dtype=torch.bfloat16, device=dev)
+            t_fs = timeit(lambda: ops.infonce_forward_raw(ab, bb, s, 0, "bf16", e_out=e_mat))
+            rs2, cs2, dg2 = ops.infonce_forward_raw(ab, bb, s, 0, "bf16", e_out=e_mat)
+            t_bs = timeit(lambda: ops.infonce_backward_raw(ab, bb, s, rs2, cs2, one, 0.5 / cols, 0, "bf16", a32=a, b32=b,
+                                                           diag=dg2, need_dscale=False, e_stored=e_mat))
+            out["forward_lse_store_e"] = {
+                "kernel": "gemm_tc_kernel<256, EpiLse<store E>, 2> (row/column sums + bf16 E through TMA stores)",
+                "launches": 1, "ms_per_launch": t_fs, "flops_per_launch": f, "tflops": f / t_fs / 1e9,
+                "bytes_written": 2.0 * rows * cols}
+            out["backward_fused_stored_e"] = {
+                "kernel": "infonce_bwd_fused_kernel<256, 8, 8> (E -> coefficients on transform warps + dI/dT slices)",
+                "launches": 1, "ms_per_launch": t_bs, "flops_per_launch": 2 * f, "tflops": 2 * f / t_bs / 1e9,
+                "note": "no recomputation: executed = algorithmic; the timing includes the prep and matching-pair kernels"}
+            del e_mat
+        except Exception as exc:  # noqa: BLE001  (informational section: never lose the bench line over it)
+            out["stored_e_breakdown_error"] = repr(exc)
     # the block loop the fused launch replaces (general shapes still use it), phases separated with MMG_BWD_PHASES
     os.environ["MMG_BWD_FUSED"] = "0"
     try:
