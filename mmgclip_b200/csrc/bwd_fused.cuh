@@ -79,6 +79,11 @@ struct BwdFusedParams {
   // gradient rows a super-tile accumulates into and its operand rows can stay in L2.  sr = sc = 1 (the default: measured
   // no better with larger super-tiles, see fill_schedule) is plain row-major.
   int sr, sc;
+  // Per-panel dependencies (kPanel kernels, MMG_FUSED_PANEL=1; NULL otherwise): coefficient tiles of block s, row panel tm
+  // / column panel tn that are complete.  A dA slice of row panel tm only reads the coefficient tiles (tm, *), a dB slice
+  // of column panel tn only the tiles (*, tn), so they need not wait for the whole block.
+  unsigned int* doneArow;  // [nblk * tAm], wants tAn arrivals per CTA of the pair
+  unsigned int* doneAcol;  // [nblk * tAn], wants tAm arrivals per CTA of the pair
   __host__ __device__ void block_rc(int blk, int& rb, int& cb) const {
     const int per = sr * sc;
     const int sidx = blk / per, w = blk - sidx * per;
@@ -204,6 +209,22 @@ __device__ __forceinline__ void publish_tile(unsigned int* pub_cnt, unsigned int
     if ((old & (kEW - 1)) == kEW - 1) {  // last of the CTA's epilogue warps
       fence_proxy_async_all();
       red_release_gpu_add(done_ctr, 1u);
+    }
+  }
+  __syncwarp();
+}
+
+// kPanel: the same, bumping the tile's row-panel and column-panel counters instead of the block counter
+template <int kEW>
+__device__ __forceinline__ void publish_tile2(unsigned int* pub_cnt, unsigned int seq, unsigned int* ctr_row,
+                                              unsigned int* ctr_col, int lane) {
+  if (lane == 0) {
+    tma_store_wait_all();
+    const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 7u), 1u);
+    if ((old & (kEW - 1)) == kEW - 1) {  // last of the CTA's epilogue warps
+      fence_proxy_async_all();
+      red_release_gpu_add(ctr_row, 1u);
+      red_release_gpu_add(ctr_col, 1u);
     }
   }
   __syncwarp();
@@ -356,7 +377,9 @@ __device__ __forceinline__ void stored_e_rows_hook(const BwdFusedParams& p, cons
 // instead of right after its own stores.  Separate instantiation: the default kernels do not contain any of it.  Written
 // after the round's GPU budget was spent -- compiled and covered at schedule level by tests/test_fused_schedule_cpu.py,
 // not yet run on a GPU.
-template <int BN, int kEW, int kTW, bool kTrace = false, bool kDefer = false>
+// kPanel (MMG_FUSED_PANEL=1): per-panel instead of per-block doneA dependencies (see BwdFusedParams::doneArow).  Separate
+// instantiations, same status as kDefer: compiled, schedule-level semantics checked on the CPU, not yet run on a GPU.
+template <int BN, int kEW, int kTW, bool kTrace = false, bool kDefer = false, bool kPanel = false>
 __global__ void __launch_bounds__(32 * (4 + kEW + kTW), 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
@@ -440,7 +463,12 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 0, ntr, 0, it.type, it.blk, it.tm, it.tn);
-      if (it.type != 0 && it.blk > verified) {
+      if constexpr (kPanel) {
+        if (it.type == 1)
+          wait_counter(p.doneArow + it.blk * p.tAm + it.tm, static_cast<unsigned int>(p.tAn) * 2u, lane);
+        else if (it.type == 2)
+          wait_counter(p.doneAcol + it.blk * p.tAn + it.tm, static_cast<unsigned int>(p.tAm) * 2u, lane);
+      } else if (it.type != 0 && it.blk > verified) {
         wait_counter(p.doneA + it.blk, wantA, lane);
         verified = it.blk;
       }
@@ -537,6 +565,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int n = 0;
     float carry = 0.f;
     int pending = -1;     // block whose coefficient-tile stores of this warp are not yet published in doneA
+    int pend_tm = 0, pend_tn = 0;  // (kPanel) that tile's panels
+    (void)pend_tm; (void)pend_tn;
     unsigned int a_seq = 0;  // coefficient tiles this warp has finished (identical across the CTA's epilogue warps)
     int verified = -1;    // scratch buffers of blocks [0, verified + nbuf] are known to be free
     int ntr = 0;
@@ -549,7 +579,11 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       if (pending >= 0) {
         // publish the previous coefficient tile (deferred to here so the stores' latency is off the critical path, and
         // done BEFORE blocking on the next accumulator so it never depends on this item's progress)
-        publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
+        if constexpr (kPanel)
+          publish_tile2<kEW>(pub_cnt, a_seq++, p.doneArow + pending * p.tAm + pend_tm, p.doneAcol + pending * p.tAn + pend_tn,
+                             lane);
+        else
+          publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
         pending = -1;
       }
       if (kStoredE && it.type == 0) continue;  // the transform warps own the coefficient tiles
@@ -578,6 +612,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         FusedGrad::template run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
                            epi_scratch + acc_stage * BN + half * (BN / (kEW / 4)), &mGst, staging, 0, carry);
         pending = it.blk;
+        pend_tm = it.tm; pend_tn = it.tn;
       } else {
         // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
         if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
@@ -600,7 +635,13 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       }
       if constexpr (kTrace) if (ewarp == 0 && lane == 0) trace_event(p.trace, 2, ntr, 2, it.type, it.blk, it.tm, it.tn);
     }
-    if (pending >= 0) publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
+    if (pending >= 0) {
+      if constexpr (kPanel)
+        publish_tile2<kEW>(pub_cnt, a_seq++, p.doneArow + pending * p.tAm + pend_tm, p.doneAcol + pending * p.tAn + pend_tn,
+                           lane);
+      else
+        publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
+    }
     FusedGrad::finish(gp, carry, lane);
   } else if (kStoredE && warp >= 4 + kEW) {
     // ===================== transform warps (stored-E mode, both CTAs) =====================
@@ -637,7 +678,12 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         if (tw == 0 && lane == 0) {
           __threadfence();
           fence_proxy_async_all();
-          red_release_gpu_add(p.doneA + it.blk, 1u);
+          if constexpr (kPanel) {
+            red_release_gpu_add(p.doneArow + it.blk * p.tAm + it.tm, 1u);
+            red_release_gpu_add(p.doneAcol + it.blk * p.tAn + it.tn, 1u);
+          } else {
+            red_release_gpu_add(p.doneA + it.blk, 1u);
+          }
           if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, it.type, it.blk, it.tm, it.tn);
         }
       } else {
@@ -650,7 +696,12 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           if (tw == 0 && lane == 0) {
             __threadfence();
             fence_proxy_async_all();
-            red_release_gpu_add(p.doneA + blk, 1u);
+            if constexpr (kPanel) {
+              red_release_gpu_add(p.doneArow + blk * p.tAm + ptm, 1u);
+              red_release_gpu_add(p.doneAcol + blk * p.tAn + ptn, 1u);
+            } else {
+              red_release_gpu_add(p.doneA + blk, 1u);
+            }
             if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, 0, blk, ptm, ptn);
           }
         };

@@ -426,7 +426,8 @@ static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0, bool re
   if (nbuf > nblk) nbuf = nblk < 1 ? 1 : nblk;
   f.Rb = Rb; f.Cb = Cb; f.nbuf = nbuf; f.kslI = kslI; f.kslT = kslT;
   f.g_bytes = ((size_t)nbuf * Rb * Cb * 2 + 255) / 256 * 256;
-  f.total_bytes = f.g_bytes + (size_t)2 * nblk * sizeof(unsigned int) + 256;
+  // counters: doneA[nblk], doneB[nblk], then the per-panel counters doneArow[nblk * Rb/256], doneAcol[nblk * Cb/256]
+  f.total_bytes = f.g_bytes + (size_t)nblk * (2 + Rb / 256 + Cb / 256) * sizeof(unsigned int) + 256;
   if (env_int("MMG_FUSED_TRACE", 0) != 0) {
     f.trace_off = (f.total_bytes + 255) / 256 * 256;
     f.trace_bytes = (size_t)sm_count() * kTraceRoles * kTraceCap * 16;
@@ -573,7 +574,11 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
   p.doneA = ctr;
   p.doneB = ctr + p.nblk;
-  cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)2 * p.nblk * sizeof(unsigned int), st);
+  // per-panel dependencies (kPanel kernels): 256-column tiles only
+  const bool panel = BN == 256 && env_int("MMG_FUSED_PANEL", 0) != 0;
+  p.doneArow = panel ? ctr + 2 * p.nblk : nullptr;
+  p.doneAcol = panel ? ctr + 2 * p.nblk + p.nblk * p.tAm : nullptr;
+  cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)p.nblk * (2 + (panel ? p.tAm + p.tAn : 0)) * sizeof(unsigned int), st);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
 
   CUtensorMap mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA;
@@ -626,7 +631,20 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, true>;
     slot = 8;
   }
-  static bool configured[9] = {false, false, false, false, false, false, false, false, false};
+  // MMG_FUSED_PANEL=1: per-panel doneA dependencies (kPanel) -- same status as MMG_STORED_DEFER
+  if (panel && slot == 0 && ew == 8) {
+    kern = infonce_bwd_fused_kernel<256, 8, 0, false, false, true>;
+    slot = 9;
+  } else if (panel && slot == 4) {
+    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, false, true>;
+    slot = 10;
+  } else if (panel && slot == 8) {
+    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, true, true>;
+    slot = 11;
+  } else {
+    p.doneArow = p.doneAcol = nullptr;
+  }
+  static bool configured[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
   if (!configured[slot]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");

@@ -190,3 +190,91 @@ def test_stored_e_two_stream_replay(shape, pairs, defer):
                 progressed = True
         assert progressed, f"dead-lock (defer={defer}) with {pairs} pairs: transform at {tpos}, slices at {mpos}"
     assert doneA == [nA] * nblk and doneB == [nB] * nblk
+
+
+def _needed_tiles(it, info):
+    """Coefficient tiles (tm, tn) whose scratch data a gradient slice reads."""
+    t, blk, tm, tn, kb0, nkb = it[:6]
+    lo, hi = kb0 * 64 // 256, ((kb0 + nkb) * 64 - 1) // 256
+    if t == 1:   # dA slice of row panel tm: K runs over the block's columns
+        return [(tm, c) for c in range(lo, hi + 1)]
+    return [(r, tm) for r in range(lo, hi + 1)]   # dB slice of column panel tm: K runs over the block's rows
+
+
+@pytest.mark.parametrize("shape", SHAPES[:5])
+@pytest.mark.parametrize("pairs", [3, 74])
+@pytest.mark.parametrize("mode", ["recompute", "stored"])
+@pytest.mark.parametrize("panel", [False, True])
+def test_dependency_counters_cover_the_data_each_slice_reads(shape, pairs, mode, panel):
+    """Replays the kernel's own counter arithmetic (block counters, or the per-panel counters of the kPanel kernels) and
+    checks, at the moment a gradient slice is allowed to start, that every coefficient tile it reads is complete -- and
+    that everything runs to completion."""
+    rows, cols, D, n_owners, n_parts, part = shape
+    per_pair, info = _schedule(rows, cols, D, n_owners, n_parts, part, pairs)
+    if not any(per_pair):
+        pytest.skip("shape not covered by the fused backward")
+    nA, nB, nblk, nbuf = info["nA"], info["nB"], info["nblk"], info["nbuf"]
+    tAm, tAn = info["Rb"] // 256, info["Cb"] // 256
+    assert nA == tAm * tAn
+    done_tiles = set()                     # (blk, tm, tn) published
+    blkA = [0] * nblk
+    rowA = [[0] * tAm for _ in range(nblk)]
+    colA = [[0] * tAn for _ in range(nblk)]
+    doneB = [0] * nblk
+
+    def publish(it):
+        _, blk, tm, tn = it[:4]
+        done_tiles.add((blk, tm, tn))
+        blkA[blk] += 1
+        rowA[blk][tm] += 1
+        colA[blk][tn] += 1
+
+    def b_may_start(it):
+        t, blk, tm = it[0], it[1], it[2]
+        if not panel:
+            return blkA[blk] == nA
+        return rowA[blk][tm] == tAn if t == 1 else colA[blk][tm] == tAm
+
+    def a_may_start(it):
+        blk = it[1]
+        return blk < nbuf or doneB[blk - nbuf] == nB
+
+    if mode == "stored":
+        streams = [[it for it in items if it[0] == 0] for items in per_pair] + \
+                  [[it for it in items if it[0] != 0] for items in per_pair]
+    else:
+        streams = [list(items) for items in per_pair]
+    pos = [0] * len(streams)
+    pending = [None] * len(streams)        # recompute mode: tile published when the stream reaches its next item
+    remaining = sum(len(x) for x in streams)
+    while remaining:
+        progressed = False
+        for si, st in enumerate(streams):
+            while pos[si] < len(st):
+                it = st[pos[si]]
+                if mode == "recompute" and pending[si] is not None:
+                    publish(pending[si])
+                    pending[si] = None
+                    progressed = True
+                if it[0] == 0:
+                    if not a_may_start(it):
+                        break
+                    if mode == "recompute":
+                        pending[si] = it
+                    else:
+                        publish(it)
+                else:
+                    if not b_may_start(it):
+                        break
+                    for tm, tn in _needed_tiles(it, info):
+                        assert (it[1], tm, tn) in done_tiles, f"slice {it} started before tile ({tm},{tn}) of its block"
+                    doneB[it[1]] += 1
+                pos[si] += 1
+                remaining -= 1
+                progressed = True
+            if mode == "recompute" and pos[si] == len(st) and pending[si] is not None:
+                publish(pending[si])
+                pending[si] = None
+                progressed = True
+        assert progressed, f"dead-lock (mode={mode}, panel={panel}) at {pos}"
+    assert len(done_tiles) == nA * nblk and doneB == [nB] * nblk
