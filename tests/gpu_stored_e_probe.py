@@ -1,6 +1,9 @@
 """Probe (not a pytest): stored-E forward/backward against the recompute path.
     python tests/gpu_stored_e_probe.py check          # correctness at small / ragged-free shapes
     python tests/gpu_stored_e_probe.py time [B] [D]   # timings at the benchmark shape
+    python tests/gpu_stored_e_probe.py variants       # opt-in kernel variants (panel counters, deferred publish, 16
+                                                      # transform warps): correctness vs the default, then launch times
+    python tests/gpu_stored_e_probe.py trace [B] [prefix]   # MMG_FUSED_TRACE timelines -> <prefix>_{stored,recompute}.npy
 """
 import math
 import sys
@@ -133,8 +136,64 @@ def trace(B, D, out_prefix):
               f"{(t.max() - t.min()) / 1e6:.3f} ms", flush=True)
 
 
+VARIANTS = [
+    ("recompute", False, {}),
+    ("recompute+panel", False, {"MMG_FUSED_PANEL": "1"}),
+    ("stored", True, {}),
+    ("stored+panel", True, {"MMG_FUSED_PANEL": "1"}),
+    ("stored+defer", True, {"MMG_STORED_DEFER": "1"}),
+    ("stored+defer+panel", True, {"MMG_STORED_DEFER": "1", "MMG_FUSED_PANEL": "1"}),
+    ("stored+tw16", True, {"MMG_STORED_TW": "16"}),
+]
+
+
+def variants(B=32768, D=512):
+    """Every opt-in kernel variant of the fused backward against the default recompute kernel: correctness at a few
+    shapes (the library reads the switches at launch time, so one process can toggle them), then launch times at B."""
+    import os
+    keys = ("MMG_FUSED_PANEL", "MMG_STORED_DEFER", "MMG_STORED_TW")
+    s = torch.tensor(math.log(1 / 0.07), device="cuda").exp()
+
+    def setenv(env):
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+
+    for n, d in [(256, 256), (1024, 512), (4096, 512), (8192, 256)]:
+        a, b = embeddings(n, d, seed=n + d)
+        setenv({})
+        ref = run(a, b, s, False)
+        for name, stored, env in VARIANTS[1:]:
+            setenv(env)
+            r = run(a, b, s, stored)
+            tol = 2e-3 if stored else 1e-5
+            da, db = rel(r[3], ref[3]), rel(r[4], ref[4])
+            print(f"n={n} D={d} {name:20s} dA {da:.2e} dB {db:.2e} {'ok' if max(da, db) < tol else 'MISMATCH'}", flush=True)
+    a, b = embeddings(B, D, seed=1)
+    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    gl = torch.ones((), device="cuda")
+    E = torch.empty((B, B), dtype=torch.bfloat16, device="cuda")
+    probe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ops.set_backward_probe(probe)
+    for rnd in range(2):
+        for name, stored, env in VARIANTS:
+            setenv(env)
+            e = E if stored else None
+            ts = []
+            for _ in range(5):
+                r = ops.infonce_forward_raw(ab, bb, s, 0, "bf16", e_out=e)
+                ops.infonce_backward_raw(ab, bb, s, r[0], r[1], gl, 0.5 / B, 0, "bf16", a32=a, b32=b, diag=r[2],
+                                         need_dscale=False, e_stored=e)
+                torch.cuda.synchronize()
+                ts.append(probe[0].elapsed_time(probe[1]))
+            print(f"B={B} round {rnd} {name:20s} fused bwd launch " + " ".join(f"{x:.3f}" for x in ts[1:]), flush=True)
+    setenv({})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "trace":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trace":
         trace(int(sys.argv[2]) if len(sys.argv) > 2 else 32768, 512, sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/trace")
     elif len(sys.argv) > 1 and sys.argv[1] == "time":
         time_(int(sys.argv[2]) if len(sys.argv) > 2 else 32768, int(sys.argv[3]) if len(sys.argv) > 3 else 512)
