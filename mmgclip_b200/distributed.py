@@ -52,6 +52,10 @@ class _PeerBuffers:
         self.handle.barrier(channel=1)
 
 
+# stored-E (ops.want_store_e) in the sharded loss: opt-in until measured on several GPUs
+_STORE_E_DIST = os.environ.get("MMGCLIP_B200_STORE_E_DIST", "0") == "1"
+
+
 def peer_reduce_active() -> bool:
     """True once a sharded backward has run with the NVLink peer reduction (i.e. not on the NCCL fallback)."""
     return any(v is not None for v in _peer_cache.values())
@@ -139,8 +143,8 @@ class _Kernels:
         return ops._operand(t, prec)
 
     @staticmethod
-    def forward(a_op, b_all_op, scale, diag_offset, prec, colsum=None):
-        return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec, colsum=colsum)
+    def forward(a_op, b_all_op, scale, diag_offset, prec, colsum=None, e_out=None):
+        return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec, colsum=colsum, e_out=e_out)
 
     @staticmethod
     def loss(rowsum, colsum_slice, diag, scale, inv_two_b):
@@ -199,13 +203,22 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
             dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
         off = rank * bl
+        # stored-E (ops.want_store_e) for the sharded loss: opt-in (MMGCLIP_B200_STORE_E_DIST=1) until it has been measured
+        # on several GPUs; only with the peer-memory backward, which is the one that reaches mmg_infonce_bwd_stored
+        e_mat = None
+        if (kernels is _Kernels and _STORE_E_DIST and a_local.is_cuda and peer_reduce_active() and
+                (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and
+                ops.want_store_e(bl, B, D, prec, ctx.needs_input_grad[2], n_owners=world)):
+            e_mat = torch.empty((bl, B), dtype=torch.bfloat16, device=a_local.device)
+        ctx.e_mat = e_mat
+        fwd_kw = {"e_out": e_mat} if e_mat is not None else {}
         cvec = _symm_vector("colsum", B, a_local.device, group) if kernels is _Kernels else None
         if cvec is not None:
             cvec.buf.zero_()  # the partial column sums accumulate straight into the symmetric buffer
-            rowsum, _, diag = kernels.forward(a_op, b_all, s, off, prec, colsum=cvec.buf[:B])
+            rowsum, _, diag = kernels.forward(a_op, b_all, s, off, prec, colsum=cvec.buf[:B], **fwd_kw)
             colsum = cvec.all_reduce()[:B]
         else:
-            rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec)
+            rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec, **fwd_kw)
             dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
         loss = kernels.loss(rowsum, colsum[off:off + bl], diag, s, 0.5 / B)
         lvec = _symm_vector("loss", 1, a_local.device, group) if kernels is _Kernels else None
@@ -234,7 +247,9 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             # gradient GEMM + reduce-scatter in one kernel: the slices add into their owners' buffers over NVLink
             dA, owns, dls = ops.infonce_backward_owners(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off,
                                                         [(peer.own, peer.ptrs)], peer.pre_sync, peer.post_sync, a32=a32,
-                                                        b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2])
+                                                        b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2],
+                                                        e_stored=ctx.e_mat)
+            ctx.e_mat = None
             dB = owns[0].clone()  # the symmetric buffer is reused by the next step
             dscale = None
             if ctx.needs_input_grad[2]:

@@ -404,7 +404,7 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
 
 def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: float, diag_offset: int, parts,
                             pre_sync=None, post_sync=None, after_part=None, a32=None, b32=None, diag=None,
-                            need_dscale: bool = True):
+                            need_dscale: bool = True, e_stored=None):
     """Row-sharded backward whose column-side gradient goes straight to its owners (mmg_infonce_bwd_owners).
 
     ``parts`` is a list of ``(own, owner_ptrs)``, one entry per column part (usually one): ``own`` is this rank's fp32
@@ -413,7 +413,10 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
     reduce-scatter sends home).  ``pre_sync`` / ``post_sync``: stream-ordered cross-rank barriers for the peer-memory
     case (every owner's buffer is initialised before anybody adds into it; all adds have landed before anybody reads its
     own).  ``after_part(i)`` runs right after part i has been launched (e.g. to start its reduce-scatter).
+    ``e_stored`` (bf16 [rows, cols] kept by the forward): stored-E backward (mmg_infonce_bwd_stored), no ``sum g*cos``.
     Returns (dA [rows, D], [own buffers], sum g*cos or None)."""
+    if e_stored is not None and need_dscale:
+        raise ValueError("the stored-E backward cannot produce d/d logit_scale")
     rows, D = a.shape
     cols = b.shape[0]
     n_parts = len(parts)
@@ -454,9 +457,14 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
         pre_sync()
     for i, (_, owner_ptrs) in enumerate(parts):
         ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
-        check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
-                                         _p(scal), _p(dA), ptrs, world, n_parts, i, _p(dls), _p(ws), ws.numel(),
-                                         _stream()), "mmg_infonce_bwd_owners")
+        if e_stored is not None:
+            check(lib.mmg_infonce_bwd_stored(_p(a), _p(b), _p(e_stored), e_stored.stride(0), rows, cols, D, diag_offset,
+                                             _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), ptrs, world, n_parts, i,
+                                             _p(ws), ws.numel(), _stream()), "mmg_infonce_bwd_stored")
+        else:
+            check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+                                             _p(scal), _p(dA), ptrs, world, n_parts, i, _p(dls), _p(ws), ws.numel(),
+                                             _stream()), "mmg_infonce_bwd_owners")
         if after_part is not None:
             after_part(i)
     if post_sync is not None:
