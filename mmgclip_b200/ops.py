@@ -661,7 +661,10 @@ class _InfoNCEFn(torch.autograd.Function):
         s = scale.detach().reshape(()).to(device=a_hat.device, dtype=torch.float32).contiguous()
         e_mat = None
         if want_store_e(n, n, D, prec, ctx.needs_input_grad[2]) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
-            e_mat = torch.empty((n, n), dtype=torch.bfloat16, device=a_hat.device)
+            try:
+                e_mat = torch.empty((n, n), dtype=torch.bfloat16, device=a_hat.device)
+            except torch.OutOfMemoryError:
+                e_mat = None  # not enough free HBM for E: the recompute path needs O(B*D) only
         rowsum, colsum, diag = infonce_forward_raw(a_op, b_op, s, 0, prec, e_out=e_mat)
         loss = infonce_loss_raw(rowsum, colsum, diag, s, 0.5 / n)
         ctx.prec = prec
