@@ -348,12 +348,16 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
   EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
   if (e_out != nullptr) {
+    // only the CTA-pair 256 x 256 tile variant of the E-storing epilogue has been run on hardware (it is the one every
+    // shape accepted by mmg_infonce_stored_supported takes)
+    if (!(tcfg.BN == 256 && tcfg.cg == 2))
+      return set_error(-3, "mmg_infonce_fwd_store: needs rows > 128 and cols > 128 (256 x 256 pair tiles)");
     // also keep E = exp(logit - s) as bf16 [rows, cols] for the stored-E backward: box = one epilogue warp's 32 x 64 block
     CUtensorMap mc;
     if ((rc = make_tmap(&mc, e_out, cols, rows, lde, 32)) != 0) return rc;
     EpiLseStore::Params es;
     es.rowsum = rowsum; es.colsum = colsum; es.diag = diag; es.scale_ptr = scale; es.diag_offset = diag_offset;
-    MMG_DISPATCH(EpiLseStore, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, es, es, st);
+    return launch<256, EpiLseStore, 2>(ma, mb, ma, mb, mc, mc, p0, p1, es, es, st);
   }
   MMG_DISPATCH(EpiLse, tcfg, ma, mb, ma, mb, ma, ma, p0, p1, e, e, st);
 }
