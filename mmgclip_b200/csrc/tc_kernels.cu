@@ -527,7 +527,8 @@ int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_p
   const int owner_rows = cols / n_owners;
   if (n_parts > 1 && ((owner_rows % n_parts) != 0 || ((owner_rows / n_parts) % 256) != 0)) return 0;
   const FusedPlan f = fused_plan(rows, cols, D, n_parts > 1 ? owner_rows / n_parts : 0, n_owners > 1);
-  return f.ok && pick_tile(rows, cols).BN == 256 ? 1 : 0;
+  const TileCfg t = pick_tile(rows, cols);
+  return f.ok && t.BN == 256 && t.cg == 2 ? 1 : 0;  // the forward's E-storing epilogue exists for pair tiles only
 }
 
 // Debug: where the MMG_FUSED_TRACE=1 timeline of the last fused launch of this shape lives inside the workspace.
