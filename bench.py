@@ -91,43 +91,165 @@ def synthetic_head_weights(d, e_image=768, e_text=768, seed=43):
 # reference arm / cpu_baseline: the oracle port of the reference step on the host cores
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference(sample_batch, steps, warmup):
+    """Time the reference's step on the host cores: its own projection.py / losses.py loaded by path where the reference
+    tree exists (kind "reference"), else the operation-for-operation port in oracle/clip_oracle.py (kind "port")."""
     import torch
     from oracle import clip_oracle as oc
+    from oracle import ref_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     xi, xt = oc.synthetic_features(sample_batch, E_IMG, E_TXT, seed=42)
     wi, wt = oc.synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
     xi, xt, wi, wt = (torch.from_numpy(t) for t in (xi, xt, wi, wt))
     ls = torch.tensor(math.log(1 / 0.07))
+    if ref_loader.load_reference() is not None:
+        kind = "reference"
+        fn = ref_loader.ReferenceStep(wi, wt, math.log(1 / 0.07))
+        step = lambda: fn(xi, xt)  # noqa: E731
+    else:
+        kind = "port"
+        step = lambda: oc.torch_train_step(xi, xt, wi, wt, ls)  # noqa: E731
     for _ in range(warmup):
-        oc.torch_train_step(xi, xt, wi, wt, ls)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        out = oc.torch_train_step(xi, xt, wi, wt, ls)
+        out = step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"pairs_per_s": sample_batch / dt, "ms_per_step": dt * 1e3, "cores": cores, "loss": float(out["loss"]),
-            "threads": torch.get_num_threads()}
+            "threads": torch.get_num_threads(), "kind": kind, "steps": steps, "warmup": warmup}
+
+
+def cpu_kind_text(kind):
+    return ("the reference's own projection.py / losses.py loaded by path + mmgclip_model.py:124-136 restated"
+            if kind == "reference" else "oracle port of the reference step (operation for operation, fp32 eager PyTorch)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = args.cpu_sample_batch
-    r = cpu_reference(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
-    desc = (f"oracle port (fp32 eager PyTorch on CPU) of the reference step at batch {sample} of {GLOBAL_BATCH}, "
-            f"{r['threads']} threads; cost per pair grows ~linearly with the batch, so the full {GLOBAL_BATCH} batch would be "
-            f"~{GLOBAL_BATCH // sample}x slower per pair")
+    sample = min(args.cpu_sample_batch or 16384, GLOBAL_BATCH)
+    r = cpu_reference(sample, max(1, args.steps), max(0, args.warmup))  # exactly the steps / warm-ups that are printed
+    desc = (f"{cpu_kind_text(r['kind'])} on the host CPU at batch {sample} of {GLOBAL_BATCH}, {r['threads']} threads, "
+            f"{r['steps']} timed steps after {r['warmup']} warm-ups; cost per pair grows ~linearly with the batch (B x B "
+            f"logits), so the full {GLOBAL_BATCH} batch would be ~{GLOBAL_BATCH / sample:.0f}x slower per pair")
+    cfg = workload_config(args.gpus, sample_batch=sample)
+    if sample != GLOBAL_BATCH:
+        cfg["workload"] += f" -- CPU arm timed on a bounded sample: batch {sample}"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample_batch=sample),
-        "cpu_baseline": {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": desc},
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "loss": r["loss"],
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": desc},
         "e2e": {"value": r["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parity of the timed step, checked outside the timed regions on the bench's own inputs (every N)
+# ----------------------------------------------------------------------------------------------------------------
+def parity_fp64(torch, dev, xi_g, xt_g, wi, wt, loss_gpu, dwi_gpu, dwt_gpu, chunk=2048):
+    """Float64 closed form of the WHOLE step on the full global batch (heads mmgclip/networks/
+    projection.py:33, normalise + logits mmgclip_model.py:128-136, CLIPLoss losses.py:36-44 and their gradients down to the
+    head weights), evaluated with torch float64 on the GPU in row chunks (cuBLAS dgemm -- an independent implementation; a
+    few hundred ms at B = 32768) and compared with what the timed step produced: the loss and both head-weight gradients
+    (after the cross-rank all-reduce at N > 1).  Errors are max-abs / max-abs and Frobenius-relative."""
+    f64 = torch.float64
+    Xi, Xt = torch.from_numpy(xi_g).to(dev, f64), torch.from_numpy(xt_g).to(dev, f64)
+    Wi, Wt = torch.from_numpy(wi).to(dev, f64), torch.from_numpy(wt).to(dev, f64)
+    s = float(torch.tensor(math.log(1 / 0.07), dtype=torch.float32).exp())  # the fp32 scale the step uses
+    ui, ut = Xi @ Wi.t(), Xt @ Wt.t()
+    ni, nt = ui.norm(dim=1, keepdim=True), ut.norm(dim=1, keepdim=True)
+    I, T = ui / ni, ut / nt
+    B = I.shape[0]
+    diag = s * (I * T).sum(1)
+    rowsum = torch.empty(B, dtype=f64, device=dev)
+    colsum = torch.zeros(B, dtype=f64, device=dev)
+    for r0 in range(0, B, chunk):
+        E = torch.exp(s * (I[r0:r0 + chunk] @ T.t()) - s)
+        rowsum[r0:r0 + chunk] = E.sum(1)
+        colsum += E.sum(0)
+    loss = float(((torch.log(rowsum) + s - diag) + (torch.log(colsum) + s - diag)).sum() / (2 * B))
+    coef = s / (2 * B)
+    rinv, cinv = coef / rowsum, coef / colsum
+    dI, dT = torch.empty_like(I), torch.zeros_like(T)
+    for r0 in range(0, B, chunk):
+        r1 = min(B, r0 + chunk)
+        G = torch.exp(s * (I[r0:r1] @ T.t()) - s) * (rinv[r0:r1, None] + cinv[None, :])
+        idx = torch.arange(r1 - r0, device=dev)
+        G[idx, r0 + idx] -= 2 * coef
+        dI[r0:r1] = G @ T
+        dT += G.t() @ I[r0:r1]
+    del G, E
+    dui = (dI - I * (I * dI).sum(1, keepdim=True)) / ni
+    dut = (dT - T * (T * dT).sum(1, keepdim=True)) / nt
+    dWi, dWt = dui.t() @ Xi, dut.t() @ Xt
+
+    def err(got, ref):
+        d = got.to(f64) - ref
+        return {"max_abs_over_max_abs": float(d.abs().max() / ref.abs().max()),
+                "frobenius_rel": float(d.norm() / ref.norm())}
+    out = {"checker": "float64 closed form of the whole step on the full global batch (torch float64 on the GPU, row "
+                      "chunks; bench.py parity_fp64), outside the timed regions",
+           "tolerance": 2e-3, "loss": loss_gpu, "loss_fp64": loss, "loss_rel_err": abs(loss_gpu - loss) / abs(loss),
+           "dw_image": err(dwi_gpu, dWi), "dw_text": err(dwt_gpu, dWt)}
+    out["ok"] = bool(out["loss_rel_err"] < 2e-3 and out["dw_image"]["frobenius_rel"] < 2e-3
+                     and out["dw_text"]["frobenius_rel"] < 2e-3)
+    return out
+
+
+def gpu_eager_reference(torch, dev, batches, iters=5):
+    """Informational: the reference's eager arithmetic (mmgclip/networks/projection.py:33, mmgclip_model.py:124-136,
+    losses.py:36-44, loss.backward()) on the same GPU under the installed torch -- fp32 as the reference runs it, and under
+    bf16 autocast.  Stock ATen / cuBLAS kernels; it materialises >= 6 [B, B] fp32 matrices (24+ GiB at B = 32768)."""
+    import torch.nn.functional as F
+    out = {}
+    for Bn in batches:
+        try:
+            xi_h, xt_h = synthetic_features(Bn, E_IMG, E_TXT, seed=42)
+            wi_h, wt_h = synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
+            xi, xt = torch.from_numpy(xi_h).to(dev), torch.from_numpy(xt_h).to(dev)
+            wi = torch.from_numpy(wi_h).to(dev).requires_grad_()
+            wt = torch.from_numpy(wt_h).to(dev).requires_grad_()
+            ls = torch.tensor(math.log(1 / 0.07), device=dev)
+            labels = torch.arange(Bn, device=dev)
+
+            def step():
+                wi.grad = wt.grad = None
+                ie, te = F.linear(xi, wi), F.linear(xt, wt)
+                ie = ie / ie.norm(dim=1, keepdim=True)
+                te = te / te.norm(dim=1, keepdim=True)
+                s = ls.exp()
+                lpi = s * ie @ te.t()
+                lpt = s * te @ ie.t()
+                loss = (F.cross_entropy(lpi, labels) + F.cross_entropy(lpt, labels)) / 2
+                loss.backward()
+                return loss
+            for mode in ("fp32", "bf16_autocast"):
+                ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode != "fp32" else torch.autocast("cuda", enabled=False)
+                with ctx:
+                    for _ in range(2):
+                        step()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(iters):
+                        loss = step()
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                out[f"b{Bn}_{mode}"] = {"ms_per_step": ms, "pairs_per_s": Bn / (ms * 1e-3), "loss": float(loss)}
+            del xi, xt, wi, wt
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001  (informational block: never lose the bench line over it)
+            out[f"b{Bn}_error"] = repr(exc)[:200]
+    out["what"] = ("the reference's eager ops on cuda:0 under torch " + torch.__version__ + " (stock ATen/cuBLAS kernels), "
+                   "device-resident inputs, CUDA-event timing; informational, outside the timed regions")
+    return out
 
 
 def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=None, symm=None, stored_e=None):
@@ -271,7 +393,8 @@ def run_gpu(args):
     wi, wt = synthetic_head_weights(D_PROJ, E_IMG, E_TXT, seed=43)
     xi_h = torch.from_numpy(xi_g[rank * bl:(rank + 1) * bl].copy())
     xt_h = torch.from_numpy(xt_g[rank * bl:(rank + 1) * bl].copy())
-    del xi_g, xt_g
+    if rank != 0 or not args.parity:
+        del xi_g, xt_g  # rank 0 keeps the global batch on the host for the float64 parity check after the timed regions
     step_bytes = (xi_h.numel() + xt_h.numel()) * 4
     n_sets = max(2, -(-(256 << 20) // step_bytes))
     n_sets = min(n_sets, 16)
@@ -291,6 +414,7 @@ def run_gpu(args):
     def step(xi, xt):
         head_i.layer.weight.grad = None
         head_t.layer.weight.grad = None
+        ops.mark("start")
         if side is not None:
             # the two heads are independent: the text head runs on a side stream so its bandwidth-bound kernels (cast,
             # normalise) overlap the other head's contraction -- and autograd replays each head's backward on the
@@ -307,12 +431,17 @@ def run_gpu(args):
                 te._mmg_bf16.record_stream(cur)
         else:
             te = head_t.forward_normalized(xt)
+            ops.mark("head_t")
             gathered = gather_columns_async(te, group=group, prec=prec) if world > 1 else None  # overlaps the image head
             ie = head_i.forward_normalized(xi)
+            ops.mark("head_i")
         loss = sharded_info_nce(ie, te, logit_scale, group=group, prec=prec, gathered=gathered)
+        ops.mark("loss")
         loss.backward()
+        ops.mark("backward")
         if world > 1:
             allreduce_gradients(head_i, head_t, group=group)
+        ops.mark("grad_ar")
         return loss
 
     def barrier():
@@ -338,6 +467,8 @@ def run_gpu(args):
             ops.set_backward_probe(probe)
         except Exception:  # noqa: BLE001  (older torch: no external events)
             probe = None
+    timeline = {} if args.timeline else None
+    ops.set_timeline(timeline)
     # e2e staging buffers (the H2D copies land here); allocated before any capture so they can be graph inputs
     stage = [(torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])) for _ in range(2)]
     # ---- one CUDA graph per input set: a step is a single cudaGraphLaunch (mmgclip_b200/graph.py) ----
@@ -387,6 +518,28 @@ def run_gpu(args):
         except Exception:  # noqa: BLE001
             live_bwd_ms = None
     loss_value = float(loss.item())
+    dw_value = (head_i.layer.weight.grad.detach().clone(), head_t.layer.weight.grad.detach().clone())
+    if timeline is not None:
+        # phase boundaries of the LAST timed step on every rank (ms since that rank's "start" mark; external events
+        # captured into the replayed graph) -> gpurun_out/timeline_n<N>.json.  Diagnostic output, not part of the JSON line.
+        torch.cuda.synchronize()
+        t0 = timeline.get("start")
+        mine = {}
+        for k, ev in timeline.items():
+            try:
+                mine[k] = t0.elapsed_time(ev)
+            except Exception:  # noqa: BLE001  (a mark that the last replay did not pass)
+                pass
+        allm = [mine]
+        if world > 1:
+            allm = [None] * world
+            dist.all_gather_object(allm, mine)
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}.json"), "w") as f:
+                json.dump({"ms_per_step": ms_value, "ranks": [dict(sorted(m.items(), key=lambda kv: kv[1])) for m in allm]}, f,
+                          indent=1)
+        ops.set_timeline(None)
 
     # ---- end-to-end timing: pinned host features -> H2D (prefetched one step ahead) -> step -> loss D2H ----
     copy_stream = torch.cuda.Stream(device=dev)
@@ -437,12 +590,30 @@ def run_gpu(args):
         sampler.end()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / K)
     clocks = sampler.stop() if sampler is not None else None
+    # peak device memory of the whole run (max over ranks): O(B*D) by design -- a [rows, B] fp32 logit matrix alone would be
+    # 4*bl*B bytes per rank (the reference materialises >= 6 such matrices at world = 1)
+    peak_mem = float(torch.cuda.max_memory_allocated(dev))
+    if world > 1:
+        t = torch.tensor([peak_mem], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        peak_mem = float(t.item())
 
     # ---- per-launch timing of the dominant kernels (informational; outside the timed regions) ----
     kernels = None
     if rank == 0 and args.kernel_breakdown:
         kernels = kernel_breakdown(torch, ops, dev, bl, B, D_PROJ,
                                    stored_e=world == 1 and ops.want_store_e(bl, B, D_PROJ, prec, False))
+    parity = None
+    if rank == 0 and args.parity:
+        try:
+            parity = parity_fp64(torch, dev, xi_g, xt_g, wi, wt, loss_value, dw_value[0], dw_value[1])
+        except Exception as exc:  # noqa: BLE001  (never lose the bench line over the checker)
+            parity = {"error": repr(exc)[:300]}
+        del xi_g, xt_g
+        torch.cuda.empty_cache()
+    eager = None
+    if rank == 0 and world == 1 and args.gpu_eager and prec == "bf16":
+        eager = gpu_eager_reference(torch, dev, sorted({4096, B}) if B <= 32768 else [4096])
 
     def finish(code=0):
         # Multi-GPU teardown: NCCL communicators that were captured into CUDA graphs do not always unwind cleanly
@@ -484,6 +655,7 @@ def run_gpu(args):
         "config": workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active(),
                                   symm=symm_allreduce_active(), stored_e=stored_e),
         "loss": loss_value,
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": step_bytes * world, "d2h_bytes_per_step": 4 * world,
@@ -491,35 +663,42 @@ def run_gpu(args):
                        "device batch upload (the next step's, on a copy stream) + the step + the loss read-back; K "
                        "uploads complete inside the timed region (CUDA events, max over ranks)"},
         "gpu_launches": int(launches),
+        "memory": {"max_allocated_bytes_per_rank": peak_mem, "one_logit_block_fp32_bytes_per_rank": 4.0 * bl * B,
+                   "note": "max over ranks of torch.cuda.max_memory_allocated for the whole run (all input sets, staging "
+                           "buffers and graphs included); no [rows, B] matrix is ever allocated on the default path"},
         # dominant kernel = the fused persistent backward launch (~65% of the step): algorithmic FLOPs per launch (dI + dT;
         # the recomputed cosines are not counted) / live CUDA-event launch duration, against the sustained bf16 peak (it
         # runs inside a long step).  `whole_step` is the same ratio for the entire step (all kernels, algorithmic FLOPs
         # only) -- the number the metric's "% of peak" means.
         "roofline": {"bound": "tensor",
                      "kernel": dom["kernel"] if dom else "gemm_tc_kernel",
-                     "achieved": dom["tflops"] if dom else ach, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": (dom["tflops"] if dom else ach) / peaks["sustained"],
-                     "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained; burst = "
-                                    + str(peaks["burst"]) + ")",
+                     "achieved": dom["tflops"] if dom else ach, "peak": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": (dom["tflops"] if dom else ach) / peaks["burst"],
+                     "frac_of_sustained_peak": (dom["tflops"] if dom else ach) / peaks["sustained"],
+                     "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops = burst cuBLAS figure, the one "
+                                    "SURVEY s8d defines the fraction against; sustained = " + str(peaks["sustained"]) + ")",
                      "traffic": ncu_traffic_bytes(stored_e),
                      "dominant_kernel_live": dom if (live_bwd_ms is not None and live_bwd_ms > 0) else None,
-                     "whole_step": {"algorithmic_flops_per_step": fl, "achieved": ach, "frac": ach / peaks["sustained"],
-                                    "frac_of_burst_peak": ach / peaks["burst"]},
+                     "whole_step": {"algorithmic_flops_per_step": fl, "achieved": ach, "frac": ach / peaks["burst"],
+                                    "frac_of_sustained_peak": ach / peaks["sustained"]},
                      "kernels": kernels},
     }
+    if eager is not None:
+        line["reference_gpu_eager"] = eager
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(args.cpu_sample_batch, 3, 1)
+        sample = min(args.cpu_sample_batch or 8192, B)
+        r = cpu_reference(sample, 3, 1)
         line["cpu_baseline"] = {
-            "value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
-            "sample": f"oracle port of the reference step (fp32 eager PyTorch, {r['threads']} threads) at batch "
-                      f"{args.cpu_sample_batch} of {B}, 3 steps; per-pair cost grows ~linearly with batch"}
+            "value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": f"{cpu_kind_text(r['kind'])}, {r['threads']} threads, at batch {sample} of {B}, 3 timed steps after "
+                      f"1 warm-up; per-pair cost grows ~linearly with the batch"}
     print(json.dumps(line))
     return finish(0)
 
 
 def kernel_breakdown(torch, ops, dev, rows, cols, d, stored_e=False):
     """Live CUDA-event timing (no profiler) of each tcgen05 kernel family at the bench shape (local rows x global
-    columns), outside the timed regions.  The backward phases are separated with the library's MMG_BWD_PHASES hook."""
+    columns), outside the timed regions."""
     gen = torch.Generator(device=dev).manual_seed(7)
     a = torch.nn.functional.normalize(torch.randn(rows, d, device=dev, generator=gen), dim=1)
     b = torch.nn.functional.normalize(torch.randn(cols, d, device=dev, generator=gen), dim=1)
@@ -575,25 +754,18 @@ def kernel_breakdown(torch, ops, dev, rows, cols, d, stored_e=False):
             del e_mat
         except Exception as exc:  # noqa: BLE001  (informational section: never lose the bench line over it)
             out["stored_e_breakdown_error"] = repr(exc)
-    # the block loop the fused launch replaces (general shapes still use it), phases separated with MMG_BWD_PHASES
-    os.environ["MMG_BWD_FUSED"] = "0"
+    # the block loop the fused launch replaces (general shapes still use it)
     try:
+        ops.set_tuning(fused=0)
         t_loop = timeit(bwd)
-        block = 8192
-        n_blocks = (-(-rows // block)) * (-(-cols // block))
-        os.environ["MMG_BWD_PHASES"] = "1"
-        t_coef = timeit(bwd)
-        os.environ["MMG_BWD_PHASES"] = "2"
-        t_grad = timeit(bwd)
     finally:
-        os.environ.pop("MMG_BWD_PHASES", None)
-        os.environ.pop("MMG_BWD_FUSED", None)
+        ops.set_tuning()
+    block = 8192
+    n_blocks = (-(-rows // block)) * (-(-cols // block))
     out["backward_block_loop"] = {
         "total_ms": t_loop, "launches": 2 * n_blocks,
-        "grad_coefficients": {"kernel": "gemm_tc_kernel<256, EpiGrad, 2>", "launches": n_blocks,
-                              "ms_per_launch": t_coef / n_blocks, "tflops_executed": f / t_coef / 1e9},
-        "grad_gemms": {"kernel": "gemm_tc_kernel<256, EpiStoreF32, 2> (dI and dT of one 8192x8192 block per launch)",
-                       "launches": n_blocks, "ms_per_launch": t_grad / n_blocks, "tflops": 2 * f / t_grad / 1e9}}
+        "kernels": "gemm_tc_kernel<256, EpiGrad, 2> (coefficients of one 8192 x 8192 block) + gemm_tc_kernel<256, EpiStoreF32, 2> "
+                   "(its dI and dT) per block"}
     return out
 
 
@@ -652,7 +824,13 @@ def main():
     ap.add_argument("--dim", type=int, default=D_PROJ,
                     help="projection dimension D (default: the metric's 512; BASELINE config 5 uses 1024)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample-batch", type=int, default=8192)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="batch of the CPU arm's bounded sample (default: 8192 for the cpu_baseline block, 16384 for "
+                         "--impl reference)")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", default=True,
+                    help="skip the float64 parity check of the timed step (rank 0, outside the timed regions)")
+    ap.add_argument("--no-gpu-eager", dest="gpu_eager", action="store_false", default=True,
+                    help="skip the informational reference_gpu_eager block (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-breakdown", action="store_true", default=True)
     ap.add_argument("--no-kernel-breakdown", dest="kernel_breakdown", action="store_false")
@@ -663,6 +841,8 @@ def main():
                     default=os.environ.get("MMGCLIP_BENCH_HEAD_OVERLAP", "0") == "1",
                     help="run the text head on a side stream (forward and, through autograd, backward)")
     ap.add_argument("--no-head-overlap", dest="head_overlap", action="store_false")
+    ap.add_argument("--timeline", action="store_true",
+                    help="diagnostic: record phase-boundary events in the step and dump them to gpurun_out/timeline_n<N>.json")
     ap.add_argument("--workload", default="clip", choices=["clip", "zeroshot"],
                     help="clip = the headline metric (default); zeroshot = BASELINE config 4 (secondary line)")
     ap.add_argument("--zeroshot-rows", type=int, default=1 << 20)

@@ -205,7 +205,15 @@ int mmg_adamw_step(float* const* params, const float* const* grads, float* const
                    const long long* numel, int n_tensors, float lr, const float* lr_dev, float beta1, float beta2,
                    float eps, float weight_decay, long long* step_state, mmg_stream_t stream);
 
-/* Debug timeline of the fused backward (environment MMG_FUSED_TRACE=1 at launch time; mmg_infonce_workspace_bytes then
+/* Plan knobs of the fused InfoNCE backward, process-wide: key in {"fused" (0 = block loop), "fused_rb", "fused_cb" (block
+ * shape), "fused_nbuf" (scratch buffers), "fused_ksl", "fused_ksl_t" (64-wide K blocks per dA / dB gradient slice),
+ * "fused_sr", "fused_sc" (block-order super-tile)}; value < 0 unsets the knob, key "reset" unsets all.  Every setting gives
+ * the same results (the tests walk several schedules with it); the defaults are the measured best.  The product library
+ * reads no environment variable -- the measurement build (make measure, -DMMG_MEASURE) maps MMG_* variables onto these. */
+int mmg_tune(const char* key, int value);
+
+/* Debug timeline of the fused backward (measurement builds only: -DMMG_MEASURE and MMG_FUSED_TRACE=1 at launch time; the
+ * product library always returns 0 here).  mmg_infonce_workspace_bytes then
  * includes the region): per CTA and role (0 TMA producer, 1 MMA issuer, 2 epilogue warp 0, 3 transform warp 0)
  * `records_per_role` records {globaltimer ns, tag} of 16 bytes at workspace + *offset; tag = role<<60 | event<<56 |
  * type<<52 | block<<32 | tm<<16 | tn (events: 0 item picked up, 1 dependency wait over, 2 item finished).  Returns 1 when
@@ -234,7 +242,8 @@ int mmg_dot_sum(const float* x, const float* y, long long n, float* out, mmg_str
 /* ---- zero-shot prompt scoring (mmgclip_model.py:201-209; evaluator.py:182-188,282-299,354-368) ------------- */
 /* logits[n,c] = (s*img[n,:]) . txt[c,:] in fp32 (scale-then-multiply, as the reference's operator precedence does),
  * probs = softmax over c, argmax with ties -> lowest index, top-k ordered (value desc, index asc).
- * img: [N, D], txt: [C, D] fp32 row-major, C <= 64, k <= 8.  Any output pointer may be NULL. */
+ * img: [N, D], txt: [C, D] fp32 row-major, k <= 8.  Any output pointer may be NULL when C <= 64; with more prompts a
+ * one-warp-per-row kernel runs instead of the tiled one and logits_out is required (it parks the row's logits there). */
 int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
                        float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
                        mmg_stream_t stream);

@@ -71,6 +71,7 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "mmg_debug_fused_trace_region": (c_int, [c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int),
                                              POINTER(c_int)]),
+    "mmg_tune": (c_int, [c_char_p, c_int]),
     "mmg_fused_bwd_schedule": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int,
                                        POINTER(c_int)]),
     "mmg_ce_fwd": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),

@@ -79,11 +79,6 @@ struct BwdFusedParams {
   // gradient rows a super-tile accumulates into and its operand rows can stay in L2.  sr = sc = 1 (the default: measured
   // no better with larger super-tiles, see fill_schedule) is plain row-major.
   int sr, sc;
-  // Per-panel dependencies (kPanel kernels, MMG_FUSED_PANEL=1; NULL otherwise): coefficient tiles of block s, row panel tm
-  // / column panel tn that are complete.  A dA slice of row panel tm only reads the coefficient tiles (tm, *), a dB slice
-  // of column panel tn only the tiles (*, tn), so they need not wait for the whole block.
-  unsigned int* doneArow;  // [nblk * tAm], wants tAn arrivals per CTA of the pair
-  unsigned int* doneAcol;  // [nblk * tAn], wants tAm arrivals per CTA of the pair
   __host__ __device__ void block_rc(int blk, int& rb, int& cb) const {
     const int per = sr * sc;
     const int sidx = blk / per, w = blk - sidx * per;
@@ -177,11 +172,6 @@ struct BwdCursor {
   }
 };
 
-// does the cursor still hold a coefficient tile?  (a cursor only ever yields A items in increasing order)
-__host__ __device__ __forceinline__ bool cur_has_more_a(const BwdCursor& cur, const BwdFusedParams&) {
-  return cur.a < cur.na_total;
-}
-
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -209,22 +199,6 @@ __device__ __forceinline__ void publish_tile(unsigned int* pub_cnt, unsigned int
     if ((old & (kEW - 1)) == kEW - 1) {  // last of the CTA's epilogue warps
       fence_proxy_async_all();
       red_release_gpu_add(done_ctr, 1u);
-    }
-  }
-  __syncwarp();
-}
-
-// kPanel: the same, bumping the tile's row-panel and column-panel counters instead of the block counter
-template <int kEW>
-__device__ __forceinline__ void publish_tile2(unsigned int* pub_cnt, unsigned int seq, unsigned int* ctr_row,
-                                              unsigned int* ctr_col, int lane) {
-  if (lane == 0) {
-    tma_store_wait_all();
-    const unsigned int old = atom_acq_rel_cta_add(pub_cnt + (seq & 7u), 1u);
-    if ((old & (kEW - 1)) == kEW - 1) {  // last of the CTA's epilogue warps
-      fence_proxy_async_all();
-      red_release_gpu_add(ctr_row, 1u);
-      red_release_gpu_add(ctr_col, 1u);
     }
   }
   __syncwarp();
@@ -315,71 +289,13 @@ __device__ __forceinline__ void stored_e_rows(const BwdFusedParams& p, const uin
 }
 
 // kTW = transform warps of the stored-E mode (0 = recompute mode): warps 4 + kEW .. 4 + kEW + kTW - 1.
-// Same, with a hook that runs once right after the first round of loads has been issued (kDefer instantiations: the
-// deferred publish of the previous tile hides its memory-barrier latency there).
-template <int kRows, class Hook>
-__device__ __forceinline__ void stored_e_rows_hook(const BwdFusedParams& p, const uint8_t* e_rows, long long e_pitch,
-                                              uint8_t* g_rows, long long g_pitch, const float* rinv_rows,
-                                              const float* cinv_cols, int row_g0, int col_g0, int lane,
-                                                   Hook&& after_first_loads) {
-  // e_rows / g_rows: first row of the share at the tile's first column; pitches in bytes
-  // row_g0: global column paired with the share's first row; col_g0: global column of the tile's first column
-  static_assert(kRows % 8 == 0, "rows are processed eight at a time");
-  float cv[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cv[j] = __ldg(cinv_cols + lane * 8 + j);
-  const bool has_diag = (row_g0 < col_g0 + 256) && (row_g0 + kRows > col_g0);  // warp-uniform
-  float dcoef = 0.f;
-  bool zero_diag = false;
-  if (has_diag) {
-    dcoef = __ldg(p.scal);
-    zero_diag = __ldg(p.scal + 2) != 0.f;
-  }
-#pragma unroll 1
-  for (int r0 = 0; r0 < kRows; r0 += 8) {
-    uint4 ev[8];
-    float ri[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      ev[i] = __ldcs(reinterpret_cast<const uint4*>(e_rows + (r0 + i) * e_pitch + lane * 16));
-      ri[i] = __ldg(rinv_rows + r0 + i);
-    }
-    if (r0 == 0) after_first_loads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t w[4] = {ev[i].x, ev[i].y, ev[i].z, ev[i].w};
-      float g[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        g[2 * k] = __uint_as_float(w[k] << 16) * (ri[i] + cv[2 * k]);
-        g[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u) * (ri[i] + cv[2 * k + 1]);
-      }
-      if (has_diag) {
-        const int dj = row_g0 + r0 + i - (col_g0 + lane * 8);  // index of the matching column among this thread's 8
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j == dj) g[j] = zero_diag ? 0.f : g[j] - dcoef;
-      }
-      uint4 o;
-      o.x = pack_bf16x2(g[0], g[1]);
-      o.y = pack_bf16x2(g[2], g[3]);
-      o.z = pack_bf16x2(g[4], g[5]);
-      o.w = pack_bf16x2(g[6], g[7]);
-      *reinterpret_cast<uint4*>(g_rows + (r0 + i) * g_pitch + lane * 16) = o;
-    }
-  }
-}
-
-// kTW = transform warps of the stored-E mode (0 = recompute mode): warps 4 + kEW .. 4 + kEW + kTW - 1.
-// kTrace compiles the debug timeline in (MMG_FUSED_TRACE=1 selects those instantiations; the production kernels carry none
-// of it).
-// kDefer (stored-E only, MMG_STORED_DEFER=1): a coefficient tile is published while the NEXT tile's loads are in flight
-// instead of right after its own stores.  Separate instantiation: the default kernels do not contain any of it.  Written
-// after the round's GPU budget was spent -- compiled and covered at schedule level by tests/test_fused_schedule_cpu.py,
-// not yet run on a GPU.
-// kPanel (MMG_FUSED_PANEL=1): per-panel instead of per-block doneA dependencies (see BwdFusedParams::doneArow).  Separate
-// instantiations, same status as kDefer: compiled, schedule-level semantics checked on the CPU, not yet run on a GPU.
-template <int BN, int kEW, int kTW, bool kTrace = false, bool kDefer = false, bool kPanel = false>
+// kTrace compiles the debug timeline in (measurement builds only, -DMMG_MEASURE + MMG_FUSED_TRACE=1; the product library
+// carries none of it).
+// Variants that were built, measured on hardware and deleted because they did not win (numbers in DESIGN.md s4.2): per-panel
+// instead of per-block doneA counters (2.60 vs 2.61 ms at 32768^2, 0.352 vs 0.355 ms at 4096 x 32768; stored-E 2.51 vs
+// 2.41 ms), a deferred publish of the stored-E tiles (2.51 vs 2.41 ms), sixteen transform warps (2.44 vs 2.41 ms), 128-column
+// accumulator tiles (5.9 vs 2.6 ms) and sixteen epilogue warps (2.65 vs 2.61 ms).
+template <int BN, int kEW, int kTW, bool kTrace = false>
 __global__ void __launch_bounds__(32 * (4 + kEW + kTW), 1)
 infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_constant__ CUtensorMap mBk,
                          const __grid_constant__ CUtensorMap mAmn, const __grid_constant__ CUtensorMap mBmn,
@@ -463,12 +379,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       const int col0 = p.global_cb(cbl) * p.Cb;  // first global column of the block
       const int buf = it.blk % p.nbuf;
       if constexpr (kTrace) if (lane == 0) trace_event(p.trace, 0, ntr, 0, it.type, it.blk, it.tm, it.tn);
-      if constexpr (kPanel) {
-        if (it.type == 1)
-          wait_counter(p.doneArow + it.blk * p.tAm + it.tm, static_cast<unsigned int>(p.tAn) * 2u, lane);
-        else if (it.type == 2)
-          wait_counter(p.doneAcol + it.blk * p.tAn + it.tm, static_cast<unsigned int>(p.tAm) * 2u, lane);
-      } else if (it.type != 0 && it.blk > verified) {
+      if (it.type != 0 && it.blk > verified) {
         wait_counter(p.doneA + it.blk, wantA, lane);
         verified = it.blk;
       }
@@ -565,8 +476,6 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int n = 0;
     float carry = 0.f;
     int pending = -1;     // block whose coefficient-tile stores of this warp are not yet published in doneA
-    int pend_tm = 0, pend_tn = 0;  // (kPanel) that tile's panels
-    (void)pend_tm; (void)pend_tn;
     unsigned int a_seq = 0;  // coefficient tiles this warp has finished (identical across the CTA's epilogue warps)
     int verified = -1;    // scratch buffers of blocks [0, verified + nbuf] are known to be free
     int ntr = 0;
@@ -579,11 +488,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       if (pending >= 0) {
         // publish the previous coefficient tile (deferred to here so the stores' latency is off the critical path, and
         // done BEFORE blocking on the next accumulator so it never depends on this item's progress)
-        if constexpr (kPanel)
-          publish_tile2<kEW>(pub_cnt, a_seq++, p.doneArow + pending * p.tAm + pend_tm, p.doneAcol + pending * p.tAn + pend_tn,
-                             lane);
-        else
-          publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
+        publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
         pending = -1;
       }
       if (kStoredE && it.type == 0) continue;  // the transform warps own the coefficient tiles
@@ -612,7 +517,6 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         FusedGrad::template run<BN>(gp, tacc, it.tm * 256 + half_off, it.tn * BN, p.Rb, p.Cb, half, q, lane, ewarp,
                            epi_scratch + acc_stage * BN + half * (BN / (kEW / 4)), &mGst, staging, 0, carry);
         pending = it.blk;
-        pend_tm = it.tm; pend_tn = it.tn;
       } else {
         // all MMAs of this slice have completed => its TMA reads of the coefficient scratch are done
         if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
@@ -635,13 +539,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       }
       if constexpr (kTrace) if (ewarp == 0 && lane == 0) trace_event(p.trace, 2, ntr, 2, it.type, it.blk, it.tm, it.tn);
     }
-    if (pending >= 0) {
-      if constexpr (kPanel)
-        publish_tile2<kEW>(pub_cnt, a_seq++, p.doneArow + pending * p.tAm + pend_tm, p.doneAcol + pending * p.tAn + pend_tn,
-                           lane);
-      else
-        publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
-    }
+    if (pending >= 0) publish_tile<kEW>(pub_cnt, a_seq++, p.doneA + pending, lane);
     FusedGrad::finish(gp, carry, lane);
   } else if (kStoredE && warp >= 4 + kEW) {
     // ===================== transform warps (stored-E mode, both CTAs) =====================
@@ -649,8 +547,6 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     const int tw = warp - (4 + kEW);
     int verified = -1;  // scratch buffers of blocks [0, verified + nbuf] are known to be free
     int ntr = 0;
-    int pend_blk = -1, pend_tm = 0, pend_tn = 0;  // kDefer: tile whose stores are not yet published
-    (void)pend_blk; (void)pend_tm; (void)pend_tn;
     uint8_t* g_base = static_cast<uint8_t*>(p.G);
     while (cur.next(p, it)) {
       if (it.type != 0) continue;
@@ -667,55 +563,18 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
       const int r0 = it.tm * 256 + static_cast<int>(cta_rank) * kBM + tw * kRowsPerWarp;  // first row inside the block
       const int c0 = it.tn * BN;                                                          // first column inside the block
       const long long grow0 = static_cast<long long>(rb) * p.Rb + r0;                     // local row
-      if constexpr (!kDefer) {
-        stored_e_rows<kRowsPerWarp>(p, static_cast<const uint8_t*>(p.E) + (grow0 * p.ldE + col0 + c0) * 2, p.ldE * 2,
-                                    g_base + ((static_cast<long long>(buf) * p.Rb + r0) * p.Cb + c0) * 2,
-                                    static_cast<long long>(p.Cb) * 2, p.rinv + grow0, p.cinv + col0 + c0,
-                                    static_cast<int>(grow0) + p.diag_offset, col0 + c0, lane);
-        // all transform warps' stores -> one gpu-scope release per CTA (the consumers read the scratch through TMA)
+      stored_e_rows<kRowsPerWarp>(p, static_cast<const uint8_t*>(p.E) + (grow0 * p.ldE + col0 + c0) * 2, p.ldE * 2,
+                                  g_base + ((static_cast<long long>(buf) * p.Rb + r0) * p.Cb + c0) * 2,
+                                  static_cast<long long>(p.Cb) * 2, p.rinv + grow0, p.cinv + col0 + c0,
+                                  static_cast<int>(grow0) + p.diag_offset, col0 + c0, lane);
+      // all transform warps' stores -> one gpu-scope release per CTA (the consumers read the scratch through TMA)
+      fence_proxy_async_all();
+      asm volatile("bar.sync 1, %0;" ::"n"((kTW > 0 ? kTW : 1) * 32) : "memory");
+      if (tw == 0 && lane == 0) {
+        __threadfence();
         fence_proxy_async_all();
-        asm volatile("bar.sync 1, %0;" ::"n"((kTW > 0 ? kTW : 1) * 32) : "memory");
-        if (tw == 0 && lane == 0) {
-          __threadfence();
-          fence_proxy_async_all();
-          if constexpr (kPanel) {
-            red_release_gpu_add(p.doneArow + it.blk * p.tAm + it.tm, 1u);
-            red_release_gpu_add(p.doneAcol + it.blk * p.tAn + it.tn, 1u);
-          } else {
-            red_release_gpu_add(p.doneA + it.blk, 1u);
-          }
-          if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, it.type, it.blk, it.tm, it.tn);
-        }
-      } else {
-        // one gpu-scope release per CTA and tile, as above, but for the PREVIOUS tile and issued once this tile's first
-        // loads are in flight.  Safe across the doneB wait above: that wait is for block blk - nbuf (nbuf >= 3), whose
-        // slices only need coefficient blocks older than the pending tile's.
-        auto publish = [&](int blk, int ptm, int ptn) {
-          fence_proxy_async_all();
-          asm volatile("bar.sync 1, %0;" ::"n"((kTW > 0 ? kTW : 1) * 32) : "memory");
-          if (tw == 0 && lane == 0) {
-            __threadfence();
-            fence_proxy_async_all();
-            if constexpr (kPanel) {
-              red_release_gpu_add(p.doneArow + blk * p.tAm + ptm, 1u);
-              red_release_gpu_add(p.doneAcol + blk * p.tAn + ptn, 1u);
-            } else {
-              red_release_gpu_add(p.doneA + blk, 1u);
-            }
-            if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, 0, blk, ptm, ptn);
-          }
-        };
-        stored_e_rows_hook<kRowsPerWarp>(
-            p, static_cast<const uint8_t*>(p.E) + (grow0 * p.ldE + col0 + c0) * 2, p.ldE * 2,
-            g_base + ((static_cast<long long>(buf) * p.Rb + r0) * p.Cb + c0) * 2, static_cast<long long>(p.Cb) * 2,
-            p.rinv + grow0, p.cinv + col0 + c0, static_cast<int>(grow0) + p.diag_offset, col0 + c0, lane, [&]() {
-              if (pend_blk >= 0) publish(pend_blk, pend_tm, pend_tn);
-            });
-        pend_blk = it.blk; pend_tm = it.tm; pend_tn = it.tn;
-        if (!cur_has_more_a(cur, p)) {  // last coefficient tile of this CTA pair: nothing left to hide behind
-          publish(pend_blk, pend_tm, pend_tn);
-          pend_blk = -1;
-        }
+        red_release_gpu_add(p.doneA + it.blk, 1u);
+        if constexpr (kTrace) trace_event(p.trace, 3, ntr, 2, it.type, it.blk, it.tm, it.tn);
       }
     }
   }

@@ -421,11 +421,13 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   if ((size_t)((long long)Rb * ldg * esz) > workspace_bytes)
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd: workspace too small (%zu bytes)", workspace_bytes);
 
-  // measurement hook (bench.py's per-kernel roofline): MMG_BWD_PHASES=1 runs only the coefficient launches, =2 only
-  // the gradient-GEMM launches (on whatever the scratch holds); unset / 3 = the real thing
   int phases = 3;
+#ifdef MMG_MEASURE
+  // measurement builds only (tests/gpu_epi_probe.py): MMG_BWD_PHASES=1 runs only the coefficient launches, =2 only the
+  // gradient-GEMM launches (on whatever the scratch holds -- wrong results); unset / 3 = the real thing
   if (const char* e = getenv("MMG_BWD_PHASES")) phases = atoi(e);
   if (phases < 1 || phases > 3) phases = 3;
+#endif
 
   // One persistent launch for the whole backward when the shape allows it (bwd_fused.cuh); explicit block shapes and
   // the phase hook select the block loop below.
@@ -502,6 +504,8 @@ int mmg_debug_fused_trace_region(int rows, int cols, int D, size_t* offset, size
   if (offset == nullptr || bytes == nullptr || records_per_role == nullptr || roles == nullptr) return 0;
   return tc_fused_trace_region(rows, cols, D, offset, bytes, records_per_role, roles);
 }
+
+int mmg_tune(const char* key, int value) { return tc_tune(key, value); }
 
 int mmg_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
                            int max_items, int* info) {
@@ -589,12 +593,18 @@ int mmg_zeroshot_score(const float* img, const float* txt, int N, int C, int D, 
                        float* probs_out, long long* argmax_out, int k, long long* topk_idx_out, float* topk_val_out,
                        mmg_stream_t stream) {
   if (N < 0 || C <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score: bad shape %dx%dx%d", N, C, D);
-  if (C > 64) return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "mmg_zeroshot_score: at most 64 prompts (got %d)", C);
   if (k < 0 || k > 8 || k > C) return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score: need 0 <= k <= min(8, C)");
   if (N == 0) return 0;
   MMG_REQ(img);
   MMG_REQ(txt);
   MMG_REQ(scale);
+  if (C > 64) {
+    // more prompts than the tiled kernels take: one-warp-per-row kernel, which parks the row's logits in logits_out
+    if (logits_out == nullptr)
+      return set_error(MMG_ERR_BAD_ARG, "mmg_zeroshot_score: logits_out is required for more than 64 prompts (got %d)", C);
+    return simt_zeroshot_wide(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k, topk_idx_out, topk_val_out,
+                              static_cast<cudaStream_t>(stream));
+  }
   return simt_zeroshot(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k, topk_idx_out, topk_val_out,
                        static_cast<cudaStream_t>(stream));
 }

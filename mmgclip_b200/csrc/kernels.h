@@ -64,6 +64,7 @@ int tc_zeroshot(const float* img, const float* txt, int N, int C, int D, const f
                 float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
 
+int tc_tune(const char* key, int value);
 int tc_fused_bwd_schedule(int rows, int cols, int D, int n_owners, int n_parts, int part, int pairs, int pair, int* items,
                           int max_items, int* info);
 
@@ -115,6 +116,9 @@ int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long
                 float* loss_out, cudaStream_t st);
 int simt_ce_bwd(const float* logits, long long ld, int n, int m, const long long* labels, const float* lse,
                 const float* grad_loss, float coef, float* dlogits, long long ldd, cudaStream_t st);
+int simt_zeroshot_wide(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits,
+                       float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
+                       cudaStream_t st);
 int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits_out,
                   float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
                   cudaStream_t st);

@@ -570,21 +570,30 @@ int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0,
 // =====================================================================================================
 // loss finalisation (single block, fixed-order tree => deterministic)
 // =====================================================================================================
+// Guard of the fixed softmax shift m = s (E = exp(logit - s), valid for unit-norm inputs and moderate s): a row or column
+// whose terms ALL underflowed (sum == 0: s * (1 - max cos) > ~87) or overflowed (un-normalised inputs) cannot be
+// normalised; instead of letting log(0) / coef/0 leak inf into the loss and the gradients silently, the loss is set to NaN
+// here (the reference's per-row-max cross-entropy would still be finite -- mmgclip_b200.ops.info_nce documents the range
+// and the materialised fallback).
 __global__ void __launch_bounds__(1024)
 infonce_loss_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum, const float* __restrict__ diag,
                     int n, const float* __restrict__ scale, float inv_two_b, float* __restrict__ loss_out) {
   __shared__ double part[1024];
   const float s = *scale;
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024)
-    acc += (double)(logf(rowsum[i]) + s - diag[i]) + (double)(logf(colsum[i]) + s - diag[i]);
+  int bad = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float rs = rowsum[i], cs = colsum[i];
+    bad |= !(rs > 0.f && rs < INFINITY) || !(cs > 0.f && cs < INFINITY);
+    acc += (double)(logf(rs) + s - diag[i]) + (double)(logf(cs) + s - diag[i]);
+  }
   part[threadIdx.x] = acc;
-  __syncthreads();
+  bad = __syncthreads_or(bad);
   for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) loss_out[0] = (float)(part[0] * (double)inv_two_b);
+  if (threadIdx.x == 0) loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)(part[0] * (double)inv_two_b);
 }
 
 int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
@@ -642,7 +651,8 @@ ce_fwd_kernel(const float* __restrict__ logits, long long ld, int n, int m, cons
     if (lane == 0) {
       lse[r] = l;
       const long long lab = labels ? labels[r] : r;
-      term = l - lr[lab];
+      // an out-of-range class index (torch raises a device-side assert) poisons the loss instead of reading out of bounds
+      term = (lab >= 0 && lab < m) ? l - lr[lab] : __int_as_float(0x7fc00000);
     }
   }
   __shared__ float wsum[8];
@@ -917,6 +927,83 @@ int simt_zeroshot(const float* img, const float* txt, int N, int C, int D, const
   zeroshot_kernel<<<(N + 63) / 64, 256, 0, st>>>(img, txt, N, C, D, scale, logits_out, probs_out, argmax_out, k,
                                                  topk_idx, topk_val);
   MMG_LAUNCH_CHECK("zeroshot_kernel");
+  return 0;
+}
+
+// Any number of prompts (the tiled kernels above and in zeroshot_tc.cu stop at 64, PromptClassifier has no such limit):
+// one warp per image row.  The scaled row sits in shared memory; lanes stride over the prompts' elements (coalesced,
+// the prompt matrix stays in L1/L2), shuffle-reduce each logit, park the row's logits in global memory (logits_out or a
+// caller-provided scratch row block) and finish softmax / argmax-of-probabilities / top-k from there with the same tie
+// rules.  A fallback for rare shapes, not a tuned kernel.
+__global__ void __launch_bounds__(256)
+zeroshot_wide_kernel(const float* __restrict__ img, const float* __restrict__ txt, int N, int C, int D,
+                     const float* __restrict__ scale, float* __restrict__ logits, float* __restrict__ probs_out,
+                     long long* __restrict__ argmax_out, int k, long long* __restrict__ topk_idx,
+                     float* __restrict__ topk_val) {
+  extern __shared__ float rowbuf[];  // 8 warps x D
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gm = (long long)blockIdx.x * 8 + warp;
+  if (gm >= N) return;
+  const float s = *scale;
+  float* a = rowbuf + warp * D;
+  for (int i = lane; i < D; i += 32) a[i] = s * img[gm * D + i];  // (logit_scale * image_embeddings) first
+  __syncwarp();
+  float* lr = logits + gm * C;
+  for (int c = 0; c < C; ++c) {
+    const float* b = txt + (long long)c * D;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) acc = fmaf(a[i], b[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) lr[c] = acc;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
+  mx = warp_max(mx);
+  float den = 0.f;
+  for (int c = lane; c < C; c += 32) den += expf(lr[c] - mx);
+  den = warp_sum(den);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float p = expf(lr[c] - mx) / den;
+    if (probs_out != nullptr) probs_out[gm * C + c] = p;
+    if (p > bv) { bv = p; bi = c; }  // ascending c per lane: the first occurrence wins
+  }
+  warp_argmax(bv, bi);
+  if (lane == 0 && argmax_out != nullptr) argmax_out[gm] = bi;
+  if (k > 0 && topk_idx != nullptr) {
+    // k selection passes over the logits (value desc, index asc); already-taken indices are skipped by comparing with
+    // the previous winner in (value, index) order
+    float pv = INFINITY;
+    int pi = -1;
+    for (int j = 0; j < k; ++j) {
+      float v = -INFINITY;
+      int vi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        const float x = lr[c];
+        const bool after_prev = (x < pv) || (x == pv && c > pi);
+        if (after_prev && (x > v || (x == v && c < vi))) { v = x; vi = c; }
+      }
+      warp_argmax(v, vi);
+      if (lane == 0) {
+        topk_idx[gm * k + j] = vi;
+        if (topk_val != nullptr) topk_val[gm * k + j] = v;
+      }
+      pv = v; pi = vi;
+    }
+  }
+}
+
+int simt_zeroshot_wide(const float* img, const float* txt, int N, int C, int D, const float* scale, float* logits,
+                       float* probs_out, long long* argmax_out, int k, long long* topk_idx, float* topk_val,
+                       cudaStream_t st) {
+  if (N <= 0) return 0;
+  const size_t smem = (size_t)8 * D * sizeof(float);
+  if (smem > 48 * 1024) return set_error(-3, "zeroshot (wide): D = %d exceeds 1536", D);
+  zeroshot_wide_kernel<<<(N + 7) / 8, 256, smem, st>>>(img, txt, N, C, D, scale, logits, probs_out, argmax_out, k,
+                                                       topk_idx, topk_val);
+  MMG_LAUNCH_CHECK("zeroshot_wide_kernel");
   return 0;
 }
 

@@ -65,13 +65,22 @@ static int make_out_tmap_f32(CUtensorMap* m, const float* ptr, long long cols, l
   if (r != CUDA_SUCCESS) return set_error(-4, "cuTensorMapEncodeTiled (fp32 output) failed (CUresult %d)", (int)r);
   return 0;
 }
+// Measured-and-rejected alternatives of the mainloop (A/B switches) only exist in measurement builds (make measure,
+// -DMMG_MEASURE): MMG_TC_TMA_OUT=0 (direct stores instead of TMA stores), MMG_TC_DUAL_SPLIT=1, MMG_TC_PAIR=0 (single-CTA
+// tiles), MMG_TC_TAIL=1 (tail balancing), MMG_TC_PREFETCH=n (L2 prefetch distance).  The product library is compiled with
+// the defaults as constants and reads no environment variable.
+static int measure_env(const char* name, int dflt) {
+#ifdef MMG_MEASURE
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
 static bool out_tma_ok(const float* C, long long ldc) {
-  static int en = -1;
-  if (en < 0) {
-    const char* e = getenv("MMG_TC_TMA_OUT");
-    en = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return en == 1 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc & 3) == 0;
+  static const int en = measure_env("MMG_TC_TMA_OUT", 1);
+  return en != 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc & 3) == 0;
 }
 
 // operand with `rows` along M/N and `K` along the contraction
@@ -122,11 +131,7 @@ static GemmProblem empty_problem() {
 static bool tail_balance_enabled();
 static int prefetch_distance();
 static bool dual_split_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMG_TC_DUAL_SPLIT");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower at 8192^2 blocks (1.84 vs 1.75 ms): opt-in
-  }
+  static const int v = measure_env("MMG_TC_DUAL_SPLIT", 0);  // measured slower at 8192^2 blocks (1.84 vs 1.75 ms)
   return v == 1;
 }
 
@@ -192,31 +197,17 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
 }
 
 // Tile shape: 256-row CTA pairs (cta_group::2) when both extents fill them, else single-CTA 128 x {256,128} tiles.
-// MMG_TC_PAIR=0 in the environment forces single-CTA tiles (debugging / A-B measurements).
 static bool pair_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMG_TC_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
+  static const int v = measure_env("MMG_TC_PAIR", 1);
+  return v != 0;
 }
 static bool tail_balance_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMG_TC_TAIL");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower (scalar atomics in the tail): opt-in
-  }
+  static const int v = measure_env("MMG_TC_TAIL", 0);  // measured slower (scalar atomics in the tail)
   return v == 1;
 }
 static int prefetch_distance() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MMG_TC_PREFETCH");
-    v = e != nullptr ? atoi(e) : 0;  // measured slower than no prefetch on B200: opt-in
-    if (v < 0) v = 0;
-  }
-  return v;
+  static const int v = measure_env("MMG_TC_PREFETCH", 0);  // measured slower than no prefetch on B200
+  return v < 0 ? 0 : v;
 }
 // The InfoNCE epilogues run on 8 epilogue warps.  A 16-warp variant (4 column groups, setmaxnreg re-balancing) was
 // measured slower on B200 at 32768^2 x 512 (forward 0.754 vs 0.723 ms, coefficient launches 1.095 vs 1.019 ms): the
@@ -376,8 +367,7 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   // output map: g block [rb, cb] bf16 (pitch ldg), box = 32 rows x 64 columns (one epilogue warp's block)
   CUtensorMap mc;
   if ((rc = make_tmap(&mc, G, cb, rb, ldg, 32)) != 0) return rc;
-  int dbg = 0;  // measurement hook (tests/gpu_epi_probe.py): results are wrong when set
-  if (const char* d = getenv("MMG_EPI_DBG")) dbg = atoi(d);
+  const int dbg = measure_env("MMG_EPI_DBG", 0);  // measurement builds only (tests/gpu_epi_probe.py): wrong results when set
   EpiGrad::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
   e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
@@ -388,9 +378,40 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
 // ---------------------------------------------------------------------------------------------------------
 // fused persistent backward (bwd_fused.cuh)
 // ---------------------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e != nullptr ? atoi(e) : dflt;
+// Plan knobs of the fused backward (fused on/off, block shape, scratch buffers, slice lengths, block order): process-wide
+// overrides set through mmg_tune() -- the tests walk other schedules with it; unset = the measured defaults.  Every value
+// gives correct results.  Measurement builds also honour the MMG_* environment variables of the same names.
+enum TuneKey { kTuneFused, kTuneRb, kTuneCb, kTuneNbuf, kTuneKsl, kTuneKslT, kTuneSr, kTuneSc, kTuneCount };
+static const char* const kTuneNames[kTuneCount] = {"fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl",
+                                                   "fused_ksl_t", "fused_sr", "fused_sc"};
+static const char* const kTuneEnv[kTuneCount] = {"MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF",
+                                                 "MMG_FUSED_KSL", "MMG_FUSED_KSL_T", "MMG_FUSED_SR", "MMG_FUSED_SC"};
+static std::mutex g_tune_mu;
+static int g_tune[kTuneCount] = {-1, -1, -1, -1, -1, -1, -1, -1};  // -1 = unset
+
+int tc_tune(const char* key, int value) {
+  if (key == nullptr) return set_error(-1, "mmg_tune: key is NULL");
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  if (strcmp(key, "reset") == 0) {
+    for (int i = 0; i < kTuneCount; ++i) g_tune[i] = -1;
+    return 0;
+  }
+  for (int i = 0; i < kTuneCount; ++i)
+    if (strcmp(key, kTuneNames[i]) == 0) {
+      g_tune[i] = value < 0 ? -1 : value;
+      return 0;
+    }
+  return set_error(-1, "mmg_tune: unknown key '%s'", key);
+}
+
+static int tune_int(TuneKey k, int dflt) {
+  int v;
+  {
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    v = g_tune[k];
+  }
+  if (v >= 0) return v;
+  return measure_env(kTuneEnv[k], dflt);
 }
 
 struct FusedPlan {
@@ -408,9 +429,9 @@ static int largest_divisor(int n, int cap) {
 static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0, bool remote_owners = false) {
   FusedPlan f;
   memset(&f, 0, sizeof(f));
-  if (env_int("MMG_BWD_FUSED", 1) == 0) return f;
+  if (tune_int(kTuneFused, 1) == 0) return f;
   if (rows < 256 || cols < 256 || D < 256 || (D % 256) != 0) return f;
-  int Rb = env_int("MMG_FUSED_RB", 0), Cb = env_int("MMG_FUSED_CB", 0);
+  int Rb = tune_int(kTuneRb, 0), Cb = tune_int(kTuneCb, 0);
   if (Rb <= 0) Rb = largest_divisor(rows, 4096);
   // col_unit > 0: column blocks must also divide col_unit (the columns of one part of one owner)
   if (Cb <= 0) Cb = largest_divisor(col_unit > 0 ? col_unit : cols, 2048);
@@ -419,20 +440,20 @@ static FusedPlan fused_plan(int rows, int cols, int D, int col_unit = 0, bool re
   // K blocks (of 64) per gradient slice: every slice ends in a 256 x 256 fp32 reduce-add at L2, so slices are long
   // (Remote owners -- the column-side gradient goes to other GPUs over NVLink -- take whole-K dB slices: every element
   // then crosses the link once per row block instead of once per slice; 8 x B200: 0.775 vs 0.945 ms per step.)
-  int kslI = env_int("MMG_FUSED_KSL", 32);
-  int kslT = env_int("MMG_FUSED_KSL_T", remote_owners ? Rb / kBK : env_int("MMG_FUSED_KSL", 32));
+  int kslI = tune_int(kTuneKsl, 32);
+  int kslT = tune_int(kTuneKslT, remote_owners ? Rb / kBK : kslI);
   while (kslI > 1 && ((Cb / kBK) % kslI) != 0) kslI >>= 1;
   while (kslT > 1 && ((Rb / kBK) % kslT) != 0) kslT >>= 1;
   if (kslI < 1 || kslT < 1) return f;
-  int nbuf = env_int("MMG_FUSED_NBUF", 4);
+  int nbuf = tune_int(kTuneNbuf, 4);
   if (nbuf < 3) nbuf = 3;
   const int nblk = (rows / Rb) * (cols / Cb);
   if (nbuf > nblk) nbuf = nblk < 1 ? 1 : nblk;
   f.Rb = Rb; f.Cb = Cb; f.nbuf = nbuf; f.kslI = kslI; f.kslT = kslT;
   f.g_bytes = ((size_t)nbuf * Rb * Cb * 2 + 255) / 256 * 256;
-  // counters: doneA[nblk], doneB[nblk], then the per-panel counters doneArow[nblk * Rb/256], doneAcol[nblk * Cb/256]
-  f.total_bytes = f.g_bytes + (size_t)nblk * (2 + Rb / 256 + Cb / 256) * sizeof(unsigned int) + 256;
-  if (env_int("MMG_FUSED_TRACE", 0) != 0) {
+  // counters: doneA[nblk], doneB[nblk]
+  f.total_bytes = f.g_bytes + (size_t)nblk * 2 * sizeof(unsigned int) + 256;
+  if (measure_env("MMG_FUSED_TRACE", 0) != 0) {
     f.trace_off = (f.total_bytes + 255) / 256 * 256;
     f.trace_bytes = (size_t)sm_count() * kTraceRoles * kTraceCap * 16;
     f.total_bytes = f.trace_off + f.trace_bytes;
@@ -470,9 +491,9 @@ static void fill_schedule(BwdFusedParams* pp, const FusedPlan& f, int rows, int 
   p.part_row0 = part * p.blocks_per_part * f.Cb;
   if (p.nbuf > p.nblk) p.nbuf = p.nblk < 1 ? 1 : p.nblk;
   // super-tile of the block order (BwdFusedParams::block_rc).  Default 1 x 1 = row-major: at 32768^2 x 512 super-tiles
-  // of 2x2 .. 4x4 blocks measured the same or slightly slower (2.52 -> 2.54 ms; stored-E 2.16 -> 2.20 ms) -- the launch is
-  // bound by the block-level doneA / doneB dependencies, not by L2 capacity.  MMG_FUSED_SR / MMG_FUSED_SC select others.
-  int sr = env_int("MMG_FUSED_SR", 1), sc = env_int("MMG_FUSED_SC", 1);
+  // of 2x2 .. 4x4 blocks measured the same or slightly slower (2.52 -> 2.54 ms; stored-E 2.16 -> 2.20 ms).  mmg_tune
+  // "fused_sr" / "fused_sc" select others.
+  int sr = tune_int(kTuneSr, 1), sc = tune_int(kTuneSc, 1);
   const int nbr = rows / f.Rb;
   if (sr <= 0) sr = 1;
   if (sc <= 0) sc = 1;
@@ -563,8 +584,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   for (int i = 0; i < n_owners; ++i)
     if (dB_owners[i] == nullptr || !out_tma_ok(dB_owners[i], D)) return 0;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return 0;
-  int BN = env_int("MMG_FUSED_BN", 256) == 128 ? 128 : 256;  // accumulator tile width: 256 -> 2 stages, 128 -> 4
-  if (e_stored != nullptr) BN = 256;
+  constexpr int BN = 256;  // accumulator tile width (two TMEM stages)
   BwdFusedParams p;
   fill_schedule(&p, f, rows, cols, D, n_owners, n_parts, part, BN);
   p.E = e_stored; p.ldE = lde; p.G = workspace;
@@ -579,11 +599,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   unsigned int* ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + f.g_bytes);
   p.doneA = ctr;
   p.doneB = ctr + p.nblk;
-  // per-panel dependencies (kPanel kernels): 256-column tiles only
-  const bool panel = BN == 256 && env_int("MMG_FUSED_PANEL", 0) != 0;
-  p.doneArow = panel ? ctr + 2 * p.nblk : nullptr;
-  p.doneAcol = panel ? ctr + 2 * p.nblk + p.nblk * p.tAm : nullptr;
-  cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)p.nblk * (2 + (panel ? p.tAm + p.tAn : 0)) * sizeof(unsigned int), st);
+  cudaError_t e = cudaMemsetAsync(ctr, 0, (size_t)p.nblk * 2 * sizeof(unsigned int), st);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(fused backward counters)");
 
   CUtensorMap mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA;
@@ -604,52 +620,22 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   }
 
   constexpr int kStoredTW = 8;  // transform warps of the stored-E kernel
-  int ew = env_int("MMG_FUSED_EPI_WARPS", 8) == 16 ? 16 : 8;
-  if (e_stored != nullptr) ew = 8;
-  const int variant = e_stored != nullptr ? 4 : (BN == 128 ? 1 : 0) + (ew == 16 ? 2 : 0);
+  constexpr int ew = 8;         // epilogue warps
+  const bool stored = e_stored != nullptr;
   auto kern = infonce_bwd_fused_kernel<256, 8, 0>;
-  int smem_bytes = FusedSmemT<256, 8>::kTotal;
-  if (variant == 1) { kern = infonce_bwd_fused_kernel<128, 8, 0>; smem_bytes = FusedSmemT<128, 8>::kTotal; }
-  if (variant == 2) { kern = infonce_bwd_fused_kernel<256, 16, 0>; smem_bytes = FusedSmemT<256, 16>::kTotal; }
-  if (variant == 3) { kern = infonce_bwd_fused_kernel<128, 16, 0>; smem_bytes = FusedSmemT<128, 16>::kTotal; }
-  if (variant == 4) { kern = infonce_bwd_fused_kernel<256, 8, kStoredTW>; smem_bytes = FusedSmemT<256, 8>::kTotal; }
-  // MMG_STORED_TW=16: sixteen transform warps (8 rows each, twice the E bytes in flight per SM; 896 threads -> 72 registers
-  // per thread).  Compiles without spills; not yet measured -- opt-in.
-  int stored_tw = kStoredTW;
-  if (variant == 4 && env_int("MMG_STORED_TW", kStoredTW) == 16) {
-    kern = infonce_bwd_fused_kernel<256, 8, 16>;
-    stored_tw = 16;
+  if (stored) kern = infonce_bwd_fused_kernel<256, 8, kStoredTW>;
+  const int smem_bytes = FusedSmemT<256, 8>::kTotal;
+  int slot = stored ? 1 : 0;
+#ifdef MMG_MEASURE
+  if (p.trace != nullptr) {  // debug timeline: separate instantiations
+    if (stored) kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, true>;
+    else kern = infonce_bwd_fused_kernel<256, 8, 0, true>;
+    slot += 2;
   }
-  int slot = variant;
-  if (p.trace != nullptr && (variant == 0 || variant == 4)) {  // debug timeline: separate instantiations
-    if (variant == 0) kern = infonce_bwd_fused_kernel<256, 8, 0, true>;
-    else kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, true>;
-    slot = variant == 0 ? 5 : 6;
-    stored_tw = kStoredTW;
-  } else {
-    p.trace = nullptr;
-  }
-  if (variant == 4 && stored_tw == 16) slot = 7;
-  // MMG_STORED_DEFER=1: deferred publish of the stored-E coefficient tiles (kDefer in bwd_fused.cuh) -- compiled, covered
-  // at schedule level on the CPU, NOT yet run on a GPU; opt-in for the next measurement session
-  if (variant == 4 && slot == 4 && p.nbuf >= 3 && env_int("MMG_STORED_DEFER", 0) != 0) {
-    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, true>;
-    slot = 8;
-  }
-  // MMG_FUSED_PANEL=1: per-panel doneA dependencies (kPanel) -- same status as MMG_STORED_DEFER
-  if (panel && slot == 0 && ew == 8) {
-    kern = infonce_bwd_fused_kernel<256, 8, 0, false, false, true>;
-    slot = 9;
-  } else if (panel && slot == 4) {
-    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, false, true>;
-    slot = 10;
-  } else if (panel && slot == 8) {
-    kern = infonce_bwd_fused_kernel<256, 8, kStoredTW, false, true, true>;
-    slot = 11;
-  } else {
-    p.doneArow = p.doneAcol = nullptr;
-  }
-  static bool configured[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+#else
+  p.trace = nullptr;
+#endif
+  static bool configured[4] = {false, false, false, false};
   if (!configured[slot]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(infonce_bwd_fused_kernel)");
@@ -659,7 +645,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pairs * 2);
-  cfg.blockDim = dim3(32 * (4 + ew + (variant == 4 ? stored_tw : 0)));
+  cfg.blockDim = dim3(32 * (4 + ew + (stored ? kStoredTW : 0)));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -415,8 +415,10 @@ size_t tc_zeroshot_workspace_bytes(int C, int D) {
 }
 
 bool tc_zeroshot_supported(const float* img, int N, int C, int D) {
+#ifdef MMG_MEASURE
   if (const char* e = getenv("MMG_ZEROSHOT_TC"))
     if (e[0] == '0') return false;
+#endif
   return N >= 1 && C >= 1 && C <= kZsC && D >= 4 && (D % 4) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0;
 }
 
@@ -457,8 +459,11 @@ int tc_zeroshot(const float* img, const float* txt, int N, int C, int D, const f
   }
   const int ntiles = (N + kZsRows - 1) / kZsRows;
   const int grid = ntiles < sms ? ntiles : sms;
-  int flags = 0;  // measurement hook: bit 0 = write the truncated hi term back explicitly
+  int flags = 0;
+#ifdef MMG_MEASURE
+  // measurement builds only: bit 0 = write the truncated hi term back explicitly
   if (const char* f = getenv("MMG_ZEROSHOT_FLAGS")) flags = atoi(f);
+#endif
   zeroshot_tc_kernel<<<grid, kZsThreads, kZsSmem, st>>>(mImg, mThi, mTlo, N, C, D, flags, logits_out, probs_out,
                                                         argmax_out, k, topk_idx, topk_val);
   e = cudaGetLastError();

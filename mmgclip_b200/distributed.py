@@ -186,7 +186,7 @@ def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] 
 
 class _ShardedInfoNCEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None, pending=None):
+    def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None, pending=None, b_key=None):
         ctx.pending = pending
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
@@ -196,8 +196,9 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         B = bl * world
         s = scale.detach().reshape(()).to(device=a_local.device, dtype=torch.float32).contiguous()
         a_op = kernels.operand(a_local, prec)
-        if gathered is not None and gathered.local is b_local:
+        if gathered is not None and (gathered.local is b_local or gathered.local is b_key):
             b_all = gathered.wait()
+            ops.mark("gather_wait")
         else:
             b_op = kernels.operand(b_local, prec)
             b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
@@ -216,7 +217,9 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if cvec is not None:
             cvec.buf.zero_()  # the partial column sums accumulate straight into the symmetric buffer
             rowsum, _, diag = kernels.forward(a_op, b_all, s, off, prec, colsum=cvec.buf[:B], **fwd_kw)
+            ops.mark("lse_fwd")
             colsum = cvec.all_reduce()[:B]
+            ops.mark("colsum_ar")
         else:
             rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec, **fwd_kw)
             dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
@@ -225,6 +228,7 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if lvec is not None:
             lvec.buf[:1].copy_(loss.reshape(1))
             loss = lvec.all_reduce()[0]
+            ops.mark("loss_ar")
         else:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
@@ -251,19 +255,20 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
                                                         e_stored=ctx.e_mat)
             ctx.e_mat = None
             dB = owns[0].clone()  # the symmetric buffer is reused by the next step
+            ops.mark("clone")
             dscale = None
             if ctx.needs_input_grad[2]:
                 dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
                 dscale = (dls / s).reshape(ctx.scale_shape)
-            return dA, dB, dscale, None, None, None, None, None
+            return dA, dB, dscale, None, None, None, None, None, None
         dA, dB_all, dls = kernels.backward(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off, prec, a32,
                                            b32_local, diag, need_dscale=ctx.needs_input_grad[2])
         dB = torch.empty((bl, D), dtype=dB_all.dtype, device=dB_all.device)
         pending = ctx.pending
         if pending is not None and pending.get("deferred") and dist.get_backend(group) != "gloo":
             # The column-side gradients travel while the caller's row-side (image head) backward runs: the current
-            # stream only waits for the reduce-scatter in the hook sharded_info_nce() put on b_local, i.e. right before
-            # the column side's producer runs its backward.
+            # stream only waits for the reduce-scatter in the backward of the identity node sharded_info_nce() put in
+            # front of b_local (_AwaitColumnGrad), i.e. before the gradient meets any other consumer's.
             pending["work"] = dist.reduce_scatter_tensor(dB, dB_all, op=dist.ReduceOp.SUM, group=group, async_op=True)
             pending["keep"] = dB_all  # stays referenced until the wait
         else:
@@ -272,7 +277,7 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
             dscale = (dls / s).reshape(ctx.scale_shape)
-        return dA, dB, dscale, None, None, None, None, None
+        return dA, dB, dscale, None, None, None, None, None, None
 
 
 def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, group=None, prec: Optional[str] = None,
@@ -285,19 +290,36 @@ def sharded_info_nce(a_local: torch.Tensor, b_local: torch.Tensor, logit_scale, 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return ops.info_nce(a_local, b_local, logit_scale, prec=prec)
     pending = {}
+    b_in = b_local
     if torch.is_grad_enabled() and b_local.requires_grad:
-        # tensor hooks run right before b_local's producer executes its backward (or before .grad accumulation for a
-        # leaf): that is where the asynchronous reduce-scatter of the column-side gradients is waited for
-        def _wait(grad, _pending=pending):
-            work = _pending.pop("work", None)
-            if work is not None:
-                work.wait()  # stream-ordered, no host sync
-            _pending.pop("keep", None)
-            return grad
-
-        b_local.register_hook(_wait)
+        # The NCCL-fallback backward returns dB while its asynchronous reduce-scatter is still in flight.  b_local is
+        # routed through a private identity node so that this gradient has exactly ONE producer and the wait happens in
+        # that node's backward -- i.e. before autograd can add it to the gradients b_local receives from other consumers
+        # (MMGCLIPLoss uses the text embeddings as the column side of two losses).
+        b_in = _AwaitColumnGrad.apply(b_local, pending)
+        bf = getattr(b_local, "_mmg_bf16", None)
+        if bf is not None:
+            b_in._mmg_bf16 = bf  # keep the bf16 operand copy the normalise kernel attached
         pending["deferred"] = True
-    return _ShardedInfoNCEFn.apply(a_local, b_local, logit_scale, group, prec, _kernels, gathered, pending)
+    return _ShardedInfoNCEFn.apply(a_local, b_in, logit_scale, group, prec, _kernels, gathered, pending, b_local)
+
+
+class _AwaitColumnGrad(torch.autograd.Function):
+    """Identity on the column-side embeddings; its backward makes the current stream wait for the asynchronous
+    reduce-scatter that fills the incoming gradient (stream-ordered, no host sync)."""
+
+    @staticmethod
+    def forward(ctx, b_local, pending):
+        ctx.pending = pending
+        return b_local.view_as(b_local)
+
+    @staticmethod
+    def backward(ctx, grad):
+        work = ctx.pending.pop("work", None)
+        if work is not None:
+            work.wait()
+        ctx.pending.pop("keep", None)
+        return grad, None
 
 
 def allreduce_gradients(*modules: torch.nn.Module, group=None) -> None:

@@ -68,9 +68,10 @@ class AveragedMedicalCLIPLoss(nn.Module):
     the column averaging and the cross-entropies are kernels.
     """
 
-    def __init__(self, similarity_threshold=0.65):
+    def __init__(self, similarity_threshold=0.65, precision=None):
         super().__init__()
         self.similarity_threshold = similarity_threshold
+        self.precision = precision
 
     def _mesaure_embeddings_similarity(self, embeddings):
         unit = ops.l2_normalize(embeddings.detach().to(torch.float32), prec="fp32")
@@ -103,7 +104,12 @@ class AveragedMedicalCLIPLoss(nn.Module):
             w[lab, c] = 1.0 / counts[lab]
         return ops.linear(logits.to(torch.float32), w.to(logits.device), None, prec="fp32")
 
-    def forward(self, image_embeddings, text_embeddings, logit_scale, logits_per_image, logits_per_text):
+    def forward(self, image_embeddings, text_embeddings, logit_scale, logits_per_image=None, logits_per_text=None,
+                **kwargs):
+        if logits_per_image is None:  # a caller that skipped the materialisation (mmgclip_model.py:135-136)
+            logits_per_image = ops.similarity_logits(image_embeddings, text_embeddings, logit_scale, prec=self.precision)
+        if logits_per_text is None:
+            logits_per_text = ops.similarity_logits(text_embeddings, image_embeddings, logit_scale, prec=self.precision)
         sim = self._mesaure_embeddings_similarity(text_embeddings)
         list_labels = self._assign_labels(sim, threshold=self.similarity_threshold)
         averaged = self._average_logits(logits=logits_per_image, list_labels=list_labels)

@@ -47,8 +47,9 @@ class MMGCLIP(nn.Module):
         (default) reproduces that: a constant tensor, absent from ``parameters()``/``state_dict()``.  ``True`` registers
         it (what the reference does on CPU).  ``load_state_dict`` accepts checkpoints of either flavour.
       * ``logits_per_image`` / ``logits_per_text`` are materialised when they are cheap or needed (evaluation,
-        ``validation=True``, n != m, or n*m <= ``materialize_logits_below``); for large paired training batches they are
-        ``None`` and the fused losses consume the embeddings instead -- the B x B matrix is never built.
+        ``validation=True``, n != m, n*m <= ``materialize_logits_below``, or a configured loss other than ``CLIPLoss`` /
+        ``MMGCLIPLoss``); for large paired training batches under the fused losses they are ``None`` and the loss
+        consumes the embeddings instead -- the B x B matrix is never built.
     """
 
     def __init__(self, config=None, text_encoder: Optional[nn.Module] = None, image_encoder: Optional[nn.Module] = None,
@@ -143,7 +144,11 @@ class MMGCLIP(nn.Module):
 
         n, m = image_embeddings.shape[0], text_embeddings.shape[0]
         validation = kwargs.get('validation', False) is True
-        materialise = (not self.training) or validation or n != m or n * m <= self.materialize_logits_below
+        # only the fused losses can do without the [n, m] logits; any other criterion (AveragedMedicalCLIPLoss, a caller's
+        # own) reads them, as does reference-side code that looks at outputs['logits_per_image'] in the train loop
+        fused_loss = _cfg(self.config, "loss.config.loss_name") in ("CLIPLoss", "MMGCLIPLoss")
+        materialise = ((not self.training) or validation or n != m or n * m <= self.materialize_logits_below
+                       or not fused_loss)
         logits_per_image = logits_per_text = None
         if materialise:
             logits_per_image = ops.similarity_logits(image_embeddings, text_embeddings, logit_scale, prec=self.precision)
@@ -202,7 +207,11 @@ class PromptClassifier(nn.Module):
             "class_list": class_list,
         }
         if visualize:
+            # the reference's default (mmgclip_model.py:188,213-247) draws a matplotlib bar chart; plotting is outside the
+            # accelerated path, so the call keeps its signature and its assertion, returns the same dict and says so
             assert image_id is not None, "For visualizing results, image_id value is required."
-            raise NotImplementedError("plotting is outside the accelerated path; call with visualize=False "
-                                      "(generate_report.py:204-363 does) and plot outputs['classes_similarities']")
+            import warnings
+            warnings.warn("mmgclip_b200.PromptClassifier: visualize=True does not plot (plotting is out of scope); plot "
+                          "outputs['classes_similarities'] against outputs['class_list'] on the caller's side",
+                          stacklevel=2)
         return outputs

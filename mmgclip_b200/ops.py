@@ -77,6 +77,45 @@ def set_backward_probe(events) -> None:
     _bwd_probe = events
 
 
+# Optional phase timeline of a step (bench.py --timeline): named external CUDA events recorded on the current stream at
+# phase boundaries; like the probe above they are captured into CUDA graphs, so after a replay they hold that replay's
+# timestamps.  None (the default) = no events are recorded anywhere.
+_timeline = None
+
+
+def set_timeline(marks) -> None:
+    """marks: dict name -> event (filled on first use) or None."""
+    global _timeline
+    _timeline = marks
+
+
+def mark(name: str) -> None:
+    if _timeline is None:
+        return
+    ev = _timeline.get(name)
+    if ev is None:
+        ev = _timeline[name] = torch.cuda.Event(enable_timing=True, external=True)
+    ev.record()
+
+
+_TUNE_KEYS = ("fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl", "fused_ksl_t", "fused_sr", "fused_sc")
+
+
+def set_tuning(**kw) -> None:
+    """Plan knobs of the fused InfoNCE backward (mmg_tune): ``fused`` (0 = block loop), ``fused_rb`` / ``fused_cb`` (block
+    shape), ``fused_nbuf`` (scratch buffers), ``fused_ksl`` / ``fused_ksl_t`` (K blocks per gradient slice), ``fused_sr`` /
+    ``fused_sc`` (block-order super-tile).  Every setting computes the same result; the defaults are the measured best.
+    ``set_tuning()`` without arguments restores them; a value of None unsets one knob."""
+    lib = _lib.load()
+    if not kw:
+        check(lib.mmg_tune(b"reset", 0), "mmg_tune")
+        return
+    for k, v in kw.items():
+        if k not in _TUNE_KEYS:
+            raise ValueError(f"Invalid tuning key: {k}")
+        check(lib.mmg_tune(k.encode(), -1 if v is None else int(v)), "mmg_tune")
+
+
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Grow-only scratch per device (the L2-resident gradient-coefficient block lives here)."""
     key = (device.type, device.index)
@@ -277,14 +316,13 @@ def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: b
     return du, dub
 
 
-# Stored-E mode of the bf16 InfoNCE: the forward keeps E = exp(logit - s) as bf16 [rows, cols] and the backward transforms
-# it into the gradient coefficients instead of recomputing the cosines on the tensor cores (4 instead of 6 B^2 D FLOPs in
-# the backward) -- at the price of 2*rows*cols bytes of HBM, i.e. the O(B*D) memory bound is given up on purpose.  Used
-# when E fits the budget below (MiB; 0 = never), the shape is covered by the fused backward and logit_scale carries no
-# gradient (the cosines are gone, so sum g*cos cannot be formed).  Default 4 GiB: a paired batch of up to 46340 rows per
-# GPU (2 GiB at the benchmark's 32768); larger problems -- BASELINE config 5's 131072 rows -- keep the O(B*D) recompute
-# path.  Same box, whole step at B = 32768: 3.74 vs 4.01 ms.
-_store_e_mb = int(os.environ.get("MMGCLIP_B200_STORE_E_MB", "4096"))
+# Stored-E mode of the bf16 InfoNCE -- OPT-IN, off by default.  The default path never materialises anything of size
+# rows x cols in HBM (O(B*D) memory; the backward recomputes the cosines on the tensor cores).  With a budget
+# (MMGCLIP_B200_STORE_E_MB > 0, or set_store_e_budget_mb) the forward keeps E = exp(logit - s) as bf16 [rows, cols] and the
+# backward transforms it into the gradient coefficients instead of recomputing (4 instead of 6 B^2 D FLOPs in the backward)
+# at the price of 2*rows*cols bytes of HBM per live loss.  Only taken when E fits the budget, the shape is covered by the
+# fused backward and logit_scale carries no gradient (the cosines are gone, so sum g*cos cannot be formed).
+_store_e_mb = int(os.environ.get("MMGCLIP_B200_STORE_E_MB", "0"))
 
 
 def get_store_e_budget_mb() -> int:
@@ -453,8 +491,10 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
             own.zero_()
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC["bf16"], rows, cols, D)
     ws = _workspace(dev, nbytes)
+    mark("bwd_prep")
     if pre_sync is not None:
         pre_sync()
+    mark("pre_sync")
     for i, (_, owner_ptrs) in enumerate(parts):
         ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
         if e_stored is not None:
@@ -467,8 +507,10 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
                                              _stream()), "mmg_infonce_bwd_owners")
         if after_part is not None:
             after_part(i)
+    mark("bwd_fused")
     if post_sync is not None:
         post_sync()
+    mark("post_sync")
     return dA, [own for own, _ in parts], dls
 
 
@@ -699,10 +741,45 @@ class _InfoNCEFn(torch.autograd.Function):
                 None)
 
 
+# Range of the fixed softmax shift.  The fused kernels use m = s for every row and column: E = exp(s*cos - s).  That needs
+# |cos| <= 1 (L2-normalised inputs) and is unconditionally safe while 2*s stays below -log(FLT_MIN) = 87.3: no term can
+# underflow, so no row / column sum can vanish.  Beyond that a row whose best cosine is far from 1 can lose ALL its terms
+# (s * (1 - max cos) > 87), where the reference's per-row-max cross-entropy stays finite.  Policy:
+#   * scale known on the host (float / CPU tensor) and above the bound: the materialised, row-max-stabilised path
+#     (similarity_logits + cross_entropy) up to FIXED_SHIFT_FALLBACK_ROWS rows, ValueError above;
+#   * scale on the device (no host sync on the hot path): the loss kernel turns a vanished / overflowed sum into a NaN
+#     loss instead of silent inf gradients (simt_kernels.cu, infonce_loss_kernel).
+FIXED_SHIFT_MAX_SCALE = 43.0
+FIXED_SHIFT_FALLBACK_ROWS = 16384
+
+
+def _host_scale(logit_scale):
+    """The scale's value if it can be had without a device sync, else None."""
+    if not torch.is_tensor(logit_scale):
+        return float(logit_scale)
+    if not logit_scale.is_cuda:
+        return float(logit_scale.detach().reshape(()))
+    return None
+
+
 def info_nce(a_hat: torch.Tensor, b_hat: torch.Tensor, logit_scale: torch.Tensor, prec: Optional[str] = None):
-    """Symmetric InfoNCE of L2-normalised [n, D] embeddings; `logit_scale` is the already-exponentiated scale."""
+    """Symmetric InfoNCE of L2-normalised [n, D] embeddings; `logit_scale` is the already-exponentiated scale.
+
+    Inputs must be L2-normalised and the scale moderate (see FIXED_SHIFT_MAX_SCALE above; CLIP's 1/0.07 = 14.3 and its
+    usual clamp region up to 43 are inside)."""
     prec = _resolve(prec)
     _need_cuda(a_hat, b_hat)
+    s_host = _host_scale(logit_scale)
+    if s_host is not None and not (0.0 < s_host <= FIXED_SHIFT_MAX_SCALE):
+        if s_host <= 0.0 or s_host != s_host:
+            raise ValueError(f"info_nce: logit_scale must be a positive number (got {s_host})")
+        n = a_hat.shape[0]
+        if n > FIXED_SHIFT_FALLBACK_ROWS:
+            raise ValueError(f"info_nce: logit_scale {s_host:.1f} exceeds the fixed-shift range ({FIXED_SHIFT_MAX_SCALE}) and "
+                             f"{n} rows are too many for the materialised fallback (<= {FIXED_SHIFT_FALLBACK_ROWS})")
+        lpi = similarity_logits(a_hat, b_hat, logit_scale, prec=prec)
+        lpt = similarity_logits(b_hat, a_hat, logit_scale, prec=prec)
+        return (cross_entropy(lpi) + cross_entropy(lpt)) / 2
     if not torch.is_tensor(logit_scale):
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=a_hat.device)
     return _InfoNCEFn.apply(a_hat, b_hat, logit_scale, _operand(a_hat, prec), _operand(b_hat, prec), prec)
@@ -891,7 +968,8 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
                    want_logits: bool = True, want_probs: bool = True, impl: str = "auto"):
     """logits = (s*I) @ T^T, softmax(-1), argmax (ties -> lowest index), top-k (value desc, index asc).
 
-    Returns dict(logits, probs, argmax[int64], topk_idx[int64, k], topk_val).  C <= 64 prompts, k <= 8.
+    Returns dict(logits, probs, argmax[int64], topk_idx[int64, k], topk_val).  k <= 8; any number of prompts (more than
+    64 take a one-warp-per-row kernel instead of the tiled ones).
     (mmgclip_model.py:201-209; evaluator.py:182-188, 282-299, 354-368)
 
     ``impl``: "ffma" = fp32 FFMA kernel (what small batches use); "tc" = tensor-core kernel (3xTF32 split, logits within
@@ -908,7 +986,7 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
         s = logit_scale.detach().reshape(()).to(device=dev, dtype=torch.float32).contiguous()
     else:
         s = torch.tensor(float(logit_scale), dtype=torch.float32, device=dev)
-    logits = torch.empty((N, C), dtype=torch.float32, device=dev) if want_logits else None
+    logits = torch.empty((N, C), dtype=torch.float32, device=dev) if (want_logits or C > 64) else None
     probs = torch.empty((N, C), dtype=torch.float32, device=dev) if want_probs else None
     amax = torch.empty(N, dtype=torch.int64, device=dev)
     tki = torch.empty((N, k), dtype=torch.int64, device=dev) if k > 0 else None
@@ -916,7 +994,7 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
     if impl not in ("auto", "tc", "ffma"):
         raise ValueError(f"Invalid impl: {impl}")
     lib = _lib.load()
-    tc_ok = N > 0 and C <= 64 and D % 4 == 0 and img.data_ptr() % 16 == 0 and os.environ.get("MMG_ZEROSHOT_TC", "1") != "0"
+    tc_ok = N > 0 and C <= 64 and D % 4 == 0 and img.data_ptr() % 16 == 0
     if impl == "tc" and not tc_ok:
         raise ValueError("zeroshot_score(impl='tc') needs C <= 64, D % 4 == 0 and 16-byte aligned embeddings")
     if tc_ok and (impl == "tc" or (impl == "auto" and N >= _ZEROSHOT_TC_MIN_ROWS)):
@@ -926,7 +1004,7 @@ def zeroshot_score(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
     else:
         check(lib.mmg_zeroshot_score(_p(img), _p(txt), N, C, D, _p(s), _p(logits), _p(probs), _p(amax), k, _p(tki),
                                      _p(tkv), _stream()), "mmg_zeroshot_score")
-    return {"logits": logits, "probs": probs, "argmax": amax, "topk_idx": tki, "topk_val": tkv}
+    return {"logits": logits if want_logits else None, "probs": probs, "argmax": amax, "topk_idx": tki, "topk_val": tkv}
 
 
 # -------------------------------------------------------------------------------------------------------------------

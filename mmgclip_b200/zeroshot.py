@@ -24,7 +24,7 @@ def _to_device(x, device):
 
 def score_prompts(image_embeddings, text_embeddings, logit_scale, top_k: int = 0, device: Optional[str] = None,
                   chunk_rows: int = 1 << 22):
-    """Probabilities [N, C], argmax [N] (int64) and optional top-k for N image embeddings against C <= 64 prompts.
+    """Probabilities [N, C], argmax [N] (int64) and optional top-k for N image embeddings against C prompts.
 
     Inputs are L2-normalised embeddings (torch tensors or NumPy arrays, as ``Evaluator.encode_*`` return) and the
     exponentiated ``logit_scale``.  Rows are processed in chunks so N is bounded only by memory for the outputs.

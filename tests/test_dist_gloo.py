@@ -94,6 +94,56 @@ def test_sharded_infonce_two_ranks_equals_closed_form(tmp_path):
         assert np.allclose(out["wg"], 3.0) and np.allclose(out["bg"], 30.0)  # gradients are summed across ranks
 
 
+def _worker_two_losses(rank, world, port, out_dir):
+    """The column-side embeddings feed TWO sharded losses (MMGCLIPLoss: CLIP term + text<->text term, losses.py:73-91) and a
+    third, ordinary consumer: the gradients of all three must add up -- the situation in which the NCCL-fallback path's
+    deferred reduce-scatter used to race with autograd's accumulation (every column gradient now has one producer, the
+    private identity node of sharded_info_nce)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmgclip_b200 import distributed as D
+    rng = np.random.RandomState(11)
+    n, d = 12, 16
+    unit = lambda x: x / np.linalg.norm(x, axis=1, keepdims=True)  # noqa: E731
+    a, b, c = (unit(rng.standard_normal((n, d))) for _ in range(3))
+    bl = n // world
+    sl = slice(rank * bl, (rank + 1) * bl)
+    al, blt, cl = (torch.from_numpy(x[sl]).requires_grad_() for x in (a, b, c))
+    s = float(np.float32(1 / 0.07))
+    st = torch.tensor(s, dtype=torch.float64)
+    loss = (D.sharded_info_nce(al, blt, st, prec="fp32", _kernels=NumpyKernels)
+            + 0.5 * D.sharded_info_nce(cl, blt, st, prec="fp32", _kernels=NumpyKernels) + 0.25 * (blt * blt).sum())
+    loss.backward()
+    np.savez(os.path.join(out_dir, f"t{rank}.npz"), loss=loss.detach().numpy(), da=al.grad.numpy(), db=blt.grad.numpy(),
+             dc=cl.grad.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_column_side_feeding_two_sharded_losses(tmp_path):
+    from oracle import clip_oracle as oc
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_two_losses, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.RandomState(11)
+    n, d = 12, 16
+    unit = lambda x: x / np.linalg.norm(x, axis=1, keepdims=True)  # noqa: E731
+    a, b, c = (unit(rng.standard_normal((n, d))) for _ in range(3))
+    s = float(np.float32(1 / 0.07))
+    r1, r2 = oc.closed_form_info_nce(a, b, s), oc.closed_form_info_nce(c, b, s)
+    bl = n // world
+    for r in range(world):
+        out = np.load(os.path.join(str(tmp_path), f"t{r}.npz"))
+        sl = slice(r * bl, (r + 1) * bl)
+        want_loss = r1["loss"] + 0.5 * r2["loss"] + 0.25 * float((b[sl] ** 2).sum())
+        assert abs(float(out["loss"]) - want_loss) < 1e-12
+        assert np.allclose(out["da"], r1["da"][sl], rtol=1e-10, atol=1e-13)
+        assert np.allclose(out["dc"], 0.5 * r2["da"][sl], rtol=1e-10, atol=1e-13)
+        assert np.allclose(out["db"], r1["db"][sl] + 0.5 * r2["db"][sl] + 0.5 * b[sl], rtol=1e-10, atol=1e-13)
+
+
 def test_single_process_path_needs_no_process_group():
     from mmgclip_b200 import distributed as D
     x = torch.randn(4, 8)

@@ -132,22 +132,29 @@ def test_unsupported_shape_reports_zero():
 
 
 @pytest.mark.parametrize("sr,sc", [(1, 1), (2, 4), (4, 2), (8, 16), (3, 5)])
-def test_block_order_super_tiles(monkeypatch, sr, sc):
+def test_block_order_super_tiles(sr, sc):
     """Any super-tile shape (non-dividing requests fall back to a dividing one) keeps the schedule complete and live."""
-    monkeypatch.setenv("MMG_FUSED_SR", str(sr))
-    monkeypatch.setenv("MMG_FUSED_SC", str(sc))
-    test_schedule_is_complete_and_deadlock_free((32768, 32768, 512, 1, 1, 0), 74)
-    test_schedule_is_complete_and_deadlock_free((4096, 32768, 512, 8, 2, 1), 74)
+    lib = _lib.load()
+    try:
+        assert lib.mmg_tune(b"fused_sr", sr) == 0 and lib.mmg_tune(b"fused_sc", sc) == 0
+        test_schedule_is_complete_and_deadlock_free((32768, 32768, 512, 1, 1, 0), 74)
+        test_schedule_is_complete_and_deadlock_free((4096, 32768, 512, 8, 2, 1), 74)
+    finally:
+        assert lib.mmg_tune(b"reset", 0) == 0
+
+
+def test_tune_rejects_unknown_keys():
+    lib = _lib.load()
+    assert lib.mmg_tune(b"no_such_knob", 1) != 0
+    assert b"unknown key" in lib.mmg_last_error_string()
 
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("pairs", [1, 5, 74])
-@pytest.mark.parametrize("defer", [False, True])
-def test_stored_e_two_stream_replay(shape, pairs, defer):
+def test_stored_e_two_stream_replay(shape, pairs, defer=False):
     """Stored-E mode runs two independent streams per CTA pair: the transform warps walk the coefficient tiles (waiting
     for doneB of the block whose buffer they overwrite), the producer / MMA / epilogue warps walk the gradient slices
-    (waiting for doneA of their block).  ``defer``: a tile is published only once the NEXT tile of the pair has passed its
-    wait (kDefer kernels, MMG_STORED_DEFER=1), the last one immediately.  Both must run to completion."""
+    (waiting for doneA of their block).  Both must run to completion."""
     rows, cols, D, n_owners, n_parts, part = shape
     per_pair, info = _schedule(rows, cols, D, n_owners, n_parts, part, pairs)
     if not any(per_pair):
@@ -204,10 +211,8 @@ def _needed_tiles(it, info):
 @pytest.mark.parametrize("shape", SHAPES[:5])
 @pytest.mark.parametrize("pairs", [3, 74])
 @pytest.mark.parametrize("mode", ["recompute", "stored"])
-@pytest.mark.parametrize("panel", [False, True])
-def test_dependency_counters_cover_the_data_each_slice_reads(shape, pairs, mode, panel):
-    """Replays the kernel's own counter arithmetic (block counters, or the per-panel counters of the kPanel kernels) and
-    checks, at the moment a gradient slice is allowed to start, that every coefficient tile it reads is complete -- and
+def test_dependency_counters_cover_the_data_each_slice_reads(shape, pairs, mode, panel=False):
+    """Replays the kernel's own counter arithmetic (block counters) and checks, at the moment a gradient slice is allowed to start, that every coefficient tile it reads is complete -- and
     that everything runs to completion."""
     rows, cols, D, n_owners, n_parts, part = shape
     per_pair, info = _schedule(rows, cols, D, n_owners, n_parts, part, pairs)

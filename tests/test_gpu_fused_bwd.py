@@ -11,14 +11,12 @@ from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
-ENV = ("MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF", "MMG_FUSED_KSL", "MMG_FUSED_KSL_T")
-
-
 def _setenv(**kw):
-    for k in ENV:
-        os.environ.pop(k, None)
-    for k, v in kw.items():
-        os.environ[k] = str(v)
+    """Plan knobs of the fused backward (mmg_tune); no arguments = back to the defaults."""
+    from mmgclip_b200 import ops
+    ops.set_tuning()
+    if kw:
+        ops.set_tuning(**kw)
 
 
 def _problem(rows, cols, d, off, seed=3):
@@ -39,9 +37,9 @@ def _problem(rows, cols, d, off, seed=3):
     (512, 512, 256, 0, {}),
     (768, 768, 1024, 0, {}),
     (1024, 2048, 512, 512, {}),
-    (1024, 2048, 512, 1024, {"MMG_FUSED_RB": 256, "MMG_FUSED_CB": 512, "MMG_FUSED_NBUF": 3, "MMG_FUSED_KSL": 2}),
+    (1024, 2048, 512, 1024, {"fused_rb": 256, "fused_cb": 512, "fused_nbuf": 3, "fused_ksl": 2}),
     (4096, 8192, 512, 4096, {}),
-    (4096, 4096, 512, 0, {"MMG_FUSED_RB": 1024, "MMG_FUSED_CB": 1024, "MMG_FUSED_NBUF": 5, "MMG_FUSED_KSL": 4, "MMG_FUSED_KSL_T": 16}),
+    (4096, 4096, 512, 0, {"fused_rb": 1024, "fused_cb": 1024, "fused_nbuf": 5, "fused_ksl": 4, "fused_ksl_t": 16}),
 ])
 def test_fused_backward_matches_block_loop(rows, cols, d, off, cfg):
     ops, a, b, ab, bb, s, rs, cs, diag = _problem(rows, cols, d, off)
@@ -49,7 +47,7 @@ def test_fused_backward_matches_block_loop(rows, cols, d, off, cfg):
     b32 = b[off:off + rows].contiguous()
     run = lambda: ops.infonce_backward_raw(ab, bb, s, rs, cs, one, 0.5 / cols, off, "bf16", a32=a, b32=b32, diag=diag)  # noqa: E731
     try:
-        _setenv(MMG_BWD_FUSED=0)
+        _setenv(fused=0)
         dA0, dB0, dl0 = run()
         torch.cuda.synchronize()
         _setenv(**cfg)

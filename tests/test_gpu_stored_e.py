@@ -1,4 +1,4 @@
-"""Stored-E variant of the bf16 InfoNCE (MMGCLIP_B200_STORE_E_MB, default 4096 MiB): the forward keeps E = exp(logit - s) as bf16 and
+"""Stored-E variant of the bf16 InfoNCE (opt-in: MMGCLIP_B200_STORE_E_MB or ops.set_store_e_budget_mb; off by default): the forward keeps E = exp(logit - s) as bf16 and
 the fused backward transforms it instead of recomputing the cosines.  Checked against the recompute path of the same
 library and against the float64 closed form of the oracle -- same tolerances as the default bf16 path (loss 2e-3,
 embedding gradients 4e-3 max-abs/max-abs)."""
@@ -14,15 +14,12 @@ from oracle import clip_oracle as oc
 
 pytestmark = pytest.mark.gpu
 
-ENV = ("MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF", "MMG_FUSED_KSL", "MMG_FUSED_KSL_T",
-       "MMG_FUSED_SR", "MMG_FUSED_SC")
-
-
 def _setenv(**kw):
-    for k in ENV:
-        os.environ.pop(k, None)
-    for k, v in kw.items():
-        os.environ[k] = str(v)
+    """Plan knobs of the fused backward (mmg_tune); no arguments = back to the defaults."""
+    from mmgclip_b200 import ops
+    ops.set_tuning()
+    if kw:
+        ops.set_tuning(**kw)
 
 
 def _embeddings(n, d, seed):
@@ -35,8 +32,8 @@ def _embeddings(n, d, seed):
 @pytest.mark.parametrize("n,d,cfg", [
     (256, 256, {}),
     (1024, 512, {}),
-    (2048, 256, {"MMG_FUSED_RB": 512, "MMG_FUSED_CB": 256, "MMG_FUSED_NBUF": 3, "MMG_FUSED_KSL": 2}),
-    (4096, 512, {"MMG_FUSED_RB": 1024, "MMG_FUSED_CB": 1024, "MMG_FUSED_SR": 2, "MMG_FUSED_SC": 2}),
+    (2048, 256, {"fused_rb": 512, "fused_cb": 256, "fused_nbuf": 3, "fused_ksl": 2}),
+    (4096, 512, {"fused_rb": 1024, "fused_cb": 1024, "fused_sr": 2, "fused_sc": 2}),
 ])
 def test_stored_e_matches_recompute_and_float64(n, d, cfg):
     from mmgclip_b200 import ops
