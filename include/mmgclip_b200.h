@@ -123,6 +123,15 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
 int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                      float inv_two_b, float* loss_out, mmg_stream_t stream);
 
+/* The same loss in two parts for the row-sharded case (one cross-rank sum then serves the column sums AND the loss):
+ *     part_out[0] = sum_{r < rows} ( log rowsum[r] - 2*diag[r] )            -- local rows, before the exchange
+ *     loss_out[0] = inv_two_b * ( row_part[0] + sum_{c < cols} log colsum[c] + 2*cols*s )
+ * with row_part = the sum of every rank's part and colsum the global column sums; equals mmg_infonce_loss over the whole
+ * batch (losses.py:40-43).  Deterministic reductions; a vanished / overflowed sum gives NaN. */
+int mmg_infonce_row_part(const float* rowsum, const float* diag, int rows, float* part_out, mmg_stream_t stream);
+int mmg_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
+                          float* loss_out, mmg_stream_t stream);
+
 /* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c]; scal (4 floats): [1] = dcoef =
  * 2*s*gl*inv_two_b; [0] = the diagonal coefficient mmg_infonce_bwd itself subtracts (dcoef, or 0 when diag_in_fp32);
  * [2] = diag_in_fp32 flag: mmg_infonce_bwd then ZEROES the matching-pair element of g and the caller applies it with

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mmg_infonce_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmg_infonce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    "mmg_infonce_row_part": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mmg_infonce_loss_cols": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "mmg_infonce_bwd_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "mmg_infonce_bwd_diag": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -362,6 +362,24 @@ int mmg_infonce_loss(const float* rowsum, const float* colsum, const float* diag
   return simt_infonce_loss(rowsum, colsum, diag, n, scale, inv_two_b, loss_out, static_cast<cudaStream_t>(stream));
 }
 
+int mmg_infonce_row_part(const float* rowsum, const float* diag, int rows, float* part_out, mmg_stream_t stream) {
+  if (rows <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_row_part: rows must be positive");
+  MMG_REQ(rowsum);
+  MMG_REQ(diag);
+  MMG_REQ(part_out);
+  return simt_infonce_row_part(rowsum, diag, rows, part_out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
+                          float* loss_out, mmg_stream_t stream) {
+  if (cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_loss_cols: cols must be positive");
+  MMG_REQ(colsum);
+  MMG_REQ(scale);
+  MMG_REQ(row_part);
+  MMG_REQ(loss_out);
+  return simt_infonce_loss_cols(colsum, cols, scale, row_part, inv_two_b, loss_out, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                          float* scal, mmg_stream_t stream) {

@@ -105,6 +105,9 @@ int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0,
 
 int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                       float inv_two_b, float* loss_out, cudaStream_t st);
+int simt_infonce_row_part(const float* rowsum, const float* diag, int rows, float* part_out, cudaStream_t st);
+int simt_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
+                           float* loss_out, cudaStream_t st);
 int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
                           const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                           float* scal, cudaStream_t st);

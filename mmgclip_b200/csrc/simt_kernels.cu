@@ -575,31 +575,100 @@ int simt_grad_block(float* S, long long lds, int rb, int cb, int row0, int col0,
 // normalised; instead of letting log(0) / coef/0 leak inf into the loss and the gradients silently, the loss is set to NaN
 // here (the reference's per-row-max cross-entropy would still be finite -- mmgclip_b200.ops.info_nce documents the range
 // and the materialised fallback).
+// Sum over a 1024-thread block in double, fixed order (warp shuffles, then one warp over the 32 warp sums): every thread
+// gets the total.  `bad` is OR-ed across the block.
+__device__ __forceinline__ double block_sum_1024(double v, int& bad) {
+  __shared__ double wpart[32];
+  __shared__ double total;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = v;
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x < 32) {
+    double t = wpart[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) total = t;
+  }
+  __syncthreads();
+  return total;
+}
+
+// Each thread sums its strided share of f(i) in fp32 over four independent chains (<= a few dozen terms of magnitude ~10:
+// ~1e-7 relative), the block total is formed in double.
 __global__ void __launch_bounds__(1024)
 infonce_loss_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum, const float* __restrict__ diag,
                     int n, const float* __restrict__ scale, float inv_two_b, float* __restrict__ loss_out) {
-  __shared__ double part[1024];
   const float s = *scale;
-  double acc = 0.0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int bad = 0;
-  for (int i = threadIdx.x; i < n; i += 1024) {
+  int k = 0;
+  for (int i = threadIdx.x; i < n; i += 1024, ++k) {
     const float rs = rowsum[i], cs = colsum[i];
     bad |= !(rs > 0.f && rs < INFINITY) || !(cs > 0.f && cs < INFINITY);
-    acc += (double)(logf(rs) + s - diag[i]) + (double)(logf(cs) + s - diag[i]);
+    acc[k & 3] += (logf(rs) - diag[i]) + (logf(cs) - diag[i]);
   }
-  part[threadIdx.x] = acc;
-  bad = __syncthreads_or(bad);
-  for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)(part[0] * (double)inv_two_b);
+  const double tot = block_sum_1024((double)(acc[0] + acc[1]) + (double)(acc[2] + acc[3]), bad);
+  if (threadIdx.x == 0)
+    loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)((tot + 2.0 * (double)n * (double)s) * (double)inv_two_b);
 }
 
 int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                       float inv_two_b, float* loss_out, cudaStream_t st) {
   infonce_loss_kernel<<<1, 1024, 0, st>>>(rowsum, colsum, diag, n, scale, inv_two_b, loss_out);
   MMG_LAUNCH_CHECK("infonce_loss_kernel");
+  return 0;
+}
+
+// Row-sharded loss in two parts, so that ONE cross-rank sum serves the column sums and the loss:
+//   part_out[0] = sum_{local r} ( log rowsum[r] - 2*diag[r] )                 (before the exchange; rides in the same
+//                                                                              all-reduce as the partial column sums)
+//   loss        = inv_two_b * ( sum_ranks part + sum_{all c} log colsum[c] + 2*cols*s )   (after it, on every rank)
+// which equals inv_two_b * sum_i (log rowsum_i + log colsum_i + 2s - 2 diag_i) over the global batch (the matching-pair
+// logit of column c is the one of row c).  A vanished / overflowed sum poisons the part (NaN), and with it the loss.
+__global__ void __launch_bounds__(1024)
+infonce_row_part_kernel(const float* __restrict__ rowsum, const float* __restrict__ diag, int rows,
+                        float* __restrict__ part_out) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int bad = 0;
+  int k = 0;
+  for (int i = threadIdx.x; i < rows; i += 1024, ++k) {
+    const float rs = rowsum[i];
+    bad |= !(rs > 0.f && rs < INFINITY);
+    acc[k & 3] += logf(rs) - 2.0f * diag[i];
+  }
+  const double tot = block_sum_1024((double)(acc[0] + acc[1]) + (double)(acc[2] + acc[3]), bad);
+  if (threadIdx.x == 0) part_out[0] = bad ? __int_as_float(0x7fc00000) : (float)tot;
+}
+
+__global__ void __launch_bounds__(1024)
+infonce_loss_cols_kernel(const float* __restrict__ colsum, int cols, const float* __restrict__ scale,
+                         const float* __restrict__ row_part, float inv_two_b, float* __restrict__ loss_out) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int bad = 0;
+  int k = 0;
+  for (int i = threadIdx.x; i < cols; i += 1024, ++k) {
+    const float cs = colsum[i];
+    bad |= !(cs > 0.f && cs < INFINITY);
+    acc[k & 3] += logf(cs);
+  }
+  const double tot = block_sum_1024((double)(acc[0] + acc[1]) + (double)(acc[2] + acc[3]), bad);
+  if (threadIdx.x == 0) {
+    const double v = ((double)row_part[0] + tot + 2.0 * (double)cols * (double)(*scale)) * (double)inv_two_b;
+    loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)v;  // a NaN part propagates by itself
+  }
+}
+
+int simt_infonce_row_part(const float* rowsum, const float* diag, int rows, float* part_out, cudaStream_t st) {
+  infonce_row_part_kernel<<<1, 1024, 0, st>>>(rowsum, diag, rows, part_out);
+  MMG_LAUNCH_CHECK("infonce_row_part_kernel");
+  return 0;
+}
+
+int simt_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
+                           float* loss_out, cudaStream_t st) {
+  infonce_loss_cols_kernel<<<1, 1024, 0, st>>>(colsum, cols, scale, row_part, inv_two_b, loss_out);
+  MMG_LAUNCH_CHECK("infonce_loss_cols_kernel");
   return 0;
 }
 

@@ -39,11 +39,29 @@ _peer_cache = {}
 
 
 class _PeerBuffers:
+    """A ring of symmetric [rows, D] fp32 buffers (one per in-flight column-side gradient) with their peer mappings.
+
+    The backward hands the ring slot itself to autograd as dB (no copy): a slot is written again four sharded backward
+    calls of the same shape later, long after the gradient has been consumed by the column side's producer.  Callers that
+    may keep the tensor (a leaf or ``retain_grad()`` column side) get a private copy instead."""
+
+    RING = 4
+
     def __init__(self, rows, D, device, group):
         import torch.distributed._symmetric_memory as symm_mem
-        self.own = symm_mem.empty((rows, D), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.own, group=group if group is not None else dist.group.WORLD)
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        grp = group if group is not None else dist.group.WORLD
+        self.slots = []
+        for _ in range(self.RING):
+            own = symm_mem.empty((rows, D), dtype=torch.float32, device=device)
+            handle = symm_mem.rendezvous(own, group=grp)
+            self.slots.append((own, handle, [int(p) for p in handle.buffer_ptrs]))
+        self.i = -1
+        self.own, self.handle, self.ptrs = self.slots[0]
+
+    def next(self):
+        self.i = (self.i + 1) % self.RING
+        self.own, self.handle, self.ptrs = self.slots[self.i]
+        return self
 
     def pre_sync(self):
         self.handle.barrier(channel=0)
@@ -147,8 +165,12 @@ class _Kernels:
         return ops.infonce_forward_raw(a_op, b_all_op, scale, diag_offset, prec, colsum=colsum, e_out=e_out)
 
     @staticmethod
-    def loss(rowsum, colsum_slice, diag, scale, inv_two_b):
-        return ops.infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b)
+    def row_part(rowsum, diag, out=None):
+        return ops.infonce_row_part_raw(rowsum, diag, out=out)
+
+    @staticmethod
+    def loss_cols(colsum, scale, row_part, inv_two_b):
+        return ops.infonce_loss_cols_raw(colsum, scale, row_part, inv_two_b)
 
     @staticmethod
     def backward(a_op, b_all_op, scale, rowsum, colsum, grad_loss, inv_two_b, diag_offset, prec, a32, b32_paired,
@@ -188,6 +210,8 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a_local, b_local, scale, group, prec, kernels, gathered=None, pending=None, b_key=None):
         ctx.pending = pending
+        key = b_key if b_key is not None else b_local
+        ctx.private_db = bool(key.is_leaf or key.retains_grad)
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         bl, D = a_local.shape
@@ -213,24 +237,25 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             e_mat = torch.empty((bl, B), dtype=torch.bfloat16, device=a_local.device)
         ctx.e_mat = e_mat
         fwd_kw = {"e_out": e_mat} if e_mat is not None else {}
-        cvec = _symm_vector("colsum", B, a_local.device, group) if kernels is _Kernels else None
+        # ONE cross-rank sum per forward: the partial column sums [B] and, in element B of the same vector, this rank's part
+        # of the loss that is known before the exchange (sum over its rows of log rowsum - 2 diag).  Afterwards every rank
+        # holds the global column sums and finishes the loss locally (sum over ALL columns of log colsum) -- no second
+        # all-reduce for the scalar, and the value is bit-identical on every rank.
+        cvec = _symm_vector("colsum", B + 1, a_local.device, group) if kernels is _Kernels else None
         if cvec is not None:
             cvec.buf.zero_()  # the partial column sums accumulate straight into the symmetric buffer
             rowsum, _, diag = kernels.forward(a_op, b_all, s, off, prec, colsum=cvec.buf[:B], **fwd_kw)
+            kernels.row_part(rowsum, diag, out=cvec.buf[B:B + 1])
             ops.mark("lse_fwd")
-            colsum = cvec.all_reduce()[:B]
+            red = cvec.all_reduce()
+            colsum, part = red[:B], red[B:B + 1]
             ops.mark("colsum_ar")
         else:
             rowsum, colsum, diag = kernels.forward(a_op, b_all, s, off, prec, **fwd_kw)
-            dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
-        loss = kernels.loss(rowsum, colsum[off:off + bl], diag, s, 0.5 / B)
-        lvec = _symm_vector("loss", 1, a_local.device, group) if kernels is _Kernels else None
-        if lvec is not None:
-            lvec.buf[:1].copy_(loss.reshape(1))
-            loss = lvec.all_reduce()[0]
-            ops.mark("loss_ar")
-        else:
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+            vec = torch.cat([colsum, kernels.row_part(rowsum, diag).to(colsum.dtype).reshape(1)])
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            colsum, part = vec[:B], vec[B:B + 1]
+        loss = kernels.loss_cols(colsum, s, part, 0.5 / B)
         ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
         ctx.scale_shape = scale.shape
         ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach(), diag)
@@ -248,13 +273,14 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         if kernels is _Kernels and prec == "bf16" and a_op.is_cuda:
             peer = _peer_buffers(bl, D, a_op.device, group)
         if peer is not None:
+            peer.next()
             # gradient GEMM + reduce-scatter in one kernel: the slices add into their owners' buffers over NVLink
             dA, owns, dls = ops.infonce_backward_owners(a_op, b_all, s, rowsum, colsum, grad_loss, 0.5 / ctx.B, ctx.off,
                                                         [(peer.own, peer.ptrs)], peer.pre_sync, peer.post_sync, a32=a32,
                                                         b32=b32_local, diag=diag, need_dscale=ctx.needs_input_grad[2],
                                                         e_stored=ctx.e_mat)
             ctx.e_mat = None
-            dB = owns[0].clone()  # the symmetric buffer is reused by the next step
+            dB = owns[0].clone() if ctx.private_db else owns[0]  # a ring slot (see _PeerBuffers) unless it may be kept
             ops.mark("clone")
             dscale = None
             if ctx.needs_input_grad[2]:
@@ -324,17 +350,35 @@ class _AwaitColumnGrad(torch.autograd.Function):
 
 def allreduce_gradients(*modules: torch.nn.Module, group=None) -> None:
     """Sum parameter gradients across ranks (one flat all-reduce for all given modules): with the global loss above each
-    rank's head gradient covers only its own rows."""
+    rank's head gradient covers only its own rows.
+
+    On the symmetric-memory path the summed gradients are handed back as VIEWS of the persistent flat buffer (no copy
+    out): ``p.grad`` is valid until the next call with the same parameters overwrites it -- what an optimizer step or a
+    graph replay needs.  A gradient that is already such a view (gradients accumulated in place over micro-steps) is
+    summed where it lies."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
+    params = [p for m in modules for p in m.parameters() if p.grad is not None]
+    grads = [p.grad for p in params]
     if not grads:
         return
     n = sum(g.numel() for g in grads)
     vec = _symm_vector("grads", n, grads[0].device, group) if all(g.dtype == torch.float32 for g in grads) else None
     if vec is not None:
-        torch.cat([g.reshape(-1) for g in grads], out=vec.buf[:n])
+        o = 0
+        in_place = True
+        for g in grads:
+            in_place = in_place and g.is_contiguous() and g.data_ptr() == vec.buf.data_ptr() + 4 * o
+            o += g.numel()
+        if not in_place:
+            torch.cat([g.reshape(-1) for g in grads], out=vec.buf[:n])
         flat = vec.all_reduce()
+        o = 0
+        if flat.data_ptr() == vec.buf.data_ptr():
+            for p, g in zip(params, grads):
+                p.grad = flat[o:o + g.numel()].view_as(g)
+                o += g.numel()
+            return
     else:
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

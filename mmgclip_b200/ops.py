@@ -98,7 +98,7 @@ def mark(name: str) -> None:
     ev.record()
 
 
-_TUNE_KEYS = ("fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl", "fused_ksl_t", "fused_sr", "fused_sc")
+_TUNE_KEYS = ("fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl", "fused_ksl_t", "fused_sr", "fused_sc", "fused_hints", "fused_rot")
 
 
 def set_tuning(**kw) -> None:
@@ -370,6 +370,26 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
     out = torch.empty((), dtype=torch.float32, device=rowsum.device)
     check(_lib.load().mmg_infonce_loss(_p(rowsum), _p(colsum_slice), _p(diag), rowsum.numel(), _p(scale),
                                        float(inv_two_b), _p(out), _stream()), "mmg_infonce_loss")
+    return out
+
+
+def infonce_row_part_raw(rowsum, diag, out=None) -> torch.Tensor:
+    """out[0] = sum_r (log rowsum[r] - 2*diag[r]) over the local rows (mmg_infonce_row_part): the part of the sharded loss
+    that is known before the exchange.  ``out``: a 1-element fp32 view to write into (e.g. the tail of the symmetric
+    column-sum buffer, so that one all-reduce carries both)."""
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=rowsum.device)
+    check(_lib.load().mmg_infonce_row_part(_p(rowsum), _p(diag), rowsum.numel(), _p(out), _stream()),
+          "mmg_infonce_row_part")
+    return out
+
+
+def infonce_loss_cols_raw(colsum, scale, row_part, inv_two_b: float) -> torch.Tensor:
+    """loss = inv_two_b * (row_part + sum_c log colsum[c] + 2*cols*s) from the GLOBAL column sums and the summed row
+    parts (mmg_infonce_loss_cols); every rank computes the same value."""
+    out = torch.empty((), dtype=torch.float32, device=colsum.device)
+    check(_lib.load().mmg_infonce_loss_cols(_p(colsum), colsum.numel(), _p(scale), _p(row_part), float(inv_two_b), _p(out),
+                                            _stream()), "mmg_infonce_loss_cols")
     return out
 
 

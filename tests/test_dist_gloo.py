@@ -30,9 +30,13 @@ class NumpyKernels:
         return torch.from_numpy(e.sum(1)), torch.from_numpy(e.sum(0)), torch.from_numpy(diag)
 
     @staticmethod
-    def loss(rowsum, colsum_slice, diag, s, inv_two_b):
+    def row_part(rowsum, diag, out=None):
+        return (torch.log(rowsum) - 2 * diag).sum().reshape(1)
+
+    @staticmethod
+    def loss_cols(colsum, s, row_part, inv_two_b):
         sv = float(s)
-        return (inv_two_b * (torch.log(rowsum) + torch.log(colsum_slice) + 2 * sv - 2 * diag).sum()).reshape(())
+        return (inv_two_b * (row_part.sum() + torch.log(colsum).sum() + 2 * colsum.numel() * sv)).reshape(())
 
     @staticmethod
     def backward(a, b_all, s, rowsum, colsum, grad_loss, inv_two_b, off, prec, a32, b32, diag, need_dscale=True):
