@@ -82,9 +82,11 @@ int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, lon
  * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_bf16 (nullable) receives a bf16 copy. */
 int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream);
 /* du = (dy - y * <y, dy>) * inv_norm   (autograd of the line above).  Outputs (each nullable, at least one): du fp32,
- * du_bf16 = bf16(du), du_bf16_lo = bf16(du - du_bf16) for the bf16x3 weight-gradient contraction. */
+ * du_bf16 = bf16(du), du_bf16_lo = bf16(du - du_bf16) for the bf16x3 weight-gradient contraction.
+ * zero_fill (nullable; 16-byte aligned, zero_floats % 4 == 0): a buffer the same launch clears -- the split-K output of the
+ * weight-gradient contraction that follows accumulates with reduce-adds and would otherwise need a fill launch. */
 int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                   void* du_bf16_lo, mmg_stream_t stream);
+                   void* du_bf16_lo, float* zero_fill, long long zero_floats, mmg_stream_t stream);
 
 /* Hidden-layer pieces of MultiLinearHead (projection.py:54-61): ReLU/inverted-dropout backward and bias gradient.
  *   dz[i] = dy[i] * (y ? y[i] > 0 : 1) * (mask ? mask[i] * keep_scale : 1)      db[n] = sum_rows dz[:, n]
@@ -151,6 +153,15 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
 int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                          const float* rinv, const float* cinv_paired, const float* scal, float* dA, float* dB,
                          float* dlogscale_acc, int init, mmg_stream_t stream);
+
+/* mmg_infonce_bwd_prep(diag_in_fp32 = 1) and mmg_infonce_bwd_diag(init = 1) as ONE launch (what the bf16 path runs before
+ * its contraction kernel): writes rinv[rows], cinv[cols], scal[4] and the matching-pair rows dA[r,:] = g*b32[r,:],
+ * dB_matching[r,:] = g*a32[r,:] (g as above, formed from rowsum[r] and colsum[diag_offset + r] directly).  b32 and
+ * dB_matching point at the `rows` column-side rows paired with the local rows. */
+int mmg_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+                              const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
+                              float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
+                              float* dB_matching, float* dlogscale_acc, mmg_stream_t stream);
 
 /* dA[rows,D] += g . b_hat,  dB[cols,D] += g^T . a_hat,  dlogscale_acc[0] += sum g*cos   with
  *     g = exp(s*cos - s) * (rinv[r] + cinv[c]) - scal[0]*[c == r + diag_offset]    ( = s * dloss/dlogit; the

@@ -155,16 +155,24 @@ int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void
 }
 
 int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                   void* du_bf16_lo, mmg_stream_t stream) {
+                   void* du_bf16_lo, float* zero_fill, long long zero_floats, mmg_stream_t stream) {
   if (B < 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_bwd: bad shape %dx%d", B, D);
-  if (B == 0) return 0;
+  if (zero_fill != nullptr && ((reinterpret_cast<uintptr_t>(zero_fill) & 15) != 0 || zero_floats < 0 || (zero_floats & 3) != 0))
+    return set_error(MMG_ERR_BAD_ALIGN, "mmg_l2norm_bwd: zero_fill must be 16-byte aligned, a multiple of 4 floats");
+  if (B == 0) {
+    if (zero_fill != nullptr && zero_floats > 0)
+      return check_cuda(cudaMemsetAsync(zero_fill, 0, (size_t)zero_floats * 4, static_cast<cudaStream_t>(stream)),
+                        "cudaMemsetAsync(zero_fill)");
+    return 0;
+  }
   MMG_REQ(dy);
   MMG_REQ(y);
   MMG_REQ(inv_norm);
   if (du == nullptr && du_bf16 == nullptr) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_bwd: no output");
   if (du_bf16_lo != nullptr && du_bf16 == nullptr)
     return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_bwd: du_bf16_lo needs du_bf16");
-  return simt_l2norm_bwd(dy, y, inv_norm, B, D, du, du_bf16, du_bf16_lo, static_cast<cudaStream_t>(stream));
+  return simt_l2norm_bwd(dy, y, inv_norm, B, D, du, du_bf16, du_bf16_lo, zero_fill, zero_floats,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int mmg_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, mmg_stream_t stream) {
@@ -378,6 +386,28 @@ int mmg_infonce_loss_cols(const float* colsum, int cols, const float* scale, con
   MMG_REQ(row_part);
   MMG_REQ(loss_out);
   return simt_infonce_loss_cols(colsum, cols, scale, row_part, inv_two_b, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int mmg_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+                              const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
+                              float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
+                              float* dB_matching, float* dlogscale_acc, mmg_stream_t stream) {
+  if (rows <= 0 || cols <= 0 || D <= 0 || diag_offset < 0 || diag_offset + rows > cols)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep_diag: bad shape");
+  MMG_REQ(rowsum);
+  MMG_REQ(colsum);
+  MMG_REQ(scale);
+  MMG_REQ(grad_loss);
+  MMG_REQ(rinv);
+  MMG_REQ(cinv);
+  MMG_REQ(scal);
+  MMG_REQ(a32);
+  MMG_REQ(b32);
+  MMG_REQ(diag);
+  MMG_REQ(dA);
+  MMG_REQ(dB_matching);
+  return simt_infonce_bwd_prep_diag(rowsum, rows, colsum, cols, diag_offset, scale, grad_loss, inv_two_b, rinv, cinv, scal,
+                                    a32, b32, D, diag, dA, dB_matching, dlogscale_acc, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,

@@ -76,7 +76,7 @@ int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
 int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st);
 int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                    void* du_bf16_lo, cudaStream_t st);
+                    void* du_bf16_lo, float* zero, long long zero_floats, cudaStream_t st);
 int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st);
 int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                           long long n, cudaStream_t st);
@@ -114,6 +114,10 @@ int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, in
 int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                           const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
                           float* dlogscale_acc, int init, cudaStream_t st);
+int simt_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
+                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
+                               float* dB, float* dlogscale_acc, cudaStream_t st);
 int simt_dot_sum(const float* x, const float* y, long long n, float* out, cudaStream_t st);
 int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
                 float* loss_out, cudaStream_t st);

@@ -237,9 +237,18 @@ int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, voi
   return 0;
 }
 
+// `zero` (nullable, 16-byte aligned, zero_n4 float4 elements): a buffer this launch also clears -- the split-K output of
+// the weight-gradient contraction that follows it accumulates with reduce-adds and would otherwise need a fill launch.
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm, int B,
-                  int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub, __nv_bfloat16* __restrict__ dul) {
+                  int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub, __nv_bfloat16* __restrict__ dul,
+                  float4* __restrict__ zero, long long zero_n4) {
+  if (zero != nullptr) {
+    const long long per = (zero_n4 + gridDim.x - 1) / gridDim.x;
+    const long long z0 = per * blockIdx.x;
+    const long long z1 = z0 + per < zero_n4 ? z0 + per : zero_n4;
+    for (long long i = z0 + threadIdx.x; i < z1; i += 256) zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -261,10 +270,11 @@ l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
 }
 
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
-                    void* du_bf16_lo, cudaStream_t st) {
+                    void* du_bf16_lo, float* zero, long long zero_floats, cudaStream_t st) {
   if (B <= 0) return 0;
   l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16),
-                                                 reinterpret_cast<__nv_bfloat16*>(du_bf16_lo));
+                                                 reinterpret_cast<__nv_bfloat16*>(du_bf16_lo),
+                                                 reinterpret_cast<float4*>(zero), zero ? zero_floats / 4 : 0);
   MMG_LAUNCH_CHECK("l2norm_bwd_kernel");
   return 0;
 }
@@ -838,6 +848,79 @@ int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, c
   infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, diag, scale, rinv, cinvm, scal, dA, dB,
                                                           dlogscale_acc, init);
   MMG_LAUNCH_CHECK("infonce_bwd_diag_kernel");
+  return 0;
+}
+
+// prep + matching pair in one launch (the bf16 path always runs both): every block first fills its grid-stride share of
+// rinv[rows] / cinv[cols] / scal (what infonce_bwd_prep_kernel writes, for the contraction kernel that follows) and then
+// handles its eight pairs, forming their rinv / cinv on the fly from rowsum / colsum -- so the second half does not depend
+// on the first and needs no grid-wide ordering.  init = first-writer form only.
+__global__ void __launch_bounds__(256)
+infonce_bwd_prep_diag_kernel(const float* __restrict__ rowsum, int rows, const float* __restrict__ colsum, int cols,
+                             int diag_offset, const float* __restrict__ scale, const float* __restrict__ grad_loss,
+                             float inv_two_b, float* __restrict__ rinv, float* __restrict__ cinv, float* __restrict__ scal,
+                             const float* __restrict__ a32, const float* __restrict__ b32, int D,
+                             const float* __restrict__ diag, float* __restrict__ dA, float* __restrict__ dB,
+                             float* __restrict__ dlogscale_acc) {
+  const float s = *scale;
+  const float coef = s * (*grad_loss) * inv_two_b;
+  const int n = rows > cols ? rows : cols;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    if (i < rows) rinv[i] = coef / rowsum[i];
+    if (i < cols) cinv[i] = coef / colsum[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[0] = 0.f;           // the contraction subtracts nothing on the diagonal ...
+    scal[1] = 2.0f * coef;   // dcoef = s*gl/B
+    scal[2] = 1.f;           // ... it zeroes the matching-pair element of g: applied here in fp32
+    scal[3] = 0.f;
+  }
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float contrib = 0.f;
+  if (r < rows) {
+    const float lg = diag[r];
+    const float g = expf(lg - s) * (coef / rowsum[r] + coef / colsum[diag_offset + r]) - 2.0f * coef;
+    const float* ar = a32 + (long long)r * D;
+    const float* br = b32 + (long long)r * D;
+    float* dar = dA + (long long)r * D;
+    float* dbr = dB + (long long)r * D;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(ar) | reinterpret_cast<uintptr_t>(br) |
+                          reinterpret_cast<uintptr_t>(dar) | reinterpret_cast<uintptr_t>(dbr)) & 15) == 0) {
+      for (int i = lane * 4; i < D; i += 128) {
+        const float4 av = *reinterpret_cast<const float4*>(ar + i), bv = *reinterpret_cast<const float4*>(br + i);
+        *reinterpret_cast<float4*>(dar + i) = make_float4(g * bv.x, g * bv.y, g * bv.z, g * bv.w);
+        *reinterpret_cast<float4*>(dbr + i) = make_float4(g * av.x, g * av.y, g * av.z, g * av.w);
+      }
+    } else {
+      for (int i = lane; i < D; i += 32) {
+        dar[i] = g * br[i];
+        dbr[i] = g * ar[i];
+      }
+    }
+    contrib = g * (lg / s);
+  }
+  if (dlogscale_acc != nullptr) {  // uniform across the grid
+    __shared__ float wsum[8];
+    if (lane == 0) wsum[threadIdx.x >> 5] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += wsum[i];
+      atomicAdd(dlogscale_acc, t);
+    }
+  }
+}
+
+int simt_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
+                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
+                               float* dB, float* dlogscale_acc, cudaStream_t st) {
+  infonce_bwd_prep_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(rowsum, rows, colsum, cols, diag_offset, scale, grad_loss,
+                                                               inv_two_b, rinv, cinv, scal, a32, b32, D, diag, dA, dB,
+                                                               dlogscale_acc);
+  MMG_LAUNCH_CHECK("infonce_bwd_prep_diag_kernel");
   return 0;
 }
 

@@ -207,14 +207,14 @@ class _Operand:
 
 
 def gemm_heads(A: "_Operand", B: "_Operand", M: int, N: int, K: int, *, a_mn=False, b_mn=False, bias=None, relu=False,
-               k_splits: int = 1, prec: str = "bf16") -> torch.Tensor:
+               k_splits: int = 1, prec: str = "bf16", zeroed_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """alpha=1 contraction of head operands.  Split operands (hi, lo) contract as hi.hi + hi.lo + lo.hi in ONE launch over
     the concatenated K range (mmg_gemm_split); bias / ReLU ride in its epilogue."""
     if A.lo is None and B.lo is None:
         if k_splits > 1:
             if bias is not None or relu:
                 raise ValueError("bias/ReLU cannot be combined with split-K")
-            out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
+            out = zeroed_out if zeroed_out is not None else torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
             return gemm(A.hi, B.hi, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out, mode=MMG_ATOMIC_ADD, k_splits=k_splits,
                         prec=prec)
         return gemm(A.hi, B.hi, M, N, K, a_mn=a_mn, b_mn=b_mn, bias=bias, relu=relu, prec=prec)
@@ -231,7 +231,7 @@ def gemm_heads(A: "_Operand", B: "_Operand", M: int, N: int, K: int, *, a_mn=Fal
     if k_splits > 1:
         if bias is not None or relu:
             raise ValueError("bias/ReLU cannot be combined with split-K")
-        out = torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
+        out = zeroed_out if zeroed_out is not None else torch.zeros((M, N), dtype=torch.float32, device=A.hi.device)
         mode = MMG_ATOMIC_ADD
     else:
         out = torch.empty((M, N), dtype=torch.float32, device=A.hi.device)
@@ -301,16 +301,19 @@ def l2norm_fwd(u: torch.Tensor, want_bf16: bool) -> Tuple[torch.Tensor, torch.Te
 
 
 def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, want_f32: bool, want_bf16: bool,
-               want_lo: bool = False):
-    _need_cuda(dy, y, inv)
+               want_lo: bool = False, zero: Optional[torch.Tensor] = None):
+    """``zero``: an fp32 buffer (numel % 4 == 0) the same launch clears -- the split-K output of the contraction that follows."""
+    _need_cuda(dy, y, inv, zero)
     dy = dy.contiguous()
     B, D = y.shape
     du = torch.empty_like(y) if want_f32 else None
     dub = torch.empty((B, D), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
     dul = torch.empty((B, D), dtype=torch.bfloat16, device=y.device) if (want_bf16 and want_lo) else None
     if B > 0:
-        check(_lib.load().mmg_l2norm_bwd(_p(dy), _p(y), _p(inv), B, D, _p(du), _p(dub), _p(dul), _stream()),
-              "mmg_l2norm_bwd")
+        check(_lib.load().mmg_l2norm_bwd(_p(dy), _p(y), _p(inv), B, D, _p(du), _p(dub), _p(dul), _p(zero),
+                                         0 if zero is None else zero.numel(), _stream()), "mmg_l2norm_bwd")
+    elif zero is not None:
+        zero.zero_()
     if want_lo:
         return du, dub, dul
     return du, dub
@@ -417,22 +420,23 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
     diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None and diag is not None
-    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
-                                   int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
     if diag_fp32:
         # the fp32 matching-pair term is the FIRST writer of the gradient rows (no zero-fill, no read-modify-write);
         # the contraction kernels then accumulate on top.  Column rows without a local partner start from zero.
+        # The same launch writes rinv / cinv / scal (mmg_infonce_bwd_prep_diag).
         dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
         if cols == rows:
             dB = torch.empty((cols, D), dtype=torch.float32, device=dev)
         else:
             dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
         dBm = dB[diag_offset:diag_offset + rows]
-        cinvm = cinv[diag_offset:diag_offset + rows]
-        check(lib.mmg_infonce_bwd_diag(_p(a32), _p(b32), rows, D, _p(diag), _p(scale), _p(rinv), _p(cinvm), _p(scal),
-                                       _p(dA), _p(dBm), _p(dls), 1, _stream()), "mmg_infonce_bwd_diag")
+        check(lib.mmg_infonce_bwd_prep_diag(_p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
+                                            float(inv_two_b), _p(rinv), _p(cinv), _p(scal), _p(a32), _p(b32), D, _p(diag),
+                                            _p(dA), _p(dBm), _p(dls), _stream()), "mmg_infonce_bwd_prep_diag")
     else:
+        check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+                                       0, _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
         dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
         dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
     block_rows = block_rows or int(os.environ.get("MMGCLIP_B200_BLOCK_ROWS", "0"))
@@ -492,10 +496,19 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
     diag_fp32 = a32 is not None and b32 is not None and diag is not None
-    check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
-                                   int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
-    if diag_fp32:
+    if diag_fp32 and n_parts == 1:
+        # one launch: rinv / cinv / scal + the matching-pair term as first writer of dA and of this rank's own buffer
+        dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        check(lib.mmg_infonce_bwd_prep_diag(_p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
+                                            float(inv_two_b), _p(rinv), _p(cinv), _p(scal), _p(a32), _p(b32), D, _p(diag),
+                                            _p(dA), _p(parts[0][0]), _p(dls), _stream()), "mmg_infonce_bwd_prep_diag")
+    else:
+        check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+                                       int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
+    if diag_fp32 and n_parts == 1:
+        pass
+    elif diag_fp32:
         # the matching-pair term is the first writer of dA and of this rank's own buffers (part i = local rows
         # [i*rp, (i+1)*rp), whose partners are rows [0, rp) of the part's buffer)
         dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
@@ -674,9 +687,18 @@ class _ProjNormFn(torch.autograd.Function):
         prec = ctx.prec
         Bn, E, D = ctx.shape
         need_dx = ctx.needs_input_grad[0]
+        dw_buf = None
         if prec == "bf16":
             split = xo.lo is not None and (_split_dw or need_dx)
-            res = l2norm_bwd(dy, y, inv, False, True, want_lo=split)
+            ks = 1
+            if ctx.needs_input_grad[1]:
+                nseg = (1 + 2 * int(split)) if _split_dw else 1
+                ks = _split_k_for(D, E, Bn * nseg)
+                if ks > 1 and (D * E) % 4 == 0:
+                    # the split-K weight gradient accumulates with reduce-adds: its output is cleared by the normalise
+                    # backward launch that precedes it instead of a fill launch of its own
+                    dw_buf = torch.empty((D, E), dtype=torch.float32, device=dy.device)
+            res = l2norm_bwd(dy, y, inv, False, True, want_lo=split, zero=dw_buf)
             dz = _Operand(res[1], res[2] if split else None)
         else:
             dz = _Operand(l2norm_bwd(dy, y, inv, True, False)[0])
@@ -684,7 +706,8 @@ class _ProjNormFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             da, xa = _dw_operands(dz, xo)
             ks = _split_k_for(D, E, Bn * _n_segments(da, xa)) if prec == "bf16" else 1
-            dw = gemm_heads(da, xa, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks)
+            dw = gemm_heads(da, xa, D, E, Bn, a_mn=True, b_mn=True, prec=prec, k_splits=ks,
+                            zeroed_out=dw_buf if ks > 1 else None)
         if need_dx:
             dx = gemm_heads(dz, wo, Bn, E, D, b_mn=True, prec=prec)
         return dx, dw, None
