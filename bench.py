@@ -382,6 +382,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    if not args.pdl:
+        ops.set_tuning(pdl=0)
 
     B = args.batch
     if B % world:
@@ -849,6 +851,8 @@ def main():
                          "rank holds <= 8192 rows (launch-bound heads: 0.212 -> 0.184 ms/step at batch 4096), off above "
                          "(bandwidth-bound heads: no gain measured)")
     ap.add_argument("--no-head-overlap", dest="head_overlap", action="store_false")
+    ap.add_argument("--no-pdl", dest="pdl", action="store_false", default=True,
+                    help="A/B switch: launch without programmatic dependent launch (mmg_tune pdl=0)")
     ap.add_argument("--timeline", action="store_true",
                     help="diagnostic: record phase-boundary events in the step and dump them to gpurun_out/timeline_n<N>.json")
     ap.add_argument("--workload", default="clip", choices=["clip", "zeroshot"],

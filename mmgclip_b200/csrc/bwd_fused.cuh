@@ -377,6 +377,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();  // set-up done; see gemm_tc_kernel
 
   BwdCursor cur;
   cur.init(p, pair, pairs);

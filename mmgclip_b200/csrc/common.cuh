@@ -59,6 +59,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Programmatic dependent launch (see PdlAttr in kernels.h): let the next kernel of the stream be scheduled / wait for the
+// previous one to have completed with its writes visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 // ---------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------

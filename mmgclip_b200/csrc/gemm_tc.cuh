@@ -643,7 +643,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  // set-up done (nothing above touches global memory): the next kernel may be scheduled; from here on this one reads what
+  // its predecessor wrote
+  pdl_entry();
 
   const int real_tiles = p0.num_tiles() + p1.num_tiles();
   const int total_tiles = tail.rem_split > 1 ? tail.full_tiles + (real_tiles - tail.full_tiles) * tail.rem_split

@@ -13,6 +13,46 @@ int check_cuda(cudaError_t e, const char* what);
 // every kernel launch of the library is counted (mmg_kernel_launch_count)
 void count_launch();
 
+// Programmatic dependent launch (PDL).  The kernels of a training step form a chain on one stream; with the attribute below
+// a kernel may be SCHEDULED while its predecessor is still running: its CTAs run their prologue (barrier / TMEM set-up,
+// descriptor prefetch -- nothing that touches global memory) and then block in griddepcontrol.wait until the predecessor
+// grid has completed and its writes are visible.  Every kernel of the library that takes the attribute executes
+// griddepcontrol.wait before its first global access and before it exits, so completion stays transitive along the chain.
+// Captured into CUDA graphs as programmatic edges.  mmg_tune("pdl", 0) switches it off.
+bool pdl_enabled();
+struct PdlAttr {
+  cudaLaunchAttribute a[2];
+  unsigned n = 0;
+  PdlAttr() {
+    if (pdl_enabled()) {
+      a[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      a[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+  }
+  void cluster(int x) {
+    a[n].id = cudaLaunchAttributeClusterDimension;
+    a[n].val.clusterDim.x = x;
+    a[n].val.clusterDim.y = 1;
+    a[n].val.clusterDim.z = 1;
+    ++n;
+  }
+};
+
+// <<<grid, block, smem, st>>> with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  PdlAttr at;
+  cfg.attrs = at.a;
+  cfg.numAttrs = at.n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- tensor-core (bf16, tcgen05) launchers: tc_kernels.cu ----
 struct TcOperand {
   const void* ptr;   // bf16

@@ -22,6 +22,14 @@ namespace mmg {
     count_launch();                                    \
   } while (0)
 
+// launch with the programmatic-dependent-launch attribute (kernels.h); the kernel calls pdl_entry() first thing
+#define MMG_LAUNCH_PDL(what, kern, grid, block, smem, st, ...)                                        \
+  do {                                                                                                \
+    cudaError_t e__ = launch_pdl(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__);               \
+    if (e__ != cudaSuccess) return check_cuda(e__, what);                                             \
+    count_launch();                                                                                   \
+  } while (0)
+
 // =====================================================================================================
 // fp32 contraction  C[M,N] (op)= alpha * A . B^T (+bias)(ReLU)
 // 64x64 block tile, 16-deep K slab, 256 threads x (4x4) register micro-tile.
@@ -128,6 +136,7 @@ int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long
 // casts
 // =====================================================================================================
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
@@ -150,8 +159,29 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 // A_hi.B_hi + A_hi.B_lo + A_lo.B_hi on the bf16 tensor pipe is accurate to ~2^-17 per operand ("bf16x3").
 __global__ void cast_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+  long long done = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long j = i0; j < n4; j += stride) {
+      const float4 v = reinterpret_cast<const float4*>(x)[j];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                          h3 = __float2bfloat16_rn(v.w);
+      uint2 oh, ol;
+      oh.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      oh.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+      ol.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+      ol.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+      reinterpret_cast<uint2*>(hi)[j] = oh;
+      reinterpret_cast<uint2*>(lo)[j] = ol;
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + i0; i < n; i += stride) {
     const float v = x[i];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[i] = h;
@@ -168,16 +198,14 @@ static inline int ew_blocks(long long n, int per_thread) {
 
 int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
-  cast_split_kernel<<<ew_blocks(n, 2), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                     reinterpret_cast<__nv_bfloat16*>(lo), n);
-  MMG_LAUNCH_CHECK("cast_split_kernel");
+  MMG_LAUNCH_PDL("cast_split_kernel", cast_split_kernel, ew_blocks(n, 4), 256, 0, st, x, reinterpret_cast<__nv_bfloat16*>(hi),
+                 reinterpret_cast<__nv_bfloat16*>(lo), n);
   return 0;
 }
 
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
-  cast_bf16_kernel<<<ew_blocks(n, 4), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
-  MMG_LAUNCH_CHECK("cast_bf16_kernel");
+  MMG_LAUNCH_PDL("cast_bf16_kernel", cast_bf16_kernel, ew_blocks(n, 4), 256, 0, st, x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return 0;
 }
 
@@ -187,6 +215,7 @@ int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__ y, float* __restrict__ inv_norm,
                   __nv_bfloat16* __restrict__ yb) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -232,8 +261,7 @@ l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__
 
 int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st) {
   if (B <= 0) return 0;
-  l2norm_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(u, B, D, y, inv_norm, reinterpret_cast<__nv_bfloat16*>(y_bf16));
-  MMG_LAUNCH_CHECK("l2norm_fwd_kernel");
+  MMG_LAUNCH_PDL("l2norm_fwd_kernel", l2norm_fwd_kernel, (B + 7) / 8, 256, 0, st, u, B, D, y, inv_norm, reinterpret_cast<__nv_bfloat16*>(y_bf16));
   return 0;
 }
 
@@ -243,6 +271,7 @@ __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm, int B,
                   int D, float* __restrict__ du, __nv_bfloat16* __restrict__ dub, __nv_bfloat16* __restrict__ dul,
                   float4* __restrict__ zero, long long zero_n4) {
+  pdl_entry();
   if (zero != nullptr) {
     const long long per = (zero_n4 + gridDim.x - 1) / gridDim.x;
     const long long z0 = per * blockIdx.x;
@@ -272,10 +301,9 @@ l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
                     void* du_bf16_lo, float* zero, long long zero_floats, cudaStream_t st) {
   if (B <= 0) return 0;
-  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16),
+  MMG_LAUNCH_PDL("l2norm_bwd_kernel", l2norm_bwd_kernel, (B + 7) / 8, 256, 0, st, dy, y, inv_norm, B, D, du, reinterpret_cast<__nv_bfloat16*>(du_bf16),
                                                  reinterpret_cast<__nv_bfloat16*>(du_bf16_lo),
                                                  reinterpret_cast<float4*>(zero), zero ? zero_floats / 4 : 0);
-  MMG_LAUNCH_CHECK("l2norm_bwd_kernel");
   return 0;
 }
 
@@ -609,6 +637,7 @@ __device__ __forceinline__ double block_sum_1024(double v, int& bad) {
 __global__ void __launch_bounds__(1024)
 infonce_loss_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum, const float* __restrict__ diag,
                     int n, const float* __restrict__ scale, float inv_two_b, float* __restrict__ loss_out) {
+  pdl_entry();
   const float s = *scale;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int bad = 0;
@@ -625,8 +654,7 @@ infonce_loss_kernel(const float* __restrict__ rowsum, const float* __restrict__ 
 
 int simt_infonce_loss(const float* rowsum, const float* colsum, const float* diag, int n, const float* scale,
                       float inv_two_b, float* loss_out, cudaStream_t st) {
-  infonce_loss_kernel<<<1, 1024, 0, st>>>(rowsum, colsum, diag, n, scale, inv_two_b, loss_out);
-  MMG_LAUNCH_CHECK("infonce_loss_kernel");
+  MMG_LAUNCH_PDL("infonce_loss_kernel", infonce_loss_kernel, 1, 1024, 0, st, rowsum, colsum, diag, n, scale, inv_two_b, loss_out);
   return 0;
 }
 
@@ -639,6 +667,7 @@ int simt_infonce_loss(const float* rowsum, const float* colsum, const float* dia
 __global__ void __launch_bounds__(1024)
 infonce_row_part_kernel(const float* __restrict__ rowsum, const float* __restrict__ diag, int rows,
                         float* __restrict__ part_out) {
+  pdl_entry();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int bad = 0;
   int k = 0;
@@ -654,6 +683,7 @@ infonce_row_part_kernel(const float* __restrict__ rowsum, const float* __restric
 __global__ void __launch_bounds__(1024)
 infonce_loss_cols_kernel(const float* __restrict__ colsum, int cols, const float* __restrict__ scale,
                          const float* __restrict__ row_part, float inv_two_b, float* __restrict__ loss_out) {
+  pdl_entry();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int bad = 0;
   int k = 0;
@@ -670,15 +700,13 @@ infonce_loss_cols_kernel(const float* __restrict__ colsum, int cols, const float
 }
 
 int simt_infonce_row_part(const float* rowsum, const float* diag, int rows, float* part_out, cudaStream_t st) {
-  infonce_row_part_kernel<<<1, 1024, 0, st>>>(rowsum, diag, rows, part_out);
-  MMG_LAUNCH_CHECK("infonce_row_part_kernel");
+  MMG_LAUNCH_PDL("infonce_row_part_kernel", infonce_row_part_kernel, 1, 1024, 0, st, rowsum, diag, rows, part_out);
   return 0;
 }
 
 int simt_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
                            float* loss_out, cudaStream_t st) {
-  infonce_loss_cols_kernel<<<1, 1024, 0, st>>>(colsum, cols, scale, row_part, inv_two_b, loss_out);
-  MMG_LAUNCH_CHECK("infonce_loss_cols_kernel");
+  MMG_LAUNCH_PDL("infonce_loss_cols_kernel", infonce_loss_cols_kernel, 1, 1024, 0, st, colsum, cols, scale, row_part, inv_two_b, loss_out);
   return 0;
 }
 
@@ -686,6 +714,7 @@ __global__ void infonce_bwd_prep_kernel(const float* __restrict__ rowsum, int ro
                                         int cols, const float* __restrict__ scale, const float* __restrict__ grad_loss,
                                         float inv_two_b, int diag_in_fp32, float* __restrict__ rinv,
                                         float* __restrict__ cinv, float* __restrict__ scal) {
+  pdl_entry();
   const float coef = (*scale) * (*grad_loss) * inv_two_b;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows) rinv[i] = coef / rowsum[i];
@@ -702,9 +731,8 @@ int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, in
                           const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                           float* scal, cudaStream_t st) {
   const int n = rows > cols ? rows : cols;
-  infonce_bwd_prep_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b,
+  MMG_LAUNCH_PDL("infonce_bwd_prep_kernel", infonce_bwd_prep_kernel, (n + 255) / 256, 256, 0, st, rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b,
                                                            diag_in_fp32, rinv, cinv, scal);
-  MMG_LAUNCH_CHECK("infonce_bwd_prep_kernel");
   return 0;
 }
 
@@ -794,6 +822,7 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
                         const float* __restrict__ rinv, const float* __restrict__ cinvm,
                         const float* __restrict__ scal, float* __restrict__ dA, float* __restrict__ dB,
                         float* __restrict__ dlogscale_acc, int init) {
+  pdl_entry();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const float s = *scale;
@@ -845,9 +874,8 @@ int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, c
                           const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
                           float* dlogscale_acc, int init, cudaStream_t st) {
   if (rows <= 0) return 0;
-  infonce_bwd_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a32, b32, rows, D, diag, scale, rinv, cinvm, scal, dA, dB,
+  MMG_LAUNCH_PDL("infonce_bwd_diag_kernel", infonce_bwd_diag_kernel, (rows + 7) / 8, 256, 0, st, a32, b32, rows, D, diag, scale, rinv, cinvm, scal, dA, dB,
                                                           dlogscale_acc, init);
-  MMG_LAUNCH_CHECK("infonce_bwd_diag_kernel");
   return 0;
 }
 
@@ -862,6 +890,7 @@ infonce_bwd_prep_diag_kernel(const float* __restrict__ rowsum, int rows, const f
                              const float* __restrict__ a32, const float* __restrict__ b32, int D,
                              const float* __restrict__ diag, float* __restrict__ dA, float* __restrict__ dB,
                              float* __restrict__ dlogscale_acc) {
+  pdl_entry();
   const float s = *scale;
   const float coef = s * (*grad_loss) * inv_two_b;
   const int n = rows > cols ? rows : cols;
@@ -917,10 +946,9 @@ int simt_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsu
                                const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
                                float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
                                float* dB, float* dlogscale_acc, cudaStream_t st) {
-  infonce_bwd_prep_diag_kernel<<<(rows + 7) / 8, 256, 0, st>>>(rowsum, rows, colsum, cols, diag_offset, scale, grad_loss,
+  MMG_LAUNCH_PDL("infonce_bwd_prep_diag_kernel", infonce_bwd_prep_diag_kernel, (rows + 7) / 8, 256, 0, st, rowsum, rows, colsum, cols, diag_offset, scale, grad_loss,
                                                                inv_two_b, rinv, cinv, scal, a32, b32, D, diag, dA, dB,
                                                                dlogscale_acc);
-  MMG_LAUNCH_CHECK("infonce_bwd_prep_diag_kernel");
   return 0;
 }
 

@@ -183,13 +183,10 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMa
   cfg.blockDim = dim3(32 * (4 + Epi::kWarps));
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  PdlAttr at;
+  at.cluster(kCG);
+  cfg.attrs = at.a;
+  cfg.numAttrs = at.n;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, b0, a1, b1, c0, c1, p0, p1, tail, e0, e1);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc_kernel launch");
   count_launch();
@@ -383,14 +380,14 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
 // Plan knobs of the fused backward (fused on/off, block shape, scratch buffers, slice lengths, block order): process-wide
 // overrides set through mmg_tune() -- the tests walk other schedules with it; unset = the measured defaults.  Every value
 // gives correct results.  Measurement builds also honour the MMG_* environment variables of the same names.
-enum TuneKey { kTuneFused, kTuneRb, kTuneCb, kTuneNbuf, kTuneKsl, kTuneKslT, kTuneSr, kTuneSc, kTuneHints, kTuneRot, kTuneCount };
+enum TuneKey { kTuneFused, kTuneRb, kTuneCb, kTuneNbuf, kTuneKsl, kTuneKslT, kTuneSr, kTuneSc, kTuneHints, kTuneRot, kTunePdl, kTuneCount };
 static const char* const kTuneNames[kTuneCount] = {"fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl",
-                                                   "fused_ksl_t", "fused_sr", "fused_sc", "fused_hints", "fused_rot"};
+                                                   "fused_ksl_t", "fused_sr", "fused_sc", "fused_hints", "fused_rot", "pdl"};
 static const char* const kTuneEnv[kTuneCount] = {"MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF",
                                                  "MMG_FUSED_KSL", "MMG_FUSED_KSL_T", "MMG_FUSED_SR", "MMG_FUSED_SC",
-                                                 "MMG_FUSED_HINTS", "MMG_FUSED_ROT"};
+                                                 "MMG_FUSED_HINTS", "MMG_FUSED_ROT", "MMG_PDL"};
 static std::mutex g_tune_mu;
-static int g_tune[kTuneCount] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // -1 = unset
+static int g_tune[kTuneCount] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // -1 = unset
 
 int tc_tune(const char* key, int value) {
   if (key == nullptr) return set_error(-1, "mmg_tune: key is NULL");
@@ -416,6 +413,8 @@ static int tune_int(TuneKey k, int dflt) {
   if (v >= 0) return v;
   return measure_env(kTuneEnv[k], dflt);
 }
+
+bool pdl_enabled() { return tune_int(kTunePdl, 1) != 0; }
 
 struct FusedPlan {
   int ok, Rb, Cb, nbuf, kslI, kslT;
@@ -656,13 +655,10 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   cfg.blockDim = dim3(32 * (4 + ew + (stored ? kStoredTW : 0)));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  PdlAttr at;
+  at.cluster(2);
+  cfg.attrs = at.a;
+  cfg.numAttrs = at.n;
   // (An L2 persisting access-policy window on the coefficient scratch was tried and is much slower -- 4.1 vs 2.65 ms at
   // 32768^2 -- and the device-wide set-aside also slows every later kernel of the process; not used.)
   e = cudaLaunchKernelEx(&cfg, kern, mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA, mdB, p);

@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU call 11 (1 GPU): programmatic dependent launch -- suite, then A/B at cfg 2 and N=1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/c11_pytest.log 2>&1
+tail -4 gpurun_out/c11_pytest.log
+F="--no-cpu-baseline --no-gpu-eager --no-kernel-breakdown"
+for pdl in "" "--no-pdl"; do
+timeout 120 python bench.py --batch 4096 --steps 100 --warmup 10 $F $pdl > gpurun_out/c11_cfg2$pdl.json 2> gpurun_out/c11_cfg2$pdl.err
+timeout 120 python bench.py --steps 20 --warmup 5 $F $pdl > gpurun_out/c11_n1$pdl.json 2> gpurun_out/c11_n1$pdl.err
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/c11_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1]); print(f, d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"], d["gpu_launches"], d["clocks"]["sm_mhz"], d["parity"]["ok"], d["parity"]["loss_rel_err"], d["parity"]["dw_image"])
+    except Exception as e: print(f, "ERR", e)
+PY
+tail -n 3 gpurun_out/c11_*.err
