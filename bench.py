@@ -366,7 +366,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from mmgclip_b200 import _lib, ops
     from mmgclip_b200.distributed import (allreduce_gradients, gather_columns_async, peer_reduce_active,
-                                          sharded_info_nce, symm_allreduce_active)
+                                          push_gather_active, sharded_info_nce, symm_allreduce_active)
     from mmgclip_b200.projection import LinearProjectionLayer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -660,7 +660,10 @@ def run_gpu(args):
         "config": dict(workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active(),
                                        symm=symm_allreduce_active(), stored_e=stored_e),
                        heads="the two heads run on two streams (forward and backward)" if side is not None
-                       else "the two heads run back to back on one stream"),
+                       else "the two heads run back to back on one stream",
+                       gather=("push over NVLink peer memory (mmg_push_rows into every rank's symmetric buffer + barrier) on a "
+                               "communication stream" if push_gather_active() else
+                               ("NCCL all-gather (asynchronous)" if world > 1 else "none (one GPU)"))),
         "loss": loss_value,
         "parity": parity,
         "clocks": clocks,

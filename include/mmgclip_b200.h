@@ -78,6 +78,13 @@ int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t
  * keeps the projection heads fp32-faithful (~2^-17 per operand) on the bf16 tensor pipe. */
 int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, long long n, mmg_stream_t stream);
 
+/* Push all-gather (multi-GPU exchange step 1): copy `bytes` bytes from `src` to dst_ptrs[i] + dst_offset_bytes
+ * for every i < n_dst (<= 8).  dst_ptrs is a HOST array of device pointers -- this rank's and its peers' symmetric buffers
+ * mapped into this process (NVLink peer memory); with dst_offset_bytes = rank * bytes and a cross-rank barrier afterwards
+ * every rank holds all shards.  src, offset and length are multiples of 16 bytes.  The reference has no multi-GPU code. */
+int mmg_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n_dst, long long dst_offset_bytes,
+                  mmg_stream_t stream);
+
 /* Row-wise L2 normalisation y = u / ||u||_2, no epsilon (mmgclip/networks/mmgclip_model.py:128-129,163;
  * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_bf16 (nullable) receives a bf16 copy. */
 int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream);

@@ -33,6 +33,7 @@ SIGNATURES = {
                                c_longlong, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mmg_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_cast_f32_to_bf16_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "mmg_push_rows": (c_int, [c_void_p, c_longlong, POINTER(c_void_p), c_int, c_longlong, c_void_p]),
     "mmg_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmg_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_longlong, c_void_p]),

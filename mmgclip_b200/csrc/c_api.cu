@@ -146,6 +146,20 @@ int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, lon
   return simt_cast_split(x, hi_bf16, lo_bf16, n, static_cast<cudaStream_t>(stream));
 }
 
+int mmg_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n_dst, long long dst_offset_bytes,
+                  mmg_stream_t stream) {
+  if (bytes < 0 || n_dst < 1 || n_dst > 8 || dst_offset_bytes < 0 || dst_ptrs == nullptr)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_push_rows: bad arguments (bytes %lld, %d destinations)", bytes, n_dst);
+  if (bytes == 0) return 0;
+  MMG_REQ(src);
+  if ((bytes & 15) != 0 || (dst_offset_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0)
+    return set_error(MMG_ERR_BAD_ALIGN, "mmg_push_rows: source, offset and length must be multiples of 16 bytes");
+  for (int i = 0; i < n_dst; ++i)
+    if (dst_ptrs[i] == nullptr || (reinterpret_cast<uintptr_t>(dst_ptrs[i]) & 15) != 0)
+      return set_error(MMG_ERR_BAD_ALIGN, "mmg_push_rows: destination %d is NULL or not 16-byte aligned", i);
+  return simt_push_rows(src, bytes, dst_ptrs, n_dst, dst_offset_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream) {
   if (B < 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_fwd: bad shape %dx%d", B, D);
   if (B == 0) return 0;

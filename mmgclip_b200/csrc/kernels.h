@@ -115,6 +115,8 @@ int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
 int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st);
 int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
+int simt_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n_dst, long long dst_offset_bytes,
+                   cudaStream_t st);
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
                     void* du_bf16_lo, float* zero, long long zero_floats, cudaStream_t st);
 int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st);

@@ -210,6 +210,53 @@ int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st) {
 }
 
 // =====================================================================================================
+// push all-gather: copy a contiguous block of rows into the same place of up to 8 destination buffers (this rank's and its
+// peers' symmetric buffers, mapped over NVLink) -- 16-byte loads, one 16-byte store per destination.  Followed by a
+// cross-rank barrier this IS the all-gather of the column-side embeddings: every rank receives world-1 shards at NVLink
+// line rate with no protocol, and the copy is one launch inside the step's graph.
+// =====================================================================================================
+struct PushDst {
+  void* p[8];
+};
+
+// A few CTAs per destination (NCCL-like footprint: the copy shares the GPU with the other head's projection, and a
+// handful of SMs saturates a link): CTA b serves destination b % n_dst, stripe b / n_dst of kPushStripes.
+constexpr int kPushStripes = 4;
+constexpr int kPushThreads = 512;
+
+__global__ void __launch_bounds__(kPushThreads)
+push_rows_kernel(const uint4* __restrict__ src, long long n16, const __grid_constant__ PushDst dst, int n_dst,
+                 long long dst_off16) {
+  pdl_entry();
+  const int d = blockIdx.x % n_dst;
+  const int stripe = blockIdx.x / n_dst;
+  const long long per = (n16 + kPushStripes - 1) / kPushStripes;
+  const long long i0 = per * stripe;
+  const long long i1 = i0 + per < n16 ? i0 + per : n16;
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(dst.p[d]) + dst_off16;
+  long long i = i0 + threadIdx.x;
+  // four independent 16-byte loads in flight per thread
+  for (; i + 3 * kPushThreads < i1; i += 4 * kPushThreads) {
+    const uint4 v0 = src[i], v1 = src[i + kPushThreads], v2 = src[i + 2 * kPushThreads], v3 = src[i + 3 * kPushThreads];
+    out[i] = v0;
+    out[i + kPushThreads] = v1;
+    out[i + 2 * kPushThreads] = v2;
+    out[i + 3 * kPushThreads] = v3;
+  }
+  for (; i < i1; i += kPushThreads) out[i] = src[i];
+}
+
+int simt_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n_dst, long long dst_offset_bytes,
+                   cudaStream_t st) {
+  PushDst d;
+  for (int i = 0; i < 8; ++i) d.p[i] = i < n_dst ? dst_ptrs[i] : nullptr;
+  const long long n16 = bytes / 16;
+  MMG_LAUNCH_PDL("push_rows_kernel", push_rows_kernel, n_dst * kPushStripes, kPushThreads, 0, st,
+                 reinterpret_cast<const uint4*>(src), n16, d, n_dst, dst_offset_bytes / 16);
+  return 0;
+}
+
+// =====================================================================================================
 // row L2 normalise (one warp per row, float4 loads, shuffle reduction)
 // =====================================================================================================
 __global__ void __launch_bounds__(256)

@@ -70,6 +70,83 @@ class _PeerBuffers:
         self.handle.barrier(channel=1)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Push all-gather of the column-side embeddings: every rank owns a ring of [B, D] bf16 buffers in symmetric memory; a rank
+# copies its shard straight into the same rows of every rank's buffer (mmg_push_rows: one launch, NVLink line rate, no
+# protocol) and a cross-rank barrier follows.  Both run on a communication stream, so the gather overlaps the other head's
+# projection exactly like the asynchronous NCCL all-gather it replaces (8 x B200, 4 MiB shards: NCCL 86 us from the end of
+# the text head to the gathered matrix).  A ring slot is reused only after the loss that read it has issued its backward
+# (or, without gradients, its forward): the collectives inside those (column-sum all-reduce, peer reduction barriers /
+# reduce-scatter) order every peer's last read of the slot before this rank's next push into it.  A busy ring, a non-bf16
+# operand, a non-NCCL backend or MMGCLIP_B200_PUSH_GATHER=0 select the NCCL all-gather.
+# ---------------------------------------------------------------------------------------------------------------------
+_gather_rings = {}
+_comm_streams = {}
+
+
+class _GatherSlot:
+    def __init__(self, buf, handle):
+        self.buf, self.handle = buf, handle
+        self.ptrs = [int(p) for p in handle.buffer_ptrs]
+        self.busy = False
+        self.gen = 0  # bumped by every acquire: a stale release (a finalizer of an old loss) must not free a newer gather
+
+    def release(self, gen):
+        if gen == self.gen:
+            self.busy = False
+
+
+class _GatherRing:
+    RING = 4
+
+    def __init__(self, B, D, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.slots = []
+        for _ in range(self.RING):
+            buf = symm_mem.empty((B, D), dtype=torch.bfloat16, device=device)
+            self.slots.append(_GatherSlot(buf, symm_mem.rendezvous(buf, group=grp)))
+        self.i = -1
+
+    def acquire(self):
+        """The next slot in ring order, or None while it is still being read (the same decision on every rank: the ranks
+        run the same program)."""
+        nxt = (self.i + 1) % self.RING
+        slot = self.slots[nxt]
+        if slot.busy:
+            return None
+        self.i = nxt
+        slot.busy = True
+        slot.gen += 1
+        return slot
+
+
+def _gather_ring(B, D, device, group):
+    if os.environ.get("MMGCLIP_B200_PUSH_GATHER", "1") == "0" or device.type != "cuda":
+        return None
+    if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 8 or (D * 2) % 16 != 0:
+        return None
+    key = (B, D, device.index, id(group))
+    if key not in _gather_rings:
+        try:
+            _gather_rings[key] = _GatherRing(B, D, device, group)
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"mmgclip_b200: push all-gather unavailable ({e}); using the NCCL all-gather")
+            _gather_rings[key] = None
+    return _gather_rings[key]
+
+
+def push_gather_active() -> bool:
+    return any(v is not None for v in _gather_rings.values())
+
+
+def _comm_stream(device):
+    st = _comm_streams.get(device.index)
+    if st is None:
+        st = _comm_streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
 # stored-E (ops.want_store_e) in the sharded loss: opt-in until measured on several GPUs
 _STORE_E_DIST = os.environ.get("MMGCLIP_B200_STORE_E_DIST", "0") == "1"
 
@@ -182,14 +259,25 @@ class _Kernels:
 class GatheredColumns:
     """Column-side embeddings being all-gathered in the background (see :func:`gather_columns_async`)."""
 
-    def __init__(self, local, b_all, work):
-        self.local, self.b_all, self.work = local, b_all, work
+    def __init__(self, local, b_all, work=None, event=None, slot=None):
+        self.local, self.b_all, self.work, self.event, self.slot = local, b_all, work, event, slot
+        self.gen = slot.gen if slot is not None else 0
 
     def wait(self):
+        """Make the current stream wait for the gathered matrix (no host sync)."""
         if self.work is not None:
-            self.work.wait()  # the current stream waits for the collective; no host sync
+            self.work.wait()
             self.work = None
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+            self.event = None
         return self.b_all
+
+    def release(self):
+        """The gathered matrix will not be read any more (its ring slot may take the next gather)."""
+        if self.slot is not None:
+            self.slot.release(self.gen)
+            self.slot = None
 
 
 def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] = None, _kernels=None):
@@ -201,9 +289,23 @@ def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] 
         return None
     world = dist.get_world_size(group)
     b_op = kernels.operand(b_local, prec).contiguous()
-    b_all = torch.empty((b_op.shape[0] * world, b_op.shape[1]), dtype=b_op.dtype, device=b_op.device)
+    bl, D = b_op.shape
+    if kernels is _Kernels and b_op.is_cuda and b_op.dtype == torch.bfloat16:
+        ring = _gather_ring(bl * world, D, b_op.device, group)
+        slot = ring.acquire() if ring is not None else None
+        if slot is not None:
+            comm = _comm_stream(b_op.device)
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                ops.push_rows(b_op, slot.ptrs, dist.get_rank(group) * bl * D * 2)
+                slot.handle.barrier(channel=0)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            b_op.record_stream(comm)
+            return GatheredColumns(b_local, slot.buf, event=ev, slot=slot)
+    b_all = torch.empty((bl * world, D), dtype=b_op.dtype, device=b_op.device)
     work = dist.all_gather_into_tensor(b_all, b_op, group=group, async_op=True)
-    return GatheredColumns(b_local, b_all, work)
+    return GatheredColumns(b_local, b_all, work=work)
 
 
 class _ShardedInfoNCEFn(torch.autograd.Function):
@@ -220,13 +322,11 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         B = bl * world
         s = scale.detach().reshape(()).to(device=a_local.device, dtype=torch.float32).contiguous()
         a_op = kernels.operand(a_local, prec)
-        if gathered is not None and (gathered.local is b_local or gathered.local is b_key):
-            b_all = gathered.wait()
-            ops.mark("gather_wait")
-        else:
-            b_op = kernels.operand(b_local, prec)
-            b_all = torch.empty((B, D), dtype=b_op.dtype, device=b_op.device)
-            dist.all_gather_into_tensor(b_all, b_op.contiguous(), group=group)
+        if gathered is None or not (gathered.local is b_local or gathered.local is b_key):
+            gathered = gather_columns_async(b_local if b_key is None else b_key, group=group, prec=prec, _kernels=kernels)
+        b_all = gathered.wait()
+        ops.mark("gather_wait")
+        ctx.gathered = gathered
         off = rank * bl
         # stored-E (ops.want_store_e) for the sharded loss: opt-in (MMGCLIP_B200_STORE_E_DIST=1) until it has been measured
         # on several GPUs; only with the peer-memory backward, which is the one that reaches mmg_infonce_bwd_stored
@@ -258,6 +358,15 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         loss = kernels.loss_cols(colsum, s, part, 0.5 / B)
         ctx.group, ctx.prec, ctx.kernels, ctx.off, ctx.B = group, prec, kernels, off, B
         ctx.scale_shape = scale.shape
+        if not any(ctx.needs_input_grad[:3]):
+            gathered.release()  # forward only: the column-sum all-reduce above ordered every rank's read of the slot
+        elif gathered.slot is not None:
+            # a loss that never runs its backward must not pin the ring: free the slot when the autograd node dies
+            try:
+                import weakref
+                weakref.finalize(ctx, gathered.slot.release, gathered.gen)
+            except TypeError:
+                pass  # not weak-referenceable on this torch: the ring then falls back to NCCL once it is full
         ctx.save_for_backward(a_op, b_all, s, rowsum, colsum, a_local.detach(), b_local.detach(), diag)
         return loss
 
@@ -265,6 +374,7 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
     def backward(ctx, grad_loss):
         a_op, b_all, s, rowsum, colsum, a32, b32_local, diag = ctx.saved_tensors
         group, prec, kernels = ctx.group, ctx.prec, ctx.kernels
+        gathered, ctx.gathered = ctx.gathered, None
         bl, D = a_op.shape
         # fp32 embeddings for the matching-pair term: the columns paired with this rank's rows are its own b rows
         if not (prec == "bf16" and a32.dtype == torch.float32):
@@ -282,6 +392,8 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             ctx.e_mat = None
             dB = owns[0].clone() if ctx.private_db else owns[0]  # a ring slot (see _PeerBuffers) unless it may be kept
             ops.mark("clone")
+            if gathered is not None:
+                gathered.release()  # the peer reduction's closing barrier ordered every rank's last read of the slot
             dscale = None
             if ctx.needs_input_grad[2]:
                 dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)
@@ -299,6 +411,8 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             pending["keep"] = dB_all  # stays referenced until the wait
         else:
             _reduce_scatter_sum(dB, dB_all, group)
+        if gathered is not None:
+            gathered.release()  # the reduce-scatter issued above orders every rank's last read of the slot
         dscale = None
         if ctx.needs_input_grad[2]:
             dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)

@@ -376,6 +376,18 @@ def infonce_loss_raw(rowsum, colsum_slice, diag, scale, inv_two_b: float) -> tor
     return out
 
 
+def push_rows(src: torch.Tensor, dst_ptrs, dst_offset_bytes: int) -> None:
+    """Copy the contiguous tensor ``src`` to ``dst_ptrs[i] + dst_offset_bytes`` for every destination (mmg_push_rows): the
+    push half of the all-gather over NVLink peer memory (``dst_ptrs``: device pointers of every rank's symmetric buffer)."""
+    _need_cuda(src)
+    if not src.is_contiguous():
+        raise ValueError("push_rows expects a contiguous source")
+    n = len(dst_ptrs)
+    ptrs = (ctypes.c_void_p * n)(*[int(x) for x in dst_ptrs])
+    check(_lib.load().mmg_push_rows(_p(src), src.numel() * src.element_size(), ptrs, n, int(dst_offset_bytes), _stream()),
+          "mmg_push_rows")
+
+
 def infonce_row_part_raw(rowsum, diag, out=None) -> torch.Tensor:
     """out[0] = sum_r (log rowsum[r] - 2*diag[r]) over the local rows (mmg_infonce_row_part): the part of the sharded loss
     that is known before the exchange.  ``out``: a 1-element fp32 view to write into (e.g. the tail of the symmetric

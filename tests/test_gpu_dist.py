@@ -30,6 +30,13 @@ def test_two_ranks_equal_one_rank(peer):
     _run(2, 29611 + int(peer), {"MMGCLIP_B200_PEER_REDUCE": peer})
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs")
+def test_two_ranks_nccl_all_gather_fallback():
+    """MMGCLIP_B200_PUSH_GATHER=0: the column-side embeddings travel by the NCCL all-gather instead of the push over NVLink
+    peer memory."""
+    _run(2, 29614, {"MMGCLIP_B200_PUSH_GATHER": "0"})
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs at least four GPUs")
 def test_all_ranks_of_the_box_equal_one_rank():
     _run(torch.cuda.device_count(), 29617)
