@@ -71,11 +71,6 @@ struct BwdFusedParams {
   const void* E;
   long long ldE;
   void* G;                // coefficient scratch [nbuf * Rb, Cb] bf16 (the stored-E transform writes it with plain stores)
-  // L2 eviction-priority hints (bit mask, mmg_tune "fused_hints"): 1 = coefficient stores evict_last, 2 = coefficient loads
-  // of the dA slices evict_last, 4 = coefficient loads of the dB slices (the last reader) evict_first, 8 = embedding operand
-  // loads of the coefficient tiles evict_first, 16 = dA reduce-adds evict_last, 32 = dB reduce-adds evict_first,
-  // 64 = coefficient loads of the dB slices evict_last
-  int hints;
   // Debug timeline (MMG_FUSED_TRACE=1; NULL otherwise): per CTA and role kTraceCap records {globaltimer ns, tag}, see
   // trace_event().  Read back by tests/gpu_stored_e_probe.py trace.
   unsigned long long* trace;
@@ -124,11 +119,6 @@ __device__ __forceinline__ void trace_event(unsigned long long* trace, int role,
            (static_cast<unsigned long long>(type) << 52) | (static_cast<unsigned long long>(blk & 0xfffff) << 32) |
            (static_cast<unsigned long long>(tm & 0xffff) << 16) | static_cast<unsigned long long>(tn & 0xffff);
   ++n;
-}
-
-constexpr int kFusedHintsDefault = 0;
-__device__ __forceinline__ uint64_t hint_policy(int hints, int last_bit, int first_bit) {
-  return (hints & last_bit) ? kEvictLast : ((hints & first_bit) ? kEvictFirst : kEvictNormal);
 }
 
 constexpr int kMaxOwners = 8;
@@ -309,6 +299,9 @@ __device__ __forceinline__ void stored_e_rows(const BwdFusedParams& p, const uin
 // kTW = transform warps of the stored-E mode (0 = recompute mode): warps 4 + kEW .. 4 + kEW + kTW - 1.
 // kTrace compiles the debug timeline in (measurement builds only, -DMMG_MEASURE + MMG_FUSED_TRACE=1; the product library
 // carries none of it).
+// L2 eviction-priority hints (evict_last on the coefficient scratch stores / loads, evict_first on its last reader and on the
+// streamed operands, hints on the reduce-add targets) were swept in round 2 (profiles/r02b_fused_hint_plan_sweep.log): equal
+// at best, evict_last on the scratch loads 2.74 -> 3.17-3.85 ms -- every load keeps the default policy.
 // Variants that were built, measured on hardware and deleted because they did not win (numbers in DESIGN.md s4.2): per-panel
 // instead of per-block doneA counters (2.60 vs 2.61 ms at 32768^2, 0.352 vs 0.355 ms at 4096 x 32768; stored-E 2.51 vs
 // 2.41 ms), a deferred publish of the stored-E tiles (2.51 vs 2.41 ms), sixteen transform warps (2.44 vs 2.41 ms), 128-column
@@ -391,9 +384,6 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     uint32_t phase = 0;
     int verified = -1;  // blocks [0, verified] are known to have all their coefficient tiles in the scratch
     int ntr = 0;
-    const uint64_t pol_op = hint_policy(p.hints, 0, 8);
-    const uint64_t pol_gi = hint_policy(p.hints, 2, 0);
-    const uint64_t pol_gt = hint_policy(p.hints, 64, 4);
     while (cur.next(p, it)) {
       if (kStoredE && it.type == 0) continue;  // no tensor-core work: the epilogue warps transform E
       int rb, cbl;
@@ -417,11 +407,11 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
           uint8_t* b_dst = sB + stage * S::kBBytes;
           const int k0 = (it.kb0 + kb) * kBK;
           if (it.type == 0) {
-            tma_load_2d_cg2(&mAk, &full_bar[stage], a_dst, k0, rb * p.Rb + it.tm * 256 + half_off, pol_op);
-            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, col0 + it.tn * BN + n_half, pol_op);
+            tma_load_2d_cg2(&mAk, &full_bar[stage], a_dst, k0, rb * p.Rb + it.tm * 256 + half_off, kEvictNormal);
+            tma_load_2d_cg2(&mBk, &full_bar[stage], b_dst, k0, col0 + it.tn * BN + n_half, kEvictNormal);
           } else if (it.type == 1) {
             // dA[rows] += g . b[cols]:  A = g (K-major, K = block columns),  B = b (MN-major: [K = column index][N = D])
-            tma_load_2d_cg2(&mGk, &full_bar[stage], a_dst, k0, buf * p.Rb + it.tm * 256 + half_off, pol_gi);
+            tma_load_2d_cg2(&mGk, &full_bar[stage], a_dst, k0, buf * p.Rb + it.tm * 256 + half_off, kEvictNormal);
             const int n0 = it.tn * BN + n_half;
 #pragma unroll
             for (int i = 0; i < kBHalf / 64; ++i)
@@ -432,7 +422,7 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
             const int n0 = it.tn * BN + n_half;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              tma_load_2d_cg2(&mGmn, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, buf * p.Rb + k0, pol_gt);
+              tma_load_2d_cg2(&mGmn, &full_bar[stage], a_dst + i * (kBK * 128), m0 + i * 64, buf * p.Rb + k0, kEvictNormal);
 #pragma unroll
             for (int i = 0; i < kBHalf / 64; ++i)
               tma_load_2d_cg2(&mAmn, &full_bar[stage], b_dst + i * (kBK * 128), n0 + i * 64, rb * p.Rb + k0, kEvictNormal);
@@ -503,11 +493,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int ntr = 0;
     typename FusedGrad::Params gp;
     gp.scale_ptr = p.scale; gp.scal = p.scal; gp.dlogscale_acc = p.dlogscale_acc; gp.dbg = 0;
-    gp.st_policy = (p.hints & 1) ? kEvictLast : 0ull;
     typename FusedStore::Params sp;
     sp.C = nullptr; sp.ldc = 0; sp.bias = nullptr; sp.alpha = 1.f; sp.alpha_ptr = nullptr; sp.mode = 1; sp.relu = 0;
-    sp.use_tma = 1; sp.out_policy = 0ull;
-    const unsigned long long pol_da = (p.hints & 16) ? kEvictLast : 0ull, pol_db = (p.hints & 32) ? kEvictFirst : 0ull;
+    sp.use_tma = 1;
     while (cur.next(p, it)) {
       if (pending >= 0) {
         // publish the previous coefficient tile (deferred to here so the stores' latency is off the critical path, and
@@ -546,7 +534,6 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         if (ewarp == 0 && leader && lane == 0) red_release_gpu_add(p.doneB + it.blk, 1u);
         int m0 = (it.type == 1 ? rb * p.Rb : col0) + it.tm * 256 + half_off;
         const CUtensorMap* cmap = &mdA;
-        sp.out_policy = it.type == 1 ? pol_da : pol_db;
         if (it.type == 2) {
           // the owner of these 128 gradient rows (owner_rows is a multiple of 256: a tile never straddles owners); a
           // remote owner's buffer is reached by the same TMA reduce-add, over NVLink

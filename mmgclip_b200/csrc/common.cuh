@@ -170,22 +170,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
                : "memory");
 }
-// the same two with an L2 eviction-priority hint (kEvictFirst / kEvictLast) for the lines they write
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src, int c_inner, int c_outer,
-                                                  uint64_t hint) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer), "l"(hint)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* m, const void* smem_src, int c_inner,
-                                                       int c_outer, uint64_t hint) {
-  asm volatile(
-      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
-          reinterpret_cast<uint64_t>(m)),
-      "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer), "l"(hint)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores issued by this thread have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

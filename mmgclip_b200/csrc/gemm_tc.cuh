@@ -131,7 +131,6 @@ struct EpiStoreF32T {
     int mode;           // 0: C = v   1: C += v (exclusive owner)   2: red.add (split-K)
     int relu;
     int use_tma;        // output goes through TMA store / reduce-add (needs 16-byte aligned C and pitch)
-    unsigned long long out_policy;  // L2 eviction hint of the TMA store / reduce-add (0 = none)
   };
   static constexpr int kWarps = kW;
   static constexpr int kScratchBytes = 0;
@@ -176,14 +175,8 @@ struct EpiStoreF32T {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (P.out_policy != 0ull) {
-          if (P.mode == 0) tma_store_2d_hint(cmap, box, c0, m0 + q * 32, P.out_policy);
-          else tma_reduce_add_2d_hint(cmap, box, c0, m0 + q * 32, P.out_policy);
-        } else if (P.mode == 0) {
-          tma_store_2d(cmap, box, c0, m0 + q * 32);
-        } else {
-          tma_reduce_add_2d(cmap, box, c0, m0 + q * 32);
-        }
+        if (P.mode == 0) tma_store_2d(cmap, box, c0, m0 + q * 32);
+        else tma_reduce_add_2d(cmap, box, c0, m0 + q * 32);
         tma_store_commit();
       }
     }
@@ -439,7 +432,6 @@ struct EpiGradT {
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
     int g_row_off;            // row offset of this block inside the coefficient scratch (fused backward: buffer * Rb)
     int dbg;                  // measurement hook: bit 0 = skip the math (g = cos), bit 1 = skip staging + store
-    unsigned long long st_policy;  // L2 eviction hint of the coefficient stores (0 = none)
   };
   static constexpr int kWarps = kW;
   // column terms of a tile's columns, one copy per accumulator stage: 2 x 256 floats
@@ -526,10 +518,7 @@ struct EpiGradT {
           __syncwarp();
           if (lane == 0) {
             // columns beyond N are clipped by the hardware
-            if (P.st_policy != 0ull)
-              tma_store_2d_hint(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32, P.st_policy);
-            else
-              tma_store_2d(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32);
+            tma_store_2d(cmap, box, cbeg + (ch & ~1) * 32, P.g_row_off + m0 + q * 32);
             tma_store_commit();
           }
         }

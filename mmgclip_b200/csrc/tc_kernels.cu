@@ -274,7 +274,6 @@ int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand&
   e.C = C; e.ldc = ldc; e.bias = bias; e.alpha = alpha; e.alpha_ptr = alpha_dev; e.mode = mode; e.relu = relu;
   // act(C_old + v) cannot be expressed as a reduction: accumulate + bias/ReLU keeps the direct read-modify-write path
   e.use_tma = out_tma_ok(C, ldc) && !(mode != 0 && (relu || bias != nullptr));
-  e.out_policy = 0ull;
   CUtensorMap mc = ma;
   if (e.use_tma && (rc = make_out_tmap_f32(&mc, C, N, M, ldc)) != 0) return rc;
   MMG_DISPATCH(EpiStoreF32, tcfg, ma, mb, ma1, mb1, mc, mc, p0, p1, e, e, st);
@@ -294,7 +293,6 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   EpiStoreF32::Params e0, e1;
   e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
   e0.use_tma = out_tma_ok(C0, ldc0) && out_tma_ok(C1, ldc1);
-  e0.out_policy = 0ull;
   // Wave quantisation: the two problems of one 8192 x 8192 block are 128 pair tiles on 74 CTA pairs = 2 rounds at 86%.
   // With TMA reduce-add outputs (atomic at L2) every tile may be cut into K slices, so pick the split whose slice
   // count fills whole rounds best (128 x 4 = 512 slices = 6.92 rounds of 7 -> 99%); slices stay >= 16 K-blocks long.
@@ -369,7 +367,7 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   const int dbg = measure_env("MMG_EPI_DBG", 0);  // measurement builds only (tests/gpu_epi_probe.py): wrong results when set
   EpiGrad::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
-  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg; e.st_policy = 0ull;
+  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
   MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
 }
 
@@ -380,14 +378,14 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
 // Plan knobs of the fused backward (fused on/off, block shape, scratch buffers, slice lengths, block order): process-wide
 // overrides set through mmg_tune() -- the tests walk other schedules with it; unset = the measured defaults.  Every value
 // gives correct results.  Measurement builds also honour the MMG_* environment variables of the same names.
-enum TuneKey { kTuneFused, kTuneRb, kTuneCb, kTuneNbuf, kTuneKsl, kTuneKslT, kTuneSr, kTuneSc, kTuneHints, kTuneRot, kTunePdl, kTuneCount };
+enum TuneKey { kTuneFused, kTuneRb, kTuneCb, kTuneNbuf, kTuneKsl, kTuneKslT, kTuneSr, kTuneSc, kTuneRot, kTunePdl, kTuneCount };
 static const char* const kTuneNames[kTuneCount] = {"fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl",
-                                                   "fused_ksl_t", "fused_sr", "fused_sc", "fused_hints", "fused_rot", "pdl"};
+                                                   "fused_ksl_t", "fused_sr", "fused_sc", "fused_rot", "pdl"};
 static const char* const kTuneEnv[kTuneCount] = {"MMG_BWD_FUSED", "MMG_FUSED_RB", "MMG_FUSED_CB", "MMG_FUSED_NBUF",
                                                  "MMG_FUSED_KSL", "MMG_FUSED_KSL_T", "MMG_FUSED_SR", "MMG_FUSED_SC",
-                                                 "MMG_FUSED_HINTS", "MMG_FUSED_ROT", "MMG_PDL"};
+                                                 "MMG_FUSED_ROT", "MMG_PDL"};
 static std::mutex g_tune_mu;
-static int g_tune[kTuneCount] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // -1 = unset
+static int g_tune[kTuneCount] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // -1 = unset
 
 int tc_tune(const char* key, int value) {
   if (key == nullptr) return set_error(-1, "mmg_tune: key is NULL");
@@ -596,7 +594,6 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     cudaError_t te = cudaMemsetAsync(p.trace, 0, f.trace_bytes, st);
     if (te != cudaSuccess) return check_cuda(te, "cudaMemsetAsync(fused backward trace)");
   }
-  p.hints = tune_int(kTuneHints, kFusedHintsDefault);
   p.diag_offset = diag_offset;
   // several owners (row-sharded run): start the column walk at this rank's own columns (BwdFusedParams::global_cb)
   p.col_rot = 0;

@@ -98,7 +98,7 @@ def mark(name: str) -> None:
     ev.record()
 
 
-_TUNE_KEYS = ("fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl", "fused_ksl_t", "fused_sr", "fused_sc", "fused_hints", "fused_rot", "pdl")
+_TUNE_KEYS = ("fused", "fused_rb", "fused_cb", "fused_nbuf", "fused_ksl", "fused_ksl_t", "fused_sr", "fused_sc", "fused_rot", "pdl")
 
 
 def set_tuning(**kw) -> None:
