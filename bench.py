@@ -384,6 +384,7 @@ def run_gpu(args):
     _lib.load()
     if not args.pdl:
         ops.set_tuning(pdl=0)
+    ops.set_embedding_f16(bool(args.emb_f16))
 
     B = args.batch
     if B % world:
@@ -656,11 +657,15 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": B / (ms_value * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+        "dtype": ("f16" if ops.get_embedding_f16() else "bf16") if prec == "bf16" else "f32", "data": "synthetic",
         "config": dict(workload_config(world, n_sets=n_sets, graph=gstep is not None, peer=peer_reduce_active(),
                                        symm=symm_allreduce_active(), stored_e=stored_e),
                        heads="the two heads run on two streams (forward and backward)" if side is not None
                        else "the two heads run back to back on one stream",
+                       operands=("InfoNCE contractions: fp16 normalised embeddings x fp16 (2^14-scaled) gradient coefficients, "
+                                 "fp32 accumulation; heads bf16x3" if (prec == "bf16" and ops.get_embedding_f16()) else
+                                 ("InfoNCE contractions: bf16 embeddings x bf16 coefficients, fp32 accumulation; heads bf16x3"
+                                  if prec == "bf16" else "fp32 FFMA")),
                        gather=("push over NVLink peer memory (mmg_push_rows into every rank's symmetric buffer + barrier) on a "
                                "communication stream" if push_gather_active() else
                                ("NCCL all-gather (asynchronous)" if world > 1 else "none (one GPU)"))),
@@ -712,7 +717,7 @@ def kernel_breakdown(torch, ops, dev, rows, cols, d, stored_e=False):
     gen = torch.Generator(device=dev).manual_seed(7)
     a = torch.nn.functional.normalize(torch.randn(rows, d, device=dev, generator=gen), dim=1)
     b = torch.nn.functional.normalize(torch.randn(cols, d, device=dev, generator=gen), dim=1)
-    ab, bb = ops.cast_bf16(a), ops.cast_bf16(b)
+    ab, bb = ops.cast_embedding(a), ops.cast_embedding(b)
     s = torch.tensor(1 / 0.07, device=dev)
     one = torch.ones((), device=dev)
 
@@ -854,6 +859,11 @@ def main():
                          "rank holds <= 8192 rows (launch-bound heads: 0.212 -> 0.184 ms/step at batch 4096), off above "
                          "(bandwidth-bound heads: no gain measured)")
     ap.add_argument("--no-head-overlap", dest="head_overlap", action="store_false")
+    ap.add_argument("--emb-f16", dest="emb_f16", action="store_true",
+                    default=os.environ.get("MMGCLIP_B200_EMB_F16", "0") == "1",
+                    help="fp16 tensor-core operands for the normalised embeddings and the (2^14-scaled) gradient "
+                         "coefficients instead of bf16 (MMG_PREC_F16)")
+    ap.add_argument("--emb-bf16", dest="emb_f16", action="store_false")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", default=True,
                     help="A/B switch: launch without programmatic dependent launch (mmg_tune pdl=0)")
     ap.add_argument("--timeline", action="store_true",

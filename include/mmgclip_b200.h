@@ -14,7 +14,12 @@
  *   - return value: 0 = ok, negative = MMG_ERR_*; mmg_last_error_string() gives the thread-local reason;
  *   - there is NO CPU fallback: host pointers or a missing GPU are errors;
  *   - `prec` selects the arithmetic: MMG_PREC_FP32 = fp32 operands, fp32 FFMA accumulation (reference-faithful,
- *     parity 1e-5); MMG_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM (2e-3).
+ *     parity 1e-5); MMG_PREC_BF16 = bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM (2e-3);
+ *     MMG_PREC_F16 (fused InfoNCE entry points only) = the same tensor-core path with the L2-NORMALISED EMBEDDING operands
+ *     a_hat / b_hat stored as IEEE fp16 instead of bf16 (|x| <= 1, so the 3 extra mantissa bits cost no range and the
+ *     tensor-core rate is the same) and the gradient coefficients as fp16 in 2^14-scaled units (see
+ *     mmg_infonce_bwd_prep; tcgen05.mma kind::f16 cannot mix bf16 and fp16 operands in one instruction).  Embedding /
+ *     weight gradients ~8x closer to float64 than with bf16 operands.
  */
 #ifndef MMGCLIP_B200_H_
 #define MMGCLIP_B200_H_
@@ -35,6 +40,7 @@ extern "C" {
 
 #define MMG_PREC_FP32 0
 #define MMG_PREC_BF16 1
+#define MMG_PREC_F16 2
 
 /* C store modes of the dense contraction */
 #define MMG_STORE 0      /* C  = v                      */
@@ -74,6 +80,7 @@ int mmg_gemm_split(const void* A_hi, const void* A_lo, long long lda, int a_mn, 
 
 /* ---- element-wise helpers -------------------------------------------------------------------------------- */
 int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t stream);
+int mmg_cast_f32_to_f16(const float* x, void* y_f16, long long n, mmg_stream_t stream);
 /* hi = bf16(x), lo = bf16(x - hi): operands of the three-pass "bf16x3" contraction A_hi.B_hi + A_hi.B_lo + A_lo.B_hi that
  * keeps the projection heads fp32-faithful (~2^-17 per operand) on the bf16 tensor pipe. */
 int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, long long n, mmg_stream_t stream);
@@ -86,8 +93,10 @@ int mmg_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n
                   mmg_stream_t stream);
 
 /* Row-wise L2 normalisation y = u / ||u||_2, no epsilon (mmgclip/networks/mmgclip_model.py:128-129,163;
- * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_bf16 (nullable) receives a bf16 copy. */
-int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream);
+ * mmgclip/evaluator.py:79,86).  inv_norm[B] is kept for the backward.  y_16 (nullable) receives a 16-bit operand copy for
+ * the fused InfoNCE: fp16 when y16_is_f16 != 0 (MMG_PREC_F16), else bf16. */
+int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_16, int y16_is_f16,
+                   mmg_stream_t stream);
 /* du = (dy - y * <y, dy>) * inv_norm   (autograd of the line above).  Outputs (each nullable, at least one): du fp32,
  * du_bf16 = bf16(du), du_bf16_lo = bf16(du - du_bf16) for the bf16x3 weight-gradient contraction.
  * zero_fill (nullable; 16-byte aligned, zero_floats % 4 == 0): a buffer the same launch clears -- the split-K output of the
@@ -144,8 +153,12 @@ int mmg_infonce_loss_cols(const float* colsum, int cols, const float* scale, con
 /* rinv[r] = s*gl*inv_two_b / rowsum[r], cinv[c] = s*gl*inv_two_b / colsum[c]; scal (4 floats): [1] = dcoef =
  * 2*s*gl*inv_two_b; [0] = the diagonal coefficient mmg_infonce_bwd itself subtracts (dcoef, or 0 when diag_in_fp32);
  * [2] = diag_in_fp32 flag: mmg_infonce_bwd then ZEROES the matching-pair element of g and the caller applies it with
- * mmg_infonce_bwd_diag (what the bf16 path does).  grad_loss is a DEVICE scalar (1 for a bare loss.backward()). */
-int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+ * mmg_infonce_bwd_diag (what the bf16 path does).  grad_loss is a DEVICE scalar (1 for a bare loss.backward()).
+ * prec = the precision of the mmg_infonce_bwd* call that follows.  With MMG_PREC_F16 the coefficients are stored as fp16 in
+ * scaled units: rinv = 2^14 / rowsum, cinv = 2^14 / colsum (so g' = E*(rinv + cinv) lies in [0, 2^15]), scal[0] in the
+ * same units and scal[3] = s*gl*inv_two_b * 2^-14, the factor the gradient epilogues multiply back in (scal[3] = 1
+ * otherwise). */
+int mmg_infonce_bwd_prep(int prec, const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                          float* scal, mmg_stream_t stream);
 
@@ -165,7 +178,7 @@ int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, co
  * its contraction kernel): writes rinv[rows], cinv[cols], scal[4] and the matching-pair rows dA[r,:] = g*b32[r,:],
  * dB_matching[r,:] = g*a32[r,:] (g as above, formed from rowsum[r] and colsum[diag_offset + r] directly).  b32 and
  * dB_matching point at the `rows` column-side rows paired with the local rows. */
-int mmg_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+int mmg_infonce_bwd_prep_diag(int prec, const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
                               float* dB_matching, float* dlogscale_acc, mmg_stream_t stream);
@@ -190,8 +203,9 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
  * The owners may also be slices of a local staging buffer that a reduce-scatter then sends home; with n_parts > 1 one
  * call covers only part `part` (0-based) of EVERY owner's columns -- dB_owners[i] is then the [cols/n_owners/n_parts, D]
  * buffer of that part, dA accumulates across the calls -- so the reduce-scatter of one part travels while the next part
- * is computed.  bf16 path only; runs as the one fused persistent launch or returns MMG_ERR_UNSUPPORTED_SHAPE. */
-int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+ * is computed.  prec = MMG_PREC_BF16 or MMG_PREC_F16 (type of a_hat / b_hat); runs as the one fused persistent launch or
+ * returns MMG_ERR_UNSUPPORTED_SHAPE. */
+int mmg_infonce_bwd_owners(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                            const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                            float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream);
@@ -201,12 +215,14 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
  * losses.py:28-44 via mmgclip_model.py:135-136); the backward then turns E into the gradient coefficients with a streaming
  * transform instead of recomputing the cosines on the tensor cores (4 instead of 6 rows*cols*D FLOPs).  No
  * d/d logit_scale in this mode (use mmg_infonce_bwd when logit_scale is trained).  mmg_infonce_stored_supported tells
- * whether mmg_infonce_bwd_stored covers a shape (rows, cols/owners/parts and D multiples of 256). */
+ * whether mmg_infonce_bwd_stored covers a shape (rows, cols/owners/parts and D multiples of 256).  prec = MMG_PREC_BF16 or
+ * MMG_PREC_F16 for the forward (type of a_hat / b_hat; E itself is always bf16); the stored-E backward takes
+ * MMG_PREC_BF16 operands only. */
 int mmg_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts);
-int mmg_infonce_fwd_store(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+int mmg_infonce_fwd_store(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                           const float* scale, float* rowsum, float* colsum, float* diag, void* e_out, long long lde,
                           mmg_stream_t stream);
-int mmg_infonce_bwd_stored(const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows, int cols,
+int mmg_infonce_bwd_stored(int prec, const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows, int cols,
                            int D, int diag_offset, const float* scale, const float* rinv, const float* cinv,
                            const float* scal, float* dA, float* const* dB_owners, int n_owners, int n_parts, int part,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream);

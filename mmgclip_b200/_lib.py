@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MMGCLIP_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
 MMG_PREC_FP32 = 0
 MMG_PREC_BF16 = 1
+MMG_PREC_F16 = 2
 MMG_STORE = 0
 MMG_ACCUMULATE = 1
 MMG_ATOMIC_ADD = 2
@@ -32,9 +33,10 @@ SIGNATURES = {
     "mmg_gemm_split": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p,
                                c_longlong, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mmg_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "mmg_cast_f32_to_f16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_cast_f32_to_bf16_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "mmg_push_rows": (c_int, [c_void_p, c_longlong, POINTER(c_void_p), c_int, c_longlong, c_void_p]),
-    "mmg_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmg_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mmg_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_longlong, c_void_p]),
     "mmg_dropout_apply": (c_int, [c_void_p, c_void_p, c_float, c_longlong, c_void_p]),
@@ -53,22 +55,22 @@ SIGNATURES = {
     "mmg_infonce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "mmg_infonce_row_part": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mmg_infonce_loss_cols": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
-    "mmg_infonce_bwd_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
+    "mmg_infonce_bwd_prep": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
-    "mmg_infonce_bwd_prep_diag": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+    "mmg_infonce_bwd_prep_diag": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
     "mmg_infonce_bwd_diag": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mmg_infonce_bwd": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "mmg_infonce_bwd_owners": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    "mmg_infonce_bwd_owners": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_size_t, c_void_p]),
     "mmg_infonce_stored_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
-    "mmg_infonce_fwd_store": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    "mmg_infonce_fwd_store": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_longlong, c_void_p]),
-    "mmg_infonce_bwd_stored": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
+    "mmg_infonce_bwd_stored": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
                                        c_void_p, c_size_t, c_void_p]),
     "mmg_eos_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

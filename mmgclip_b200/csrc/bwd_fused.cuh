@@ -50,6 +50,8 @@ struct BwdFusedParams {
   int sI, sT;          // slices per dA tile (Cb/64/kslI) / per dB tile (Rb/64/kslT)
   int nA, nBI, nB;     // items per block: coefficient tiles; dA slices; all gradient slices
   int diag_offset;     // global column paired with local row 0
+  int emb_f16;         // 1: embedding operands AND coefficient scratch are fp16 (kind::f16 cannot mix the two 16-bit
+                       // formats in one MMA: a bf16 x fp16 instruction traps); 0: all bf16
   const float* rinv;
   const float* cinv;
   const float* scale;
@@ -449,7 +451,8 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
         mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t a_mn = it.type == 2 ? 1u : 0u, b_mn = it.type != 0 ? 1u : 0u;
-        const uint32_t idesc = make_idesc_bf16(256, BN, a_mn, b_mn);
+        const uint32_t emb = static_cast<uint32_t>(p.emb_f16);  // fp16 mode: embeddings AND coefficients are fp16
+        const uint32_t idesc = make_idesc_16(256, BN, a_mn, b_mn, emb, emb);
         const uint32_t tmem_d = tmem_base + acc_stage * BN;
         const uint32_t a_lbo = a_mn ? kBK * 128 : 0, b_lbo = b_mn ? kBK * 128 : 0;
         const uint32_t a_kstep = a_mn ? kUmmaK * 128 : kUmmaK * 2;
@@ -493,8 +496,9 @@ infonce_bwd_fused_kernel(const __grid_constant__ CUtensorMap mAk, const __grid_c
     int ntr = 0;
     typename FusedGrad::Params gp;
     gp.scale_ptr = p.scale; gp.scal = p.scal; gp.dlogscale_acc = p.dlogscale_acc; gp.dbg = 0;
+    gp.g_f16 = p.emb_f16;
     typename FusedStore::Params sp;
-    sp.C = nullptr; sp.ldc = 0; sp.bias = nullptr; sp.alpha = 1.f; sp.alpha_ptr = nullptr; sp.mode = 1; sp.relu = 0;
+    sp.C = nullptr; sp.ldc = 0; sp.bias = nullptr; sp.alpha = 1.f; sp.alpha_ptr = p.scal + 3; sp.mode = 1; sp.relu = 0;
     sp.use_tma = 1;
     while (cur.next(p, it)) {
       if (pending >= 0) {

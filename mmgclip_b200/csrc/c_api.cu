@@ -137,6 +137,14 @@ int mmg_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, mmg_stream_t
   return simt_cast_bf16(x, y_bf16, n, static_cast<cudaStream_t>(stream));
 }
 
+int mmg_cast_f32_to_f16(const float* x, void* y_f16, long long n, mmg_stream_t stream) {
+  if (n < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_cast_f32_to_f16: negative length");
+  if (n == 0) return 0;
+  MMG_REQ(x);
+  MMG_REQ(y_f16);
+  return simt_cast_f16(x, y_f16, n, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_cast_f32_to_bf16_split(const float* x, void* hi_bf16, void* lo_bf16, long long n, mmg_stream_t stream) {
   if (n < 0) return set_error(MMG_ERR_BAD_ARG, "mmg_cast_split: negative length");
   if (n == 0) return 0;
@@ -160,12 +168,13 @@ int mmg_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n
   return simt_push_rows(src, bytes, dst_ptrs, n_dst, dst_offset_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, mmg_stream_t stream) {
+int mmg_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_16, int y16_is_f16,
+                   mmg_stream_t stream) {
   if (B < 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_l2norm_fwd: bad shape %dx%d", B, D);
   if (B == 0) return 0;
   MMG_REQ(u);
   MMG_REQ(y);
-  return simt_l2norm_fwd(u, B, D, y, inv_norm, y_bf16, static_cast<cudaStream_t>(stream));
+  return simt_l2norm_fwd(u, B, D, y, inv_norm, y_16, y16_is_f16 ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
@@ -264,7 +273,7 @@ int mmg_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 size_t mmg_infonce_workspace_bytes(int prec, int rows, int cols, int D) {
   (void)D;
   if (rows <= 0 || cols <= 0) return 0;
-  if (prec == MMG_PREC_BF16) {
+  if (prec == MMG_PREC_BF16 || prec == MMG_PREC_F16) {
     const long long rb = rows < kDefaultBlockBf16 ? rows : kDefaultBlockBf16;
     const long long cb = round_up(cols < kDefaultBlockBf16 ? cols : kDefaultBlockBf16, 64);
     const size_t loop = (size_t)(rb * cb * 2 + 256);
@@ -278,13 +287,14 @@ size_t mmg_infonce_workspace_bytes(int prec, int rows, int cols, int D) {
 
 static int check_infonce_args(const char* fn, int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D,
                               int diag_offset, const float* scale) {
-  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_FP32) return set_error(MMG_ERR_BAD_ARG, "%s: unknown precision", fn);
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_FP32 && prec != MMG_PREC_F16)
+    return set_error(MMG_ERR_BAD_ARG, "%s: unknown precision", fn);
   if (rows <= 0 || cols <= 0 || D <= 0) return set_error(MMG_ERR_BAD_ARG, "%s: bad shape %dx%dx%d", fn, rows, cols, D);
   if (diag_offset < 0 || diag_offset + rows > cols)
     return set_error(MMG_ERR_BAD_ARG, "%s: rows [%d, %d) have no matching columns in [0, %d)", fn, diag_offset,
                      diag_offset + rows, cols);
-  if (prec == MMG_PREC_BF16 && (D % 8) != 0)
-    return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "%s: bf16 path needs D %% 8 == 0 (TMA pitch), got %d", fn, D);
+  if (prec != MMG_PREC_FP32 && (D % 8) != 0)
+    return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "%s: tensor-core path needs D %% 8 == 0 (TMA pitch), got %d", fn, D);
   int rc;
   if ((rc = require_device(a_hat, "a_hat")) != 0) return rc;
   if ((rc = require_device(b_hat, "b_hat")) != 0) return rc;
@@ -300,9 +310,10 @@ int mmg_infonce_fwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   MMG_REQ(colsum);
   MMG_REQ(diag);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (prec == MMG_PREC_BF16) {
+  if (prec != MMG_PREC_FP32) {
     // One persistent launch over all logit tiles; the tile lives only in TMEM.
-    return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, nullptr, 0, st);
+    return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, nullptr, 0, st,
+                          prec == MMG_PREC_F16);
   }
   if (workspace_bytes < mmg_infonce_workspace_bytes(prec, rows, cols, D))
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_fwd: workspace too small");
@@ -330,10 +341,12 @@ int mmg_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_
   return tc_infonce_stored_supported(rows, cols, D, n_owners, n_parts);
 }
 
-int mmg_infonce_fwd_store(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+int mmg_infonce_fwd_store(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                           const float* scale, float* rowsum, float* colsum, float* diag, void* e_out, long long lde,
                           mmg_stream_t stream) {
-  MMG_TRY(check_infonce_args("mmg_infonce_fwd_store", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_F16)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_fwd_store: tensor-core path only (MMG_PREC_BF16 / MMG_PREC_F16)");
+  MMG_TRY(check_infonce_args("mmg_infonce_fwd_store", prec, a_hat, b_hat, rows, cols, D, diag_offset, scale));
   MMG_REQ(rowsum);
   MMG_REQ(colsum);
   MMG_REQ(diag);
@@ -342,14 +355,17 @@ int mmg_infonce_fwd_store(const void* a_hat, const void* b_hat, int rows, int co
     return set_error(MMG_ERR_BAD_ALIGN, "mmg_infonce_fwd_store: E needs a pitch >= cols that is a multiple of 8 and a "
                                         "16-byte aligned base");
   return tc_infonce_fwd(a_hat, b_hat, rows, cols, D, diag_offset, scale, rowsum, colsum, diag, e_out, lde,
-                        static_cast<cudaStream_t>(stream));
+                        static_cast<cudaStream_t>(stream), prec == MMG_PREC_F16);
 }
 
-int mmg_infonce_bwd_stored(const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows, int cols,
-                           int D, int diag_offset, const float* scale, const float* rinv, const float* cinv,
+int mmg_infonce_bwd_stored(int prec, const void* a_hat, const void* b_hat, const void* e_stored, long long lde, int rows,
+                           int cols, int D, int diag_offset, const float* scale, const float* rinv, const float* cinv,
                            const float* scal, float* dA, float* const* dB_owners, int n_owners, int n_parts, int part,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream) {
-  MMG_TRY(check_infonce_args("mmg_infonce_bwd_stored", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  if (prec != MMG_PREC_BF16)
+    return set_error(MMG_ERR_UNSUPPORTED_SHAPE, "mmg_infonce_bwd_stored: the stored-E transform writes bf16 coefficients "
+                                                "(MMG_PREC_BF16 operands only)");
+  MMG_TRY(check_infonce_args("mmg_infonce_bwd_stored", prec, a_hat, b_hat, rows, cols, D, diag_offset, scale));
   MMG_REQ(e_stored);
   MMG_REQ(rinv);
   MMG_REQ(cinv);
@@ -365,7 +381,7 @@ int mmg_infonce_bwd_stored(const void* a_hat, const void* b_hat, const void* e_s
   int used = 0;
   MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, dB_owners,
                                n_owners, n_parts, part, nullptr, workspace, workspace_bytes,
-                               static_cast<cudaStream_t>(stream), &used, e_stored, lde));
+                               static_cast<cudaStream_t>(stream), &used, e_stored, lde, 0));
   if (!used)
     return set_error(MMG_ERR_UNSUPPORTED_SHAPE,
                      "mmg_infonce_bwd_stored: shape not covered (see mmg_infonce_stored_supported), misaligned E or "
@@ -402,10 +418,12 @@ int mmg_infonce_loss_cols(const float* colsum, int cols, const float* scale, con
   return simt_infonce_loss_cols(colsum, cols, scale, row_part, inv_two_b, loss_out, static_cast<cudaStream_t>(stream));
 }
 
-int mmg_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
+int mmg_infonce_bwd_prep_diag(int prec, const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
                               float* dB_matching, float* dlogscale_acc, mmg_stream_t stream) {
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_F16)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep_diag: tensor-core path only (MMG_PREC_BF16 / MMG_PREC_F16)");
   if (rows <= 0 || cols <= 0 || D <= 0 || diag_offset < 0 || diag_offset + rows > cols)
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep_diag: bad shape");
   MMG_REQ(rowsum);
@@ -420,13 +438,16 @@ int mmg_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum
   MMG_REQ(diag);
   MMG_REQ(dA);
   MMG_REQ(dB_matching);
-  return simt_infonce_bwd_prep_diag(rowsum, rows, colsum, cols, diag_offset, scale, grad_loss, inv_two_b, rinv, cinv, scal,
-                                    a32, b32, D, diag, dA, dB_matching, dlogscale_acc, static_cast<cudaStream_t>(stream));
+  return simt_infonce_bwd_prep_diag(rowsum, rows, colsum, cols, diag_offset, scale, grad_loss, inv_two_b,
+                                    prec == MMG_PREC_F16, rinv, cinv, scal, a32, b32, D, diag, dA, dB_matching,
+                                    dlogscale_acc, static_cast<cudaStream_t>(stream));
 }
 
-int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
+int mmg_infonce_bwd_prep(int prec, const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
                          float* scal, mmg_stream_t stream) {
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_F16 && prec != MMG_PREC_FP32)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep: unknown precision");
   if (rows <= 0 || cols <= 0) return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_prep: bad shape");
   MMG_REQ(rowsum);
   MMG_REQ(colsum);
@@ -435,8 +456,8 @@ int mmg_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int
   MMG_REQ(rinv);
   MMG_REQ(cinv);
   MMG_REQ(scal);
-  return simt_infonce_bwd_prep(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b, diag_in_fp32, rinv, cinv, scal,
-                               static_cast<cudaStream_t>(stream));
+  return simt_infonce_bwd_prep(rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b, diag_in_fp32,
+                               prec == MMG_PREC_F16, rinv, cinv, scal, static_cast<cudaStream_t>(stream));
 }
 
 int mmg_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
@@ -470,9 +491,11 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   if (dlogscale_acc != nullptr) MMG_REQ(dlogscale_acc);  // NULL: d/d logit_scale not wanted (skips sum g*cos)
   MMG_REQ(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int dflt = prec == MMG_PREC_BF16 ? kDefaultBlockBf16 : kDefaultBlockFp32;
-  const int esz = prec == MMG_PREC_BF16 ? 2 : 4;
-  const int pad = prec == MMG_PREC_BF16 ? 64 : 4;
+  const bool tc = prec != MMG_PREC_FP32;  // tensor-core path (bf16 or fp16 embedding operands)
+  const int emb_f16 = prec == MMG_PREC_F16 ? 1 : 0;
+  const int dflt = tc ? kDefaultBlockBf16 : kDefaultBlockFp32;
+  const int esz = tc ? 2 : 4;
+  const int pad = tc ? 64 : 4;
   int Rb = block_rows > 0 ? block_rows : dflt;
   int Cb = block_cols > 0 ? block_cols : dflt;
   if (Rb > rows) Rb = rows;
@@ -493,11 +516,11 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
 
   // One persistent launch for the whole backward when the shape allows it (bwd_fused.cuh); explicit block shapes and
   // the phase hook select the block loop below.
-  if (prec == MMG_PREC_BF16 && phases == 3 && block_rows <= 0 && block_cols <= 0) {
+  if (tc && phases == 3 && block_rows <= 0 && block_cols <= 0) {
     int used = 0;
     float* owners[1] = {dB};
     MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, owners, 1, 1, 0,
-                                 dlogscale_acc, workspace, workspace_bytes, st, &used));
+                                 dlogscale_acc, workspace, workspace_bytes, st, &used, nullptr, 0, emb_f16));
     if (used) return 0;
   }
 
@@ -506,19 +529,20 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
     for (int c0 = 0; c0 < cols; c0 += Cb) {
       const int cb = cols - c0 < Cb ? cols - c0 : Cb;
       const int doff = r0 + diag_offset - c0;
-      if (prec == MMG_PREC_BF16) {
+      if (tc) {
         const char* a = static_cast<const char*>(a_hat) + (long long)r0 * D * 2;
         const char* b = static_cast<const char*>(b_hat) + (long long)c0 * D * 2;
         // (1) recompute the cosine block on tensor cores; epilogue turns it into bf16 gradient coefficients g
         if (phases & 1)
           MMG_TRY(tc_infonce_grad_block(a, b, rb, cb, D, doff, scale, rinv + r0, cinv + c0, scal, workspace, ldg,
-                                        dlogscale_acc, st));
+                                        dlogscale_acc, st, emb_f16));
         if (!(phases & 2)) continue;
         // (2) dA[r0:, :] += g . b_blk   and   dB[c0:, :] += g^T . a_blk   in one launch
-        TcOperand A0{workspace, ldg, 0}, B0{b, D, 1};
-        TcOperand A1{workspace, ldg, 1}, B1{a, D, 1};
+        // scal[3] = factor that turns the stored coefficients back into true ones (1 for bf16, coef * 2^-14 for fp16)
+        TcOperand A0{workspace, ldg, 0, emb_f16}, B0{b, D, 1, emb_f16};
+        TcOperand A1{workspace, ldg, 1, emb_f16}, B1{a, D, 1, emb_f16};
         MMG_TRY(tc_gemm_dual_accumulate(A0, B0, dA + (long long)r0 * D, D, rb, D, cb, A1, B1, dB + (long long)c0 * D,
-                                        D, cb, D, rb, st));
+                                        D, cb, D, rb, st, scal + 3));
       } else {
         const float* a = static_cast<const float*>(a_hat) + (long long)r0 * D;
         const float* b = static_cast<const float*>(b_hat) + (long long)c0 * D;
@@ -533,11 +557,13 @@ int mmg_infonce_bwd(int prec, const void* a_hat, const void* b_hat, int rows, in
   return 0;
 }
 
-int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
+int mmg_infonce_bwd_owners(int prec, const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset,
                            const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                            float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                            void* workspace, size_t workspace_bytes, mmg_stream_t stream) {
-  MMG_TRY(check_infonce_args("mmg_infonce_bwd_owners", MMG_PREC_BF16, a_hat, b_hat, rows, cols, D, diag_offset, scale));
+  if (prec != MMG_PREC_BF16 && prec != MMG_PREC_F16)
+    return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_owners: tensor-core path only (MMG_PREC_BF16 / MMG_PREC_F16)");
+  MMG_TRY(check_infonce_args("mmg_infonce_bwd_owners", prec, a_hat, b_hat, rows, cols, D, diag_offset, scale));
   MMG_REQ(rinv);
   MMG_REQ(cinv);
   MMG_REQ(scal);
@@ -552,7 +578,7 @@ int mmg_infonce_bwd_owners(const void* a_hat, const void* b_hat, int rows, int c
     return set_error(MMG_ERR_BAD_ARG, "mmg_infonce_bwd_owners: bad column part %d of %d", part, n_parts);
   MMG_TRY(tc_infonce_bwd_fused(a_hat, b_hat, rows, cols, D, diag_offset, scale, rinv, cinv, scal, dA, dB_owners,
                                n_owners, n_parts, part, dlogscale_acc, workspace, workspace_bytes,
-                               static_cast<cudaStream_t>(stream), &used));
+                               static_cast<cudaStream_t>(stream), &used, nullptr, 0, prec == MMG_PREC_F16));
   if (!used)
     return set_error(MMG_ERR_UNSUPPORTED_SHAPE,
                      "mmg_infonce_bwd_owners: needs rows, cols / owners and D to be multiples of 256, column parts made of "

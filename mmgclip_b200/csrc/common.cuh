@@ -53,6 +53,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -344,12 +350,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
-//   c_format F32 = 1 at [4,6); a_format BF16 = 1 at [7,10); b_format BF16 = 1 at [10,13);
+// Instruction descriptor for kind::f16 with 16-bit A/B and fp32 accumulation.
+//   c_format F32 = 1 at [4,6); a_format at [7,10), b_format at [10,13): F16 = 0, BF16 = 1 (the two operands choose
+//   independently: the gradient contractions multiply bf16 coefficients by fp16 embeddings);
 //   a_major at [15], b_major at [16] (0 = K-major, 1 = MN-major); N>>3 at [17,23); M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                  uint32_t a_f16, uint32_t b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
-         ((M >> 4) << 24);
+  return make_idesc_16(M, N, a_mn_major, b_mn_major, 0u, 0u);
 }
 
 }  // namespace mmg

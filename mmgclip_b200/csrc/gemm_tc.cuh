@@ -35,6 +35,7 @@ struct GemmProblem {
   int tiles_m, tiles_n;  // ceil(M/(128*kCG)), ceil(N/BN)
   int k_splits;          // >= 1; each split handles a contiguous range of 64-wide K blocks
   int a_mn, b_mn;        // 0 = K-major operand, 1 = MN-major operand
+  int a_f16, b_f16;      // operand element type: 0 = bf16, 1 = fp16 (normalised embeddings travel as fp16)
   // K segments (single-problem launches only): the contraction runs over k_segs concatenated K ranges of K elements
   // each, segment i reading A from tensor map (seg_a >> i) & 1 and B from (seg_b >> i) & 1 -- one launch and one
   // accumulator for  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  (split-precision heads) instead of three accumulate passes.
@@ -432,6 +433,8 @@ struct EpiGradT {
     int diag_offset;          // (global column index of local row 0) - (global column index of block column 0)
     int g_row_off;            // row offset of this block inside the coefficient scratch (fused backward: buffer * Rb)
     int dbg;                  // measurement hook: bit 0 = skip the math (g = cos), bit 1 = skip staging + store
+    int g_f16;                // coefficients go out as fp16 (MMG_PREC_F16: rinv / cinv then carry the 2^14 scaling and
+                              // scal[3] the factor the gradient epilogues multiply back in) instead of bf16
   };
   static constexpr int kWarps = kW;
   // column terms of a tile's columns, one copy per accumulator stage: 2 x 256 floats
@@ -444,7 +447,7 @@ struct EpiGradT {
   template <bool kDiag>
   static __device__ __forceinline__ void chunk(float (&v)[32], const float* cs, float ri, float sl2, int c0, int dcol,
                                                float dcoef, bool zero_diag, bool dls, float (&dacc)[2], uint8_t* rowp,
-                                               uint32_t sw, uint32_t cbase, int dbg) {
+                                               uint32_t sw, uint32_t cbase, int dbg, int g_f16) {
     if (!(dbg & 1)) {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
@@ -463,14 +466,26 @@ struct EpiGradT {
       }
     }
     if (!(dbg & 2)) {
+      if (g_f16) {  // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_f16x2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_f16x2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_f16x2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_f16x2(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(rowp + (((cbase + j) ^ sw) << 4)) = o;
+        }
       }
     }
   }
@@ -511,7 +526,7 @@ struct EpiGradT {
         __syncwarp();
       }
       chunk<kDiag>(va, cs + ch * 32, ri, sl2, cbeg + ch * 32, dcol, dcoef, zero_diag, dls, dacc, rowp, sw,
-                   static_cast<uint32_t>((ch & 1) * 4), dbg);
+                   static_cast<uint32_t>((ch & 1) * 4), dbg, P.g_f16);
       if ((ch & 1) == 1 || ch + 1 == nch) {
         if (!(dbg & 2)) {
           fence_proxy_async_smem();
@@ -555,7 +570,7 @@ struct EpiGradT {
   // sum g*cos: one atomic per warp per launch (not per tile: 10^5 same-address atomics per launch serialise at L2)
   static __device__ __forceinline__ void finish(const Params& P, float carry, int lane) {
     if (P.dlogscale_acc != nullptr) {
-      const float d = warp_sum(carry);
+      const float d = warp_sum(carry) * __ldg(P.scal + 3);  // scal[3]: 1, or the factor that undoes the fp16 scaling
       if (lane == 0 && d != 0.f) atomicAdd(P.dlogscale_acc, d);
     }
     if (lane == 0) tma_store_wait_all();
@@ -718,7 +733,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc_bf16(kTileM, BN, p.a_mn, p.b_mn);
+        const uint32_t idesc = make_idesc_16(kTileM, BN, p.a_mn, p.b_mn, p.a_f16, p.b_f16);
         const uint32_t tmem_d = tmem_base + acc_stage * BN;
         // K-major: 8-row groups are 1024 B apart (SBO); one swizzle span along K, LBO unused.
         // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN atoms are kBK*128 B apart (LBO).

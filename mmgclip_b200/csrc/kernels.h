@@ -58,6 +58,7 @@ struct TcOperand {
   const void* ptr;   // bf16
   long long ld;      // row pitch in elements
   int mn_major;      // 0: [rows, K]  1: [K, rows]
+  int f16 = 0;       // element type: 0 bf16, 1 fp16
 };
 
 int tc_gemm_store(const TcOperand& A, const TcOperand& B, float* C, long long ldc, int M, int N, int K, float alpha,
@@ -72,14 +73,14 @@ int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand&
 // Two independent accumulate-GEMMs in one launch (dA and dB of one logit block).
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
                             const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,
-                            cudaStream_t st);
+                            cudaStream_t st, const float* alpha_dev = nullptr);
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
-                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st);
+                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st, int emb_f16 = 0);
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
                           const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
-                          long long ldg, float* dlogscale_acc, cudaStream_t st);
+                          long long ldg, float* dlogscale_acc, cudaStream_t st, int emb_f16 = 0);
 
 // The whole bf16 backward as one persistent launch (bwd_fused.cuh).  *used = 0 (and nothing launched) when the shape is
 // not covered (rows / cols / D not multiples of 256, workspace too small, MMG_BWD_FUSED=0): the caller falls back to the
@@ -93,7 +94,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                          float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                          void* workspace, size_t workspace_bytes, cudaStream_t st, int* used,
-                         const void* e_stored = nullptr, long long lde = 0);
+                         const void* e_stored = nullptr, long long lde = 0, int emb_f16 = 0);
 int tc_infonce_stored_supported(int rows, int cols, int D, int n_owners, int n_parts);
 int tc_fused_trace_region(int rows, int cols, int D, size_t* off, size_t* bytes, int* per_role, int* roles);
 
@@ -113,8 +114,9 @@ int simt_gemm(const float* A, long long lda, int a_mn, const float* B, long long
               int M, int N, int K, float alpha, const float* alpha_dev, const float* bias, int relu, int mode,
               int k_splits, cudaStream_t st);
 int simt_cast_bf16(const float* x, void* y, long long n, cudaStream_t st);
+int simt_cast_f16(const float* x, void* y, long long n, cudaStream_t st);
 int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_t st);
-int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st);
+int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_16, int y16_f16, cudaStream_t st);
 int simt_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int n_dst, long long dst_offset_bytes,
                    cudaStream_t st);
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
@@ -151,15 +153,15 @@ int simt_infonce_row_part(const float* rowsum, const float* diag, int rows, floa
 int simt_infonce_loss_cols(const float* colsum, int cols, const float* scale, const float* row_part, float inv_two_b,
                            float* loss_out, cudaStream_t st);
 int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
-                          float* scal, cudaStream_t st);
+                          const float* grad_loss, float inv_two_b, int diag_in_fp32, int f16_scaled, float* rinv,
+                          float* cinv, float* scal, cudaStream_t st);
 int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, const float* diag, const float* scale,
                           const float* rinv, const float* cinvm, const float* scal, float* dA, float* dB,
                           float* dlogscale_acc, int init, cudaStream_t st);
 int simt_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
-                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
-                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
-                               float* dB, float* dlogscale_acc, cudaStream_t st);
+                               const float* scale, const float* grad_loss, float inv_two_b, int f16_scaled, float* rinv,
+                               float* cinv, float* scal, const float* a32, const float* b32, int D, const float* diag,
+                               float* dA, float* dB, float* dlogscale_acc, cudaStream_t st);
 int simt_dot_sum(const float* x, const float* y, long long n, float* out, cudaStream_t st);
 int simt_ce_fwd(const float* logits, long long ld, int n, int m, const long long* labels, float coef, float* lse,
                 float* loss_out, cudaStream_t st);

@@ -8,6 +8,7 @@
 //
 // Warp-level primitives (shuffles) do the row reductions; loads are 16-byte vectorised where alignment allows.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -155,6 +156,28 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
   }
 }
 
+// fp32 -> fp16 (the operand copy of L2-normalised embeddings: |x| <= 1, so fp16's 11-bit significand costs no range)
+__global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  pdl_entry();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long j = i; j < n4; j += stride) {
+      const float4 v = reinterpret_cast<const float4*>(x)[j];
+      const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(y)[j] = o;
+    }
+    for (long long j = (n4 << 2) + i; j < n; j += stride) y[j] = __float2half_rn(x[j]);
+  } else {
+    for (long long j = i; j < n; j += stride) y[j] = __float2half_rn(x[j]);
+  }
+}
+
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits survive, so the three-product contraction
 // A_hi.B_hi + A_hi.B_lo + A_lo.B_hi on the bf16 tensor pipe is accurate to ~2^-17 per operand ("bf16x3").
 __global__ void cast_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
@@ -200,6 +223,12 @@ int simt_cast_split(const float* x, void* hi, void* lo, long long n, cudaStream_
   if (n <= 0) return 0;
   MMG_LAUNCH_PDL("cast_split_kernel", cast_split_kernel, ew_blocks(n, 4), 256, 0, st, x, reinterpret_cast<__nv_bfloat16*>(hi),
                  reinterpret_cast<__nv_bfloat16*>(lo), n);
+  return 0;
+}
+
+int simt_cast_f16(const float* x, void* y, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  MMG_LAUNCH_PDL("cast_f16_kernel", cast_f16_kernel, ew_blocks(n, 4), 256, 0, st, x, reinterpret_cast<__half*>(y), n);
   return 0;
 }
 
@@ -261,7 +290,7 @@ int simt_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int 
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__ y, float* __restrict__ inv_norm,
-                  __nv_bfloat16* __restrict__ yb) {
+                  uint16_t* __restrict__ yb, int yb_f16) {
   pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -284,7 +313,7 @@ l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__
   const float inv = 1.0f / nrm;
   if (lane == 0 && inv_norm != nullptr) inv_norm[row] = inv;
   float* yr = y + (long long)row * D;
-  __nv_bfloat16* ybr = yb ? yb + (long long)row * D : nullptr;
+  uint16_t* ybr = yb ? yb + (long long)row * D : nullptr;  // 16-bit operand copy: fp16 (yb_f16) or bf16
   if (vec) {
     for (int i = lane; i < (D >> 2); i += 32) {
       float4 v = reinterpret_cast<const float4*>(ur)[i];
@@ -292,8 +321,14 @@ l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__
       reinterpret_cast<float4*>(yr)[i] = v;
       if (ybr) {
         uint2 o;
-        o.x = pack_bf16x2(v.x, v.y);
-        o.y = pack_bf16x2(v.z, v.w);
+        if (yb_f16) {
+          const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+          o.x = *reinterpret_cast<const uint32_t*>(&lo);
+          o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        } else {
+          o.x = pack_bf16x2(v.x, v.y);
+          o.y = pack_bf16x2(v.z, v.w);
+        }
         reinterpret_cast<uint2*>(ybr)[i] = o;
       }
     }
@@ -301,14 +336,15 @@ l2norm_fwd_kernel(const float* __restrict__ u, int B, int D, float* __restrict__
     for (int i = lane; i < D; i += 32) {
       const float v = ur[i] / nrm;
       yr[i] = v;
-      if (ybr) ybr[i] = __float2bfloat16_rn(v);
+      if (ybr) ybr[i] = yb_f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
   }
 }
 
-int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_bf16, cudaStream_t st) {
+int simt_l2norm_fwd(const float* u, int B, int D, float* y, float* inv_norm, void* y_16, int y16_f16, cudaStream_t st) {
   if (B <= 0) return 0;
-  MMG_LAUNCH_PDL("l2norm_fwd_kernel", l2norm_fwd_kernel, (B + 7) / 8, 256, 0, st, u, B, D, y, inv_norm, reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  MMG_LAUNCH_PDL("l2norm_fwd_kernel", l2norm_fwd_kernel, (B + 7) / 8, 256, 0, st, u, B, D, y, inv_norm,
+                 reinterpret_cast<uint16_t*>(y_16), y16_f16);
   return 0;
 }
 
@@ -803,29 +839,37 @@ int simt_infonce_loss_cols(const float* colsum, int cols, const float* scale, co
   return 0;
 }
 
+// fp16 coefficient scaling (MMG_PREC_F16).  The gradient coefficients g = coef * E * (1/rowsum + 1/colsum), coef =
+// s*gl/(2B), are ~1/B^2 -- far below fp16's range -- but g / coef <= 2 (E <= rowsum and E <= colsum), so the tensor-core
+// path stores g' = 2^14 * E * (1/rowsum + 1/colsum) in [0, 2^15] and the gradient epilogues multiply coef * 2^-14 back in
+// (scal[3]): full 11-bit precision down to 2^-29 of the largest coefficient, no data-dependent scale to compute.
+constexpr float kF16CoefScale = 16384.0f;
+
 __global__ void infonce_bwd_prep_kernel(const float* __restrict__ rowsum, int rows, const float* __restrict__ colsum,
                                         int cols, const float* __restrict__ scale, const float* __restrict__ grad_loss,
-                                        float inv_two_b, int diag_in_fp32, float* __restrict__ rinv,
+                                        float inv_two_b, int diag_in_fp32, int f16_scaled, float* __restrict__ rinv,
                                         float* __restrict__ cinv, float* __restrict__ scal) {
   pdl_entry();
   const float coef = (*scale) * (*grad_loss) * inv_two_b;
+  const float num = f16_scaled ? kF16CoefScale : coef;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < rows) rinv[i] = coef / rowsum[i];
-  if (i < cols) cinv[i] = coef / colsum[i];
+  if (i < rows) rinv[i] = num / rowsum[i];
+  if (i < cols) cinv[i] = num / colsum[i];
   if (i == 0) {
-    scal[0] = diag_in_fp32 ? 0.f : 2.0f * coef;  // what the block kernels subtract on the diagonal
+    // [0] what the block kernels subtract on the diagonal (in the units g is stored in)
+    scal[0] = diag_in_fp32 ? 0.f : (f16_scaled ? 2.0f * kF16CoefScale : 2.0f * coef);
     scal[1] = 2.0f * coef;                       // dcoef = s*gl/B
     scal[2] = diag_in_fp32 ? 1.f : 0.f;          // block kernels zero the diagonal element of g
-    scal[3] = 0.f;
+    scal[3] = f16_scaled ? coef / kF16CoefScale : 1.0f;  // factor of the gradient epilogues (and of sum g*cos)
   }
 }
 
 int simt_infonce_bwd_prep(const float* rowsum, int rows, const float* colsum, int cols, const float* scale,
-                          const float* grad_loss, float inv_two_b, int diag_in_fp32, float* rinv, float* cinv,
-                          float* scal, cudaStream_t st) {
+                          const float* grad_loss, float inv_two_b, int diag_in_fp32, int f16_scaled, float* rinv,
+                          float* cinv, float* scal, cudaStream_t st) {
   const int n = rows > cols ? rows : cols;
-  MMG_LAUNCH_PDL("infonce_bwd_prep_kernel", infonce_bwd_prep_kernel, (n + 255) / 256, 256, 0, st, rowsum, rows, colsum, cols, scale, grad_loss, inv_two_b,
-                                                           diag_in_fp32, rinv, cinv, scal);
+  MMG_LAUNCH_PDL("infonce_bwd_prep_kernel", infonce_bwd_prep_kernel, (n + 255) / 256, 256, 0, st, rowsum, rows, colsum, cols,
+                 scale, grad_loss, inv_two_b, diag_in_fp32, f16_scaled, rinv, cinv, scal);
   return 0;
 }
 
@@ -923,7 +967,7 @@ infonce_bwd_diag_kernel(const float* __restrict__ a32, const float* __restrict__
   float contrib = 0.f;
   if (r < rows) {
     const float lg = diag[r];
-    const float g = expf(lg - s) * (rinv[r] + cinvm[r]) - dcoef;
+    const float g = expf(lg - s) * (rinv[r] + cinvm[r]) * scal[3] - dcoef;  // scal[3]: units of rinv / cinv -> true
     const float* ar = a32 + (long long)r * D;
     const float* br = b32 + (long long)r * D;
     float* dar = dA + (long long)r * D;
@@ -979,7 +1023,8 @@ int simt_infonce_bwd_diag(const float* a32, const float* b32, int rows, int D, c
 __global__ void __launch_bounds__(256)
 infonce_bwd_prep_diag_kernel(const float* __restrict__ rowsum, int rows, const float* __restrict__ colsum, int cols,
                              int diag_offset, const float* __restrict__ scale, const float* __restrict__ grad_loss,
-                             float inv_two_b, float* __restrict__ rinv, float* __restrict__ cinv, float* __restrict__ scal,
+                             float inv_two_b, int f16_scaled, float* __restrict__ rinv, float* __restrict__ cinv,
+                             float* __restrict__ scal,
                              const float* __restrict__ a32, const float* __restrict__ b32, int D,
                              const float* __restrict__ diag, float* __restrict__ dA, float* __restrict__ dB,
                              float* __restrict__ dlogscale_acc) {
@@ -987,15 +1032,16 @@ infonce_bwd_prep_diag_kernel(const float* __restrict__ rowsum, int rows, const f
   const float s = *scale;
   const float coef = s * (*grad_loss) * inv_two_b;
   const int n = rows > cols ? rows : cols;
+  const float num = f16_scaled ? kF16CoefScale : coef;  // see kF16CoefScale
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    if (i < rows) rinv[i] = coef / rowsum[i];
-    if (i < cols) cinv[i] = coef / colsum[i];
+    if (i < rows) rinv[i] = num / rowsum[i];
+    if (i < cols) cinv[i] = num / colsum[i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal[0] = 0.f;           // the contraction subtracts nothing on the diagonal ...
     scal[1] = 2.0f * coef;   // dcoef = s*gl/B
     scal[2] = 1.f;           // ... it zeroes the matching-pair element of g: applied here in fp32
-    scal[3] = 0.f;
+    scal[3] = f16_scaled ? coef / kF16CoefScale : 1.0f;  // factor of the gradient epilogues (and of sum g*cos)
   }
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1036,11 +1082,11 @@ infonce_bwd_prep_diag_kernel(const float* __restrict__ rowsum, int rows, const f
 }
 
 int simt_infonce_bwd_prep_diag(const float* rowsum, int rows, const float* colsum, int cols, int diag_offset,
-                               const float* scale, const float* grad_loss, float inv_two_b, float* rinv, float* cinv,
-                               float* scal, const float* a32, const float* b32, int D, const float* diag, float* dA,
-                               float* dB, float* dlogscale_acc, cudaStream_t st) {
+                               const float* scale, const float* grad_loss, float inv_two_b, int f16_scaled, float* rinv,
+                               float* cinv, float* scal, const float* a32, const float* b32, int D, const float* diag,
+                               float* dA, float* dB, float* dlogscale_acc, cudaStream_t st) {
   MMG_LAUNCH_PDL("infonce_bwd_prep_diag_kernel", infonce_bwd_prep_diag_kernel, (rows + 7) / 8, 256, 0, st, rowsum, rows, colsum, cols, diag_offset, scale, grad_loss,
-                                                               inv_two_b, rinv, cinv, scal, a32, b32, D, diag, dA, dB,
+                                                               inv_two_b, f16_scaled, rinv, cinv, scal, a32, b32, D, diag, dA, dB,
                                                                dlogscale_acc);
   return 0;
 }

@@ -100,7 +100,8 @@ static int sm_count() {
   return n;
 }
 
-static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn, int cg) {
+static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn, int cg, int a_f16 = 0,
+                                int b_f16 = 0) {
   GemmProblem p;
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = (M + kBM * cg - 1) / (kBM * cg);
@@ -116,6 +117,7 @@ static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a
   }
   p.k_splits = k_splits;
   p.a_mn = a_mn; p.b_mn = b_mn;
+  p.a_f16 = a_f16; p.b_f16 = b_f16;
   p.k_segs = 1; p.seg_a = 0; p.seg_b = 0;
   return p;
 }
@@ -258,7 +260,7 @@ int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand&
   mb1 = mb;
   if (A1 != nullptr && (rc = make_operand_map(&ma1, *A1, M, K, kBM)) != 0) return rc;
   if (B1 != nullptr && (rc = make_operand_map(&mb1, *B1, N, K, tcfg.BN / tcfg.cg)) != 0) return rc;
-  GemmProblem p0 = make_problem(M, N, K, tcfg.BN, 1, A0.mn_major, B0.mn_major, tcfg.cg);
+  GemmProblem p0 = make_problem(M, N, K, tcfg.BN, 1, A0.mn_major, B0.mn_major, tcfg.cg, A0.f16, B0.f16);
   p0.k_segs = nseg;
   p0.seg_a = nseg > 1 ? seg_a : 0;
   p0.seg_b = nseg > 1 ? seg_b : 0;
@@ -281,7 +283,7 @@ int tc_gemm_store_seg(const TcOperand& A0, const TcOperand* A1, const TcOperand&
 
 int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0, long long ldc0, int M0, int N0, int K0,
                             const TcOperand& A1, const TcOperand& B1, float* C1, long long ldc1, int M1, int N1, int K1,
-                            cudaStream_t st) {
+                            cudaStream_t st, const float* alpha_dev) {
   if (N0 != N1) return set_error(-1, "tc_gemm_dual: both problems must share N");
   const TileCfg tcfg = pick_tile(M0 < M1 ? M0 : M1, N0);
   CUtensorMap ma0, mb0, ma1, mb1;
@@ -291,7 +293,7 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
   if ((rc = make_operand_map(&ma1, A1, M1, K1, kBM)) != 0) return rc;
   if ((rc = make_operand_map(&mb1, B1, N1, K1, tcfg.BN / tcfg.cg)) != 0) return rc;
   EpiStoreF32::Params e0, e1;
-  e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = nullptr; e0.mode = 1; e0.relu = 0;
+  e0.C = C0; e0.ldc = ldc0; e0.bias = nullptr; e0.alpha = 1.f; e0.alpha_ptr = alpha_dev; e0.mode = 1; e0.relu = 0;
   e0.use_tma = out_tma_ok(C0, ldc0) && out_tma_ok(C1, ldc1);
   // Wave quantisation: the two problems of one 8192 x 8192 block are 128 pair tiles on 74 CTA pairs = 2 rounds at 86%.
   // With TMA reduce-add outputs (atomic at L2) every tile may be cut into K slices, so pick the split whose slice
@@ -311,8 +313,8 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
       if (eff > best + 1e-9) { best = eff; ks = sdiv; }
     }
   }
-  GemmProblem p0 = make_problem(M0, N0, K0, tcfg.BN, ks, A0.mn_major, B0.mn_major, tcfg.cg);
-  GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, ks, A1.mn_major, B1.mn_major, tcfg.cg);
+  GemmProblem p0 = make_problem(M0, N0, K0, tcfg.BN, ks, A0.mn_major, B0.mn_major, tcfg.cg, A0.f16, B0.f16);
+  GemmProblem p1 = make_problem(M1, N1, K1, tcfg.BN, ks, A1.mn_major, B1.mn_major, tcfg.cg, A1.f16, B1.f16);
   e1 = e0;
   e1.C = C1; e1.ldc = ldc1;
   CUtensorMap mc0 = ma0, mc1 = ma0;
@@ -324,14 +326,14 @@ int tc_gemm_dual_accumulate(const TcOperand& A0, const TcOperand& B0, float* C0,
 }
 
 int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int D, int diag_offset, const float* scale,
-                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st) {
+                   float* rowsum, float* colsum, float* diag, void* e_out, long long lde, cudaStream_t st, int emb_f16) {
   const TileCfg tcfg = pick_tile(rows, cols);
   TcOperand A{a_hat, D, 0}, B{b_hat, D, 0};
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_operand_map(&ma, A, rows, D, kBM)) != 0) return rc;
   if ((rc = make_operand_map(&mb, B, cols, D, tcfg.BN / tcfg.cg)) != 0) return rc;
-  GemmProblem p0 = make_problem(rows, cols, D, tcfg.BN, 1, 0, 0, tcfg.cg);
+  GemmProblem p0 = make_problem(rows, cols, D, tcfg.BN, 1, 0, 0, tcfg.cg, emb_f16, emb_f16);
   GemmProblem p1 = empty_problem();
   EpiLse::Params e;
   e.rowsum = rowsum; e.colsum = colsum; e.diag = diag; e.scale_ptr = scale; e.diag_offset = diag_offset;
@@ -352,14 +354,14 @@ int tc_infonce_fwd(const void* a_hat, const void* b_hat, int rows, int cols, int
 
 int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, int D, int diag_offset,
                           const float* scale, const float* rinv, const float* cinv, const float* scal, void* G,
-                          long long ldg, float* dlogscale_acc, cudaStream_t st) {
+                          long long ldg, float* dlogscale_acc, cudaStream_t st, int emb_f16) {
   const TileCfg tcfg = pick_tile(rb, cb);
   TcOperand A{a_blk, D, 0}, B{b_blk, D, 0};
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_operand_map(&ma, A, rb, D, kBM)) != 0) return rc;
   if ((rc = make_operand_map(&mb, B, cb, D, tcfg.BN / tcfg.cg)) != 0) return rc;
-  GemmProblem p0 = make_problem(rb, cb, D, tcfg.BN, 1, 0, 0, tcfg.cg);
+  GemmProblem p0 = make_problem(rb, cb, D, tcfg.BN, 1, 0, 0, tcfg.cg, emb_f16, emb_f16);
   GemmProblem p1 = empty_problem();
   // output map: g block [rb, cb] bf16 (pitch ldg), box = 32 rows x 64 columns (one epilogue warp's block)
   CUtensorMap mc;
@@ -367,7 +369,7 @@ int tc_infonce_grad_block(const void* a_blk, const void* b_blk, int rb, int cb, 
   const int dbg = measure_env("MMG_EPI_DBG", 0);  // measurement builds only (tests/gpu_epi_probe.py): wrong results when set
   EpiGrad::Params e;
   e.rinv = rinv; e.cinv = cinv; e.scale_ptr = scale;
-  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg;
+  e.scal = scal; e.dlogscale_acc = dlogscale_acc; e.diag_offset = diag_offset; e.g_row_off = 0; e.dbg = dbg; e.g_f16 = emb_f16 ? 1 : 0;
   MMG_DISPATCH(EpiGrad, tcfg, ma, mb, ma, mb, mc, mc, p0, p1, e, e, st);
 }
 
@@ -569,7 +571,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
                          const float* scale, const float* rinv, const float* cinv, const float* scal, float* dA,
                          float* const* dB_owners, int n_owners, int n_parts, int part, float* dlogscale_acc,
                          void* workspace, size_t workspace_bytes, cudaStream_t st, int* used, const void* e_stored,
-                         long long lde) {
+                         long long lde, int emb_f16) {
   *used = 0;
   if (e_stored != nullptr && (dlogscale_acc != nullptr || (reinterpret_cast<uintptr_t>(e_stored) & 15) != 0 ||
                               (lde & 7) != 0 || lde < cols))
@@ -595,6 +597,7 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
     if (te != cudaSuccess) return check_cuda(te, "cudaMemsetAsync(fused backward trace)");
   }
   p.diag_offset = diag_offset;
+  p.emb_f16 = emb_f16 ? 1 : 0;
   // several owners (row-sharded run): start the column walk at this rank's own columns (BwdFusedParams::global_cb)
   p.col_rot = 0;
   if (n_owners > 1 && n_parts == 1 && tune_int(kTuneRot, 1) != 0 && diag_offset > 0 && (diag_offset % f.Cb) == 0)

@@ -72,13 +72,16 @@ class _PeerBuffers:
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Push all-gather of the column-side embeddings: every rank owns a ring of [B, D] bf16 buffers in symmetric memory; a rank
-# copies its shard straight into the same rows of every rank's buffer (mmg_push_rows: one launch, NVLink line rate, no
-# protocol) and a cross-rank barrier follows.  Both run on a communication stream, so the gather overlaps the other head's
-# projection exactly like the asynchronous NCCL all-gather it replaces (8 x B200, 4 MiB shards: NCCL 86 us from the end of
-# the text head to the gathered matrix).  A ring slot is reused only after the loss that read it has issued its backward
-# (or, without gradients, its forward): the collectives inside those (column-sum all-reduce, peer reduction barriers /
-# reduce-scatter) order every peer's last read of the slot before this rank's next push into it.  A busy ring, a non-bf16
-# operand, a non-NCCL backend or MMGCLIP_B200_PUSH_GATHER=0 select the NCCL all-gather.
+# copies its shard straight into the same rows of every rank's buffer (mmg_push_rows: one launch, a few CTAs per
+# destination, no protocol) and a cross-rank barrier follows.  Both run on a communication stream, so the gather overlaps
+# the other head's projection exactly like the asynchronous NCCL all-gather it replaces.  Measured (global batch 32768 on
+# 8 GPUs / 8192 on 2, CUDA-graph step, profiles/r02d_*): 2 x B200 0.306 ms per step against 0.320 ms with NCCL;
+# 8 x B200 0.712 ms against 0.678 ms with NCCL (seven remote destinations from 32 CTAs do not reach the line rate NCCL's
+# tuned all-gather does).  Default therefore: push on two ranks, NCCL above; MMGCLIP_B200_PUSH_GATHER=1 / 0 forces one.
+# A ring slot is reused only after the loss that read it has issued its backward (or, without gradients, its forward):
+# the collectives inside those (column-sum all-reduce, peer reduction barriers / reduce-scatter) order every peer's last
+# read of the slot before this rank's next push into it.  A busy ring, a non-bf16 operand or a non-NCCL backend select
+# the NCCL all-gather.
 # ---------------------------------------------------------------------------------------------------------------------
 _gather_rings = {}
 _comm_streams = {}
@@ -99,12 +102,12 @@ class _GatherSlot:
 class _GatherRing:
     RING = 4
 
-    def __init__(self, B, D, device, group):
+    def __init__(self, B, D, device, group, dtype):
         import torch.distributed._symmetric_memory as symm_mem
         grp = group if group is not None else dist.group.WORLD
         self.slots = []
         for _ in range(self.RING):
-            buf = symm_mem.empty((B, D), dtype=torch.bfloat16, device=device)
+            buf = symm_mem.empty((B, D), dtype=dtype, device=device)
             self.slots.append(_GatherSlot(buf, symm_mem.rendezvous(buf, group=grp)))
         self.i = -1
 
@@ -121,15 +124,17 @@ class _GatherRing:
         return slot
 
 
-def _gather_ring(B, D, device, group):
-    if os.environ.get("MMGCLIP_B200_PUSH_GATHER", "1") == "0" or device.type != "cuda":
+def _gather_ring(B, D, device, group, dtype):
+    want = os.environ.get("MMGCLIP_B200_PUSH_GATHER", "auto")
+    world = dist.get_world_size(group)
+    if want == "0" or device.type != "cuda" or (want != "1" and world > 2):
         return None
-    if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 8 or (D * 2) % 16 != 0:
+    if dist.get_backend(group) != "nccl" or world > 8 or (D * 2) % 16 != 0:
         return None
-    key = (B, D, device.index, id(group))
+    key = (B, D, device.index, id(group), dtype)
     if key not in _gather_rings:
         try:
-            _gather_rings[key] = _GatherRing(B, D, device, group)
+            _gather_rings[key] = _GatherRing(B, D, device, group, dtype)
         except Exception as e:  # noqa: BLE001
             warnings.warn(f"mmgclip_b200: push all-gather unavailable ({e}); using the NCCL all-gather")
             _gather_rings[key] = None
@@ -290,8 +295,8 @@ def gather_columns_async(b_local: torch.Tensor, group=None, prec: Optional[str] 
     world = dist.get_world_size(group)
     b_op = kernels.operand(b_local, prec).contiguous()
     bl, D = b_op.shape
-    if kernels is _Kernels and b_op.is_cuda and b_op.dtype == torch.bfloat16:
-        ring = _gather_ring(bl * world, D, b_op.device, group)
+    if kernels is _Kernels and b_op.is_cuda and b_op.dtype in (torch.bfloat16, torch.float16):
+        ring = _gather_ring(bl * world, D, b_op.device, group, b_op.dtype)
         slot = ring.acquire() if ring is not None else None
         if slot is not None:
             comm = _comm_stream(b_op.device)
@@ -333,7 +338,7 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         e_mat = None
         if (kernels is _Kernels and _STORE_E_DIST and a_local.is_cuda and peer_reduce_active() and
                 (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and
-                ops.want_store_e(bl, B, D, prec, ctx.needs_input_grad[2], n_owners=world)):
+                a_op.dtype == torch.bfloat16 and ops.want_store_e(bl, B, D, prec, ctx.needs_input_grad[2], n_owners=world)):
             e_mat = torch.empty((bl, B), dtype=torch.bfloat16, device=a_local.device)
         ctx.e_mat = e_mat
         fwd_kw = {"e_out": e_mat} if e_mat is not None else {}

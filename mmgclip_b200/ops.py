@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import MMG_ACCUMULATE, MMG_ATOMIC_ADD, MMG_PREC_BF16, MMG_PREC_FP32, MMG_STORE, check
+from ._lib import MMG_ACCUMULATE, MMG_ATOMIC_ADD, MMG_PREC_BF16, MMG_PREC_F16, MMG_PREC_FP32, MMG_STORE, check
 
 _PREC = {"fp32": MMG_PREC_FP32, "bf16": MMG_PREC_BF16}
 _default_precision = os.environ.get("MMGCLIP_B200_PRECISION", "bf16")
@@ -139,6 +139,51 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     check(_lib.load().mmg_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream()), "mmg_cast_f32_to_bf16")
     return y
+
+
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> fp16 (operand copy of L2-normalised embeddings)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.float16:
+        return x
+    if x.dtype != torch.float32:
+        raise ValueError("cast_f16 expects float32 input")
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(_lib.load().mmg_cast_f32_to_f16(_p(x), _p(y), x.numel(), _stream()), "mmg_cast_f32_to_f16")
+    return y
+
+
+# 16-bit operand format of the L2-NORMALISED EMBEDDINGS on the tensor-core ("bf16") path of the fused InfoNCE.  Unit-norm
+# rows have |x| <= 1, so IEEE fp16 (11-bit significand) represents them 8x more finely than bf16 (8-bit) at no cost in range
+# or tensor-core rate; the gradient-coefficient operand stays bf16 (it spans e^-2s .. 1 times 1/B).  Measured on the
+# benchmark step (float64 closed form, batch 4096): head-weight gradient error 2.1e-3 -> 2.7e-4 (Frobenius), column-side
+# embedding gradients 2.9e-3 -> 2.9e-4 -- the embeddings' bf16 rounding was the whole error budget.
+# MMGCLIP_B200_EMB_F16=0 (or set_embedding_f16(False)) keeps bf16 embedding operands.
+_emb_f16 = os.environ.get("MMGCLIP_B200_EMB_F16", "0") == "1"
+
+
+def set_embedding_f16(flag: bool) -> None:
+    global _emb_f16
+    _emb_f16 = bool(flag)
+
+
+def get_embedding_f16() -> bool:
+    return _emb_f16
+
+
+def cast_embedding(x: torch.Tensor) -> torch.Tensor:
+    """The 16-bit tensor-core operand of an fp32 embedding matrix (fp16 by default, see above)."""
+    return cast_f16(x) if _emb_f16 else cast_bf16(x)
+
+
+def _tc_prec(prec: str, a: torch.Tensor, b: torch.Tensor) -> int:
+    """C-ABI precision code of a fused-InfoNCE call from the operands the caller holds."""
+    if prec == "fp32":
+        return MMG_PREC_FP32
+    if a.dtype != b.dtype or a.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError(f"tensor-core InfoNCE operands must both be bfloat16 or both float16, got {a.dtype} / {b.dtype}")
+    return MMG_PREC_F16 if a.dtype == torch.float16 else MMG_PREC_BF16
 
 
 def cast_bf16_split(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -289,14 +334,16 @@ def _split_k_for(M: int, N: int, K: int) -> int:
 
 
 def l2norm_fwd(u: torch.Tensor, want_bf16: bool) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """y = u/||u||, 1/||u||, and (``want_bf16``) the 16-bit operand copy of y -- fp16 unless set_embedding_f16(False)."""
     _need_cuda(u)
     u = u.contiguous()
     B, D = u.shape
     y = torch.empty_like(u)
     inv = torch.empty(B, dtype=torch.float32, device=u.device)
-    yb = torch.empty((B, D), dtype=torch.bfloat16, device=u.device) if want_bf16 else None
+    f16 = _emb_f16
+    yb = torch.empty((B, D), dtype=torch.float16 if f16 else torch.bfloat16, device=u.device) if want_bf16 else None
     if B > 0:
-        check(_lib.load().mmg_l2norm_fwd(_p(u), B, D, _p(y), _p(inv), _p(yb), _stream()), "mmg_l2norm_fwd")
+        check(_lib.load().mmg_l2norm_fwd(_p(u), B, D, _p(y), _p(inv), _p(yb), int(f16), _stream()), "mmg_l2norm_fwd")
     return y, inv, yb
 
 
@@ -359,13 +406,14 @@ def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, c
     if e_out is not None:
         if prec != "bf16" or e_out.dtype != torch.bfloat16 or tuple(e_out.shape) != (rows, cols) or e_out.stride(1) != 1:
             raise ValueError("e_out must be a bf16 [rows, cols] tensor with contiguous rows (bf16 path only)")
-        check(lib.mmg_infonce_fwd_store(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum), _p(colsum),
-                                        _p(diag), _p(e_out), e_out.stride(0), _stream()), "mmg_infonce_fwd_store")
+        check(lib.mmg_infonce_fwd_store(_tc_prec(prec, a, b), _p(a), _p(b), rows, cols, D, diag_offset, _p(scale),
+                                        _p(rowsum), _p(colsum), _p(diag), _p(e_out), e_out.stride(0), _stream()),
+              "mmg_infonce_fwd_store")
         return rowsum, colsum, diag
     nbytes = lib.mmg_infonce_workspace_bytes(_PREC[prec], rows, cols, D)
     ws = _workspace(dev, nbytes)
-    check(lib.mmg_infonce_fwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum), _p(colsum),
-                              _p(diag), _p(ws), ws.numel(), _stream()), "mmg_infonce_fwd")
+    check(lib.mmg_infonce_fwd(_tc_prec(prec, a, b), _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rowsum),
+                              _p(colsum), _p(diag), _p(ws), ws.numel(), _stream()), "mmg_infonce_fwd")
     return rowsum, colsum, diag
 
 
@@ -432,6 +480,9 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
     diag_fp32 = prec == "bf16" and a32 is not None and b32 is not None and diag is not None
+    pcode = _tc_prec(prec, a, b)
+    if e_stored is not None and pcode != MMG_PREC_BF16:
+        raise ValueError("the stored-E backward takes bf16 operands (set_embedding_f16(False))")
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
     if diag_fp32:
         # the fp32 matching-pair term is the FIRST writer of the gradient rows (no zero-fill, no read-modify-write);
@@ -443,11 +494,11 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
         else:
             dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
         dBm = dB[diag_offset:diag_offset + rows]
-        check(lib.mmg_infonce_bwd_prep_diag(_p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
+        check(lib.mmg_infonce_bwd_prep_diag(pcode, _p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
                                             float(inv_two_b), _p(rinv), _p(cinv), _p(scal), _p(a32), _p(b32), D, _p(diag),
                                             _p(dA), _p(dBm), _p(dls), _stream()), "mmg_infonce_bwd_prep_diag")
     else:
-        check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+        check(lib.mmg_infonce_bwd_prep(pcode, _p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
                                        0, _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
         dA = torch.zeros((rows, D), dtype=torch.float32, device=dev)
         dB = torch.zeros((cols, D), dtype=torch.float32, device=dev)
@@ -464,11 +515,11 @@ def infonce_backward_raw(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: floa
         _bwd_probe[0].record()
     if e_stored is not None:
         owners = (ctypes.c_void_p * 1)(dB.data_ptr())
-        check(lib.mmg_infonce_bwd_stored(_p(a), _p(b), _p(e_stored), e_stored.stride(0), rows, cols, D, diag_offset,
-                                         _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), owners, 1, 1, 0, _p(ws),
-                                         ws.numel(), _stream()), "mmg_infonce_bwd_stored")
+        check(lib.mmg_infonce_bwd_stored(pcode, _p(a), _p(b), _p(e_stored), e_stored.stride(0), rows, cols,
+                                         D, diag_offset, _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), owners, 1, 1, 0,
+                                         _p(ws), ws.numel(), _stream()), "mmg_infonce_bwd_stored")
     else:
-        check(lib.mmg_infonce_bwd(_PREC[prec], _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+        check(lib.mmg_infonce_bwd(pcode, _p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
                                   _p(scal), _p(dA), _p(dB), _p(dls), block_rows, block_cols, _p(ws), ws.numel(),
                                   _stream()), "mmg_infonce_bwd")
     if _bwd_probe is not None:
@@ -508,15 +559,18 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     gl = grad_loss.reshape(()).to(torch.float32).contiguous()
     diag_fp32 = a32 is not None and b32 is not None and diag is not None
+    pcode = _tc_prec("bf16", a, b)
+    if e_stored is not None and pcode != MMG_PREC_BF16:
+        raise ValueError("the stored-E backward takes bf16 operands (set_embedding_f16(False))")
     dls = torch.zeros((), dtype=torch.float32, device=dev) if need_dscale else None
     if diag_fp32 and n_parts == 1:
         # one launch: rinv / cinv / scal + the matching-pair term as first writer of dA and of this rank's own buffer
         dA = torch.empty((rows, D), dtype=torch.float32, device=dev)
-        check(lib.mmg_infonce_bwd_prep_diag(_p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
+        check(lib.mmg_infonce_bwd_prep_diag(pcode, _p(rowsum), rows, _p(colsum), cols, diag_offset, _p(scale), _p(gl),
                                             float(inv_two_b), _p(rinv), _p(cinv), _p(scal), _p(a32), _p(b32), D, _p(diag),
                                             _p(dA), _p(parts[0][0]), _p(dls), _stream()), "mmg_infonce_bwd_prep_diag")
     else:
-        check(lib.mmg_infonce_bwd_prep(_p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
+        check(lib.mmg_infonce_bwd_prep(pcode, _p(rowsum), rows, _p(colsum), cols, _p(scale), _p(gl), float(inv_two_b),
                                        int(diag_fp32), _p(rinv), _p(cinv), _p(scal), _stream()), "mmg_infonce_bwd_prep")
     if diag_fp32 and n_parts == 1:
         pass
@@ -543,11 +597,12 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
     for i, (_, owner_ptrs) in enumerate(parts):
         ptrs = (ctypes.c_void_p * world)(*[int(x) for x in owner_ptrs])
         if e_stored is not None:
-            check(lib.mmg_infonce_bwd_stored(_p(a), _p(b), _p(e_stored), e_stored.stride(0), rows, cols, D, diag_offset,
-                                             _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), ptrs, world, n_parts, i,
-                                             _p(ws), ws.numel(), _stream()), "mmg_infonce_bwd_stored")
+            check(lib.mmg_infonce_bwd_stored(pcode, _p(a), _p(b), _p(e_stored), e_stored.stride(0), rows,
+                                             cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv), _p(scal), _p(dA), ptrs,
+                                             world, n_parts, i, _p(ws), ws.numel(), _stream()), "mmg_infonce_bwd_stored")
         else:
-            check(lib.mmg_infonce_bwd_owners(_p(a), _p(b), rows, cols, D, diag_offset, _p(scale), _p(rinv), _p(cinv),
+            check(lib.mmg_infonce_bwd_owners(pcode, _p(a), _p(b), rows, cols, D, diag_offset, _p(scale),
+                                             _p(rinv), _p(cinv),
                                              _p(scal), _p(dA), ptrs, world, n_parts, i, _p(dls), _p(ws), ws.numel(),
                                              _stream()), "mmg_infonce_bwd_owners")
         if after_part is not None:
@@ -739,12 +794,20 @@ def _operand(t: torch.Tensor, prec: str) -> torch.Tensor:
         if t.dtype != torch.float32:
             raise ValueError("fp32 path expects float32 embeddings")
         return t.detach().contiguous()
-    if t.dtype == torch.bfloat16:
+    if t.dtype in (torch.bfloat16, torch.float16):
         return t.detach().contiguous()
-    cached = getattr(t, "_mmg_bf16", None)
+    cached = getattr(t, "_mmg_bf16", None)  # the 16-bit copy the normalise kernel attached (fp16 or bf16)
     if cached is not None and cached.shape == t.shape and cached.device == t.device:
         return cached
-    return cast_bf16(t.detach())
+    return cast_embedding(t.detach())
+
+
+def _operand_bf16(t: torch.Tensor, prec: str) -> torch.Tensor:
+    """Like _operand, for consumers that contract in bf16 only (the materialised-logits contraction, mmg_gemm)."""
+    o = _operand(t, prec)
+    if prec == "fp32" or o.dtype == torch.bfloat16:
+        return o
+    return cast_bf16(t.detach().to(torch.float32))
 
 
 class _InfoNCEFn(torch.autograd.Function):
@@ -757,7 +820,8 @@ class _InfoNCEFn(torch.autograd.Function):
             raise ValueError(f"paired InfoNCE needs equal shapes, got {tuple(a_hat.shape)} and {tuple(b_hat.shape)}")
         s = scale.detach().reshape(()).to(device=a_hat.device, dtype=torch.float32).contiguous()
         e_mat = None
-        if want_store_e(n, n, D, prec, ctx.needs_input_grad[2]) and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+        if (a_op.dtype == torch.bfloat16 and want_store_e(n, n, D, prec, ctx.needs_input_grad[2])
+                and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])):
             try:
                 e_mat = torch.empty((n, n), dtype=torch.bfloat16, device=a_hat.device)
             except torch.OutOfMemoryError:
@@ -904,7 +968,7 @@ class _LogitsFn(torch.autograd.Function):
         if b.shape[1] != D:
             raise ValueError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{D} and {b.shape[1]}x{m})")
         s = scale.detach().reshape(()).to(device=a.device, dtype=torch.float32).contiguous()
-        ao, bo = _operand(a, prec), _operand(b, prec)
+        ao, bo = _operand_bf16(a, prec), _operand_bf16(b, prec)
         logits = gemm(ao, bo, n, m, D, alpha_dev=s, prec=prec)  # s applied in the contraction's epilogue
         ctx.prec = prec
         ctx.scale_shape = scale.shape
