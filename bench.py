@@ -384,6 +384,8 @@ def run_gpu(args):
     _lib.load()
     if not args.pdl:
         ops.set_tuning(pdl=0)
+    if args.emb_f16 is None:
+        args.emb_f16 = int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.batch <= 8192
     ops.set_embedding_f16(bool(args.emb_f16))
 
     B = args.batch
@@ -859,10 +861,14 @@ def main():
                          "rank holds <= 8192 rows (launch-bound heads: 0.212 -> 0.184 ms/step at batch 4096), off above "
                          "(bandwidth-bound heads: no gain measured)")
     ap.add_argument("--no-head-overlap", dest="head_overlap", action="store_false")
-    ap.add_argument("--emb-f16", dest="emb_f16", action="store_true",
-                    default=os.environ.get("MMGCLIP_B200_EMB_F16", "0") == "1",
+    ef_env = os.environ.get("MMGCLIP_B200_EMB_F16")
+    ap.add_argument("--emb-f16", dest="emb_f16", action="store_true", default=None if ef_env is None else ef_env == "1",
                     help="fp16 tensor-core operands for the normalised embeddings and the (2^14-scaled) gradient "
-                         "coefficients instead of bf16 (MMG_PREC_F16)")
+                         "coefficients instead of bf16 (MMG_PREC_F16).  Default: fp16 on one GPU up to batch 8192 (there the "
+                         "bf16 operand rounding puts the head-weight gradients at the 2e-3 bar -- 2.1e-3 at batch 4096 -- "
+                         "and the step is launch-bound, so fp16 costs nothing: 0.171 vs 0.170 ms), bf16 above (fp16 "
+                         "multipliers draw more power: 4.35 vs 4.15 ms per step at batch 32768 under the power cap, where "
+                         "bf16 is already inside the bar)")
     ap.add_argument("--emb-bf16", dest="emb_f16", action="store_false")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", default=True,
                     help="A/B switch: launch without programmatic dependent launch (mmg_tune pdl=0)")

@@ -90,14 +90,17 @@ static int make_operand_map(CUtensorMap* m, const TcOperand& op, int rows, int K
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  // per device: a process may drive several GPUs
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 static GemmProblem make_problem(int M, int N, int K, int BN, int k_splits, int a_mn, int b_mn, int cg, int a_f16 = 0,
@@ -659,6 +662,27 @@ int tc_infonce_bwd_fused(const void* a_hat, const void* b_hat, int rows, int col
   at.cluster(2);
   cfg.attrs = at.a;
   cfg.numAttrs = at.n;
+  // The kernel's CTAs wait for each other (doneA / doneB): every cluster of the grid must be resident at once.  Ask the
+  // occupancy calculator (it accounts for MPS / green-context SM limits and the per-SM shared memory) once per device and
+  // kernel variant; with fewer cluster slots than CTA pairs the caller's block loop runs instead.
+  {
+    static int max_clusters[64][4];
+    static bool known[64][4];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!known[dev][slot]) {
+      int n = 0;
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (oe != cudaSuccess) {
+        cudaGetLastError();
+        n = pairs;  // the query is unavailable: keep the one-CTA-per-SM assumption
+      }
+      max_clusters[dev][slot] = n;
+      known[dev][slot] = true;
+    }
+    if (max_clusters[dev][slot] < pairs) return 0;  // *used stays 0
+  }
   // (An L2 persisting access-policy window on the coefficient scratch was tried and is much slower -- 4.1 vs 2.65 ms at
   // 32768^2 -- and the device-wide set-aside also slows every later kernel of the process; not used.)
   e = cudaLaunchKernelEx(&cfg, kern, mAk, mBk, mAmn, mBmn, mGk, mGmn, mGst, mdA, mdB, p);
