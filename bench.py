@@ -242,7 +242,7 @@ def gpu_eager_reference(torch, dev, batches, iters=5):
                     e1.record()
                     torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / iters
-                out[f"b{Bn}_{mode}"] = {"ms_per_step": ms, "pairs_per_s": Bn / (ms * 1e-3), "loss": float(loss)}
+                out[f"b{Bn}_{mode}"] = {"ms_per_step": ms, "pairs_per_s": Bn / (ms * 1e-3), "loss": float(loss.detach())}
             del xi, xt, wi, wt
             torch.cuda.empty_cache()
         except Exception as exc:  # noqa: BLE001  (informational block: never lose the bench line over it)

@@ -108,6 +108,14 @@ int mmg_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B
  *   dz[i] = dy[i] * (y ? y[i] > 0 : 1) * (mask ? mask[i] * keep_scale : 1)      db[n] = sum_rows dz[:, n]
  * (y = layer output after ReLU+dropout, NULL = no ReLU; mask NULL = no dropout) */
 int mmg_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, mmg_stream_t stream);
+/* nn.Dropout(p) in training mode (projection.py:51,59,92,98) as ONE launch that draws, applies and records the keep mask:
+ *   keep[i] = philox4x32_10(counter = state[1] + i/4, key = state[0]).word[i % 4] >= p * 2^32
+ *   y[i] = keep[i] ? y[i] / (1 - p) : 0        mask_out[i] = keep[i]
+ * state = three DEVICE uint64 {seed, offset, 0}: the launch advances `offset` by ceil(n/4) itself (last CTA to retire), so
+ * replayed CUDA graphs draw fresh masks.  Bit-for-bit the masks differ from torch's (different stream layout), as they do
+ * between any two torch versions; the distribution is the same. */
+int mmg_dropout_draw_apply(float* y, uint8_t* mask_out, float p, long long n, unsigned long long* state,
+                           mmg_stream_t stream);
 int mmg_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                          long long n, mmg_stream_t stream);
 int mmg_colsum(const float* x, int rows, int cols, float* out, mmg_stream_t stream);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mmg_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_longlong, c_void_p]),
     "mmg_dropout_apply": (c_int, [c_void_p, c_void_p, c_float, c_longlong, c_void_p]),
+    "mmg_dropout_draw_apply": (c_int, [c_void_p, c_void_p, c_float, c_longlong, c_void_p, c_void_p]),
     "mmg_relu_dropout_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_void_p]),
     "mmg_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mmg_add": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),

@@ -205,6 +205,18 @@ int mmg_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long
   return simt_dropout_apply(y, mask, keep_scale, n, static_cast<cudaStream_t>(stream));
 }
 
+int mmg_dropout_draw_apply(float* y, uint8_t* mask_out, float p, long long n, unsigned long long* state,
+                           mmg_stream_t stream) {
+  if (n < 0 || !(p >= 0.f && p <= 1.f)) return set_error(MMG_ERR_BAD_ARG, "mmg_dropout_draw_apply: bad n or p");
+  if (n == 0) return 0;
+  MMG_REQ(y);
+  MMG_REQ(mask_out);
+  MMG_REQ(state);
+  if ((reinterpret_cast<uintptr_t>(state) & 7) != 0)
+    return set_error(MMG_ERR_BAD_ALIGN, "mmg_dropout_draw_apply: state must be 8-byte aligned");
+  return simt_dropout_draw_apply(y, mask_out, p, n, state, static_cast<cudaStream_t>(stream));
+}
+
 int mmg_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                          long long n, mmg_stream_t stream) {
   if (n <= 0) return 0;

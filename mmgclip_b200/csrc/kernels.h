@@ -122,6 +122,7 @@ int simt_push_rows(const void* src, long long bytes, void* const* dst_ptrs, int 
 int simt_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int B, int D, float* du, void* du_bf16,
                     void* du_bf16_lo, float* zero, long long zero_floats, cudaStream_t st);
 int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long long n, cudaStream_t st);
+int simt_dropout_draw_apply(float* y, uint8_t* mask, float p, long long n, unsigned long long* state, cudaStream_t st);
 int simt_relu_dropout_bwd(const float* dy, const float* y, const uint8_t* mask, float keep_scale, float* dz,
                           long long n, cudaStream_t st);
 int simt_colsum(const float* x, int rows, int cols, float* out, cudaStream_t st);

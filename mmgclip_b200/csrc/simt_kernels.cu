@@ -407,6 +407,73 @@ int simt_dropout_apply(float* y, const uint8_t* mask, float keep_scale, long lon
   return 0;
 }
 
+// Inverted dropout with the keep mask drawn IN the kernel (the reference's nn.Dropout, projection.py:51,59,92,98): one launch
+// draws, applies and records the mask.  Philox4x32-10 (counter-based, the generator family torch uses on CUDA): element i
+// takes word i % 4 of the block with counter offset + i / 4 under the key `seed`; an element is kept when its 32-bit word
+// >= p * 2^32.  state = {seed, offset, ticket} lives on the device: the last CTA to retire advances the offset by the
+// blocks this launch consumed, so a replayed CUDA graph draws fresh masks with no host involvement.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256)
+dropout_draw_apply_kernel(float* __restrict__ y, uint8_t* __restrict__ mask, float p, float keep_scale, long long n,
+                          unsigned long long* __restrict__ state) {
+  pdl_entry();
+  const unsigned long long seed = state[0], offset = state[1];
+  const uint32_t thr = p >= 1.f ? 0xFFFFFFFFu : static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  const bool drop_all = p >= 1.f;
+  const long long nblk = (n + 3) >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += stride) {
+    const unsigned long long ctr = offset + static_cast<unsigned long long>(b);
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u, static_cast<uint32_t>(seed),
+                  static_cast<uint32_t>(seed >> 32), r);
+    const long long i0 = b << 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + j;
+      if (i < n) {
+        const bool keep = !drop_all && r[j] >= thr;
+        mask[i] = keep ? 1 : 0;
+        y[i] = keep ? y[i] * keep_scale : 0.f;
+      }
+    }
+  }
+  // the last CTA to retire advances the stream position (every CTA has read `offset` before it could retire)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(&state[2], 1ull);
+    if (t == gridDim.x - 1) {
+      state[1] = offset + static_cast<unsigned long long>(nblk);
+      state[2] = 0ull;
+      __threadfence();
+    }
+  }
+}
+
+int simt_dropout_draw_apply(float* y, uint8_t* mask, float p, long long n, unsigned long long* state, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const float keep_scale = p < 1.f ? 1.0f / (1.0f - p) : 0.f;
+  MMG_LAUNCH_PDL("dropout_draw_apply_kernel", dropout_draw_apply_kernel, ew_blocks(n, 4), 256, 0, st, y, mask, p, keep_scale,
+                 n, state);
+  return 0;
+}
+
 // y is the layer output AFTER ReLU and dropout (y > 0 <=> pre-activation > 0 and kept); y == NULL means no ReLU.
 __global__ void relu_dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                         const uint8_t* __restrict__ mask, float keep_scale, float* __restrict__ dz,

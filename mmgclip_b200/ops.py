@@ -617,11 +617,42 @@ def infonce_backward_owners(a, b, scale, rowsum, colsum, grad_loss, inv_two_b: f
 # ----------------------------------------------------------------------------------------------------------------
 # autograd operators
 # ----------------------------------------------------------------------------------------------------------------
+# nn.Dropout state of the in-kernel generator (mmg_dropout_draw_apply): {seed, offset, ticket} as three int64 on each
+# device.  The seed is taken from torch.initial_seed() when a device first draws (so torch.manual_seed() before building
+# the model fixes the masks); seed_dropout() re-seeds explicitly.  The offset advances on the device, launch by launch.
+_dropout_states = {}
+
+
+def seed_dropout(seed: int, device=None) -> None:
+    """Restart the dropout stream of ``device`` (default: current CUDA device) from ``seed``."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _dropout_states[dev.index] = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0, 0], dtype=torch.int64, device=dev)
+
+
+def _dropout_state(dev: torch.device) -> torch.Tensor:
+    st = _dropout_states.get(dev.index)
+    if st is None:
+        seed_dropout(torch.initial_seed(), dev)
+        st = _dropout_states[dev.index]
+    return st
+
+
+def dropout_draw_apply(y: torch.Tensor, p: float) -> torch.Tensor:
+    """In place: y = dropout(y, p) with the keep mask drawn in the kernel; returns the uint8 mask (for the backward)."""
+    _need_cuda(y)
+    mask = torch.empty(y.shape, dtype=torch.uint8, device=y.device)
+    if y.numel() > 0:
+        check(_lib.load().mmg_dropout_draw_apply(_p(y), _p(mask), float(p), y.numel(), _p(_dropout_state(y.device)),
+                                                 _stream()), "mmg_dropout_draw_apply")
+    return mask
+
+
 class _LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b) [* dropout mask]; nn.Linear semantics (projection.py:17,45-59,88-97)."""
+    """y = act(x W^T + b) [* dropout mask]; nn.Linear semantics (projection.py:17,45-59,88-97).  The mask is either given
+    (``mask`` uint8 + ``keep_scale``) or drawn in the kernel (``drop_p`` > 0)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu: bool, mask, keep_scale: float, prec: str):
+    def forward(ctx, x, weight, bias, relu: bool, mask, keep_scale: float, prec: str, drop_p: float = 0.0):
         _need_cuda(x, weight, bias, mask)
         if x.dim() != 2:
             raise ValueError("projection heads take [B, E] inputs")
@@ -641,6 +672,10 @@ class _LinearFn(torch.autograd.Function):
         if mask is not None:
             check(_lib.load().mmg_dropout_apply(_p(y), _p(mask), float(keep_scale), y.numel(), _stream()),
                   "mmg_dropout_apply")
+        elif drop_p > 0.0:
+            mask = dropout_draw_apply(y, drop_p)
+            keep_scale = 1.0 / (1.0 - drop_p) if drop_p < 1.0 else 0.0
+            ctx.mask_drawn = mask  # readable by tests / callers that want the mask (weak convenience, not an output)
         ctx.prec, ctx.relu, ctx.keep_scale = prec, relu, keep_scale
         ctx.has_bias = bias is not None
         ctx.nx, ctx.nw = len(xo.tensors()), len(wo.tensors())
@@ -651,7 +686,7 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         if ctx.empty:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         saved = ctx.saved_tensors
         xo = _Operand.from_tensors(saved[:ctx.nx])
         wo = _Operand.from_tensors(saved[ctx.nx:ctx.nx + ctx.nw])
@@ -677,11 +712,20 @@ class _LinearFn(torch.autograd.Function):
             check(_lib.load().mmg_colsum(_p(dz), Bn, D, _p(db), _stream()), "mmg_colsum")
         if ctx.needs_input_grad[0]:
             dx = gemm_heads(dzo, wo, Bn, E, D, b_mn=True, prec=prec)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu=False, mask=None, keep_scale=1.0, prec=None):
-    return _LinearFn.apply(x, weight, bias, relu, mask, keep_scale, _resolve(prec))
+# the keep mask of the most recent in-kernel dropout draw (what a test or a debugging session compares an oracle against)
+last_dropout_mask = None
+
+
+def linear(x, weight, bias=None, relu=False, mask=None, keep_scale=1.0, prec=None, drop_p=0.0):
+    """``drop_p`` > 0: inverted dropout after the activation with the mask drawn in the kernel (mmg_dropout_draw_apply)."""
+    global last_dropout_mask
+    y = _LinearFn.apply(x, weight, bias, relu, mask, keep_scale, _resolve(prec), float(drop_p))
+    if drop_p > 0.0 and mask is None and y.grad_fn is not None:
+        last_dropout_mask = getattr(y.grad_fn, "mask_drawn", None)
+    return y
 
 
 class _L2NormFn(torch.autograd.Function):

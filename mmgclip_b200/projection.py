@@ -13,16 +13,6 @@ from torch import nn
 from . import ops
 
 
-def _dropout_mask(x: torch.Tensor, p: float):
-    """Inverted-dropout keep mask drawn from torch's generator (the reference uses nn.Dropout, projection.py:51,92)."""
-    if p <= 0.0:
-        return None, 1.0
-    if p >= 1.0:
-        return torch.zeros(x.shape, dtype=torch.uint8, device=x.device), 0.0
-    keep = torch.rand(x.shape, device=x.device) >= p
-    return keep.to(torch.uint8), 1.0 / (1.0 - p)
-
-
 class LinearProjectionLayer(nn.Module):
     """One bias-free ``Linear(embedding_dim, projection_dim)`` (reference: projection.py:4-33).
 
@@ -68,10 +58,9 @@ class MultiLinearHead(nn.Module):
         for i, layer in enumerate(self.layers):
             if i < last:
                 p = self.dropout.p if self.training else 0.0
-                # bias + ReLU live in the contraction's epilogue; the keep mask is applied to its output
-                probe = torch.empty((x.shape[0], layer.out_features), device=x.device) if p > 0 else None
-                mask, scale = _dropout_mask(probe, p) if p > 0 else (None, 1.0)
-                x = ops.linear(x, layer.weight, layer.bias, relu=True, mask=mask, keep_scale=scale, prec=self.precision)
+                # bias + ReLU live in the contraction's epilogue; the keep mask is drawn (Philox), applied and recorded by
+                # one launch on its output (the reference: nn.Dropout, projection.py:51,59)
+                x = ops.linear(x, layer.weight, layer.bias, relu=True, prec=self.precision, drop_p=p)
             else:
                 x = ops.linear(x, layer.weight, layer.bias, prec=self.precision)
         return x
@@ -97,7 +86,6 @@ class MLPProjectionHead(nn.Module):
         projected = ops.linear(x, self.projection.weight, self.projection.bias, prec=self.precision)
         h = ops.gelu(projected)
         p = self.dropout.p if self.training else 0.0
-        mask, scale = _dropout_mask(torch.empty_like(projected), p) if p > 0 else (None, 1.0)
-        h = ops.linear(h, self.fc.weight, self.fc.bias, mask=mask, keep_scale=scale, prec=self.precision)
+        h = ops.linear(h, self.fc.weight, self.fc.bias, prec=self.precision, drop_p=p)
         h = ops.residual_add(h, projected)
         return ops.layer_norm(h, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)

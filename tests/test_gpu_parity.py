@@ -302,16 +302,21 @@ def test_bf16_baseline_full_sizes(mm, rows, cols, d, off):
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_multilinear_head_training_dropout(mm, prec):
-    """MultiLinearHead in train mode: Linear -> ReLU -> Dropout(p) per hidden layer (projection.py:54-61).  The keep
-    masks come from torch's CUDA generator, so re-seeding reproduces them for the oracle."""
+    """MultiLinearHead in train mode: Linear -> ReLU -> Dropout(p) per hidden layer (projection.py:54-61).  The keep mask
+    is drawn inside the kernel (Philox, mmg_dropout_draw_apply); the oracle is handed the mask that was drawn, and
+    re-seeding the stream reproduces it."""
     P = mm.projection
     torch.manual_seed(5)
     head = P.MultiLinearHead(40, [48, 24], dropout=0.25, precision=prec).cuda().train()
     x = torch.randn(64, 40, device="cuda")
-    torch.manual_seed(123)
+    mm.ops.seed_dropout(123)
     y = head(x)
-    torch.manual_seed(123)
-    keep = torch.rand((64, 48), device="cuda") >= 0.25
+    keep = mm.ops.last_dropout_mask.bool()
+    assert keep.shape == (64, 48) and 0.6 < keep.float().mean().item() < 0.9
+    mm.ops.seed_dropout(123)
+    y_again = head(x)
+    assert torch.equal(mm.ops.last_dropout_mask.bool(), keep) and torch.equal(y_again, y)   # same seed, same masks
+    assert not torch.equal(head(x), y)                                                       # the stream advances
     w = [l.weight.detach().cpu() for l in head.layers]
     b = [l.bias.detach().cpu() for l in head.layers]
     ref = oc.torch_multi_linear_head(x.cpu(), w, b, keep_masks=[keep.cpu()], p=0.25)

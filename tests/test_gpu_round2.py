@@ -521,3 +521,64 @@ def test_push_rows_copies_a_shard_into_every_destination():
                 assert float(d.abs().max()) == 0
     with pytest.raises(ValueError):
         ops.push_rows(src, [dsts[0].data_ptr()], 8)  # offset not a multiple of 16 bytes
+
+
+def _philox4x32_10_numpy(counter, seed):
+    """Philox4x32-10 (Salmon et al., SC'11) for 64-bit counters with the two high counter words zero; returns [n, 4] uint32."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    counter = np.asarray(counter, dtype=np.uint64)
+    c = [(counter & np.uint64(0xFFFFFFFF)).astype(np.uint32), (counter >> np.uint64(32)).astype(np.uint32),
+         np.zeros_like(counter, dtype=np.uint32), np.zeros_like(counter, dtype=np.uint32)]
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c[0].astype(np.uint64)
+            p1 = M1 * c[2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+            k0, k1 = np.uint32(k0 + W0), np.uint32(k1 + W1)
+    return np.stack(c, axis=1)
+
+
+def test_in_kernel_dropout_is_philox_and_advances_on_the_device():
+    """mmg_dropout_draw_apply (nn.Dropout of the deep heads, projection.py:51,59,92,98): the keep mask equals a NumPy
+    Philox4x32-10 stream bit for bit, the values are scaled by 1/(1-p), consecutive launches continue the stream, and a
+    replayed CUDA graph draws fresh masks."""
+    from mmgclip_b200 import ops
+    n, p, seed = 1003, 0.3, 987654321012
+    ops.seed_dropout(seed)
+    y0 = torch.randn(n, device="cuda")
+    y = y0.clone()
+    m1 = ops.dropout_draw_apply(y, p)
+    y2 = y0.clone()
+    m2 = ops.dropout_draw_apply(y2, p)
+    torch.cuda.synchronize()
+    nblk = (n + 3) // 4
+    words = _philox4x32_10_numpy(np.arange(2 * nblk, dtype=np.uint64), seed).reshape(-1)
+    thr = np.uint32(int(np.float32(p).astype(np.float64) * 4294967296.0))
+    want1 = words[:n] >= thr
+    want2 = words[4 * nblk:4 * nblk + n] >= thr
+    assert np.array_equal(m1.cpu().numpy().astype(bool), want1)
+    assert np.array_equal(m2.cpu().numpy().astype(bool), want2)          # the offset advanced by ceil(n/4) on the device
+    ref = torch.where(torch.from_numpy(want1).cuda(), y0 / (1 - p), torch.zeros_like(y0))
+    assert rel_err(y.cpu(), ref.cpu()) < 1e-6
+    assert abs(float(m1.float().mean()) - (1 - p)) < 0.06
+    # CUDA graph: the same recorded launch draws different masks on every replay
+    buf = torch.ones(4096, device="cuda")
+    out = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.dropout_draw_apply(buf.clone(), 0.5)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        work = buf.clone()
+        mask = ops.dropout_draw_apply(work, 0.5)
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        out.append(mask.clone())
+    assert not torch.equal(out[0], out[1]) and not torch.equal(out[1], out[2])
+    assert ops.dropout_draw_apply(torch.ones(16, device="cuda"), 1.0).sum().item() == 0   # p = 1 drops everything
