@@ -397,6 +397,9 @@ def infonce_forward_raw(a, b, scale, diag_offset: int, prec: str, rowsum=None, c
     rows, D = a.shape
     cols = b.shape[0]
     dev = a.device
+    if rowsum is None and colsum is None:
+        both = torch.zeros(rows + cols, dtype=torch.float32, device=dev)  # one fill launch for the two accumulators
+        rowsum, colsum = both[:rows], both[rows:]
     if rowsum is None:
         rowsum = torch.zeros(rows, dtype=torch.float32, device=dev)
     if colsum is None:
