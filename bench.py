@@ -261,7 +261,8 @@ def workload_config(n_gpus, sample_batch=None, n_sets=None, graph=None, peer=Non
                "dT slices reduce-added into their owner's buffer over NVLink peer memory by the fused backward kernel)"
                if peer else "reduce-scatter dT)"),
            "l2": "step inputs rotate over distinct buffer sets; each step also streams > 126 MB of intermediates "
-                 "(128 MiB coefficient blocks, fp32 gradients), so nothing survives in the 126 MB L2 between steps"}
+                 "(the 64 MiB coefficient scratch, 128 MiB of fp32 gradients, 2 x 32 MiB operand copies), so nothing survives in the "
+                 "126 MB L2 between steps"}
     if symm:
         cfg["small_allreduces"] = ("torch symmetric memory one-shot / two-shot kernels over NVLink (column sums + the loss's "
                                    "row part in ONE sum, head grads)")
