@@ -353,6 +353,8 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
             kernels.row_part(rowsum, diag, out=cvec.buf[B:B + 1])
             ops.mark("lse_fwd")
             red = cvec.all_reduce()
+            if red.data_ptr() == cvec.buf.data_ptr():
+                red = red.clone()  # very large B: the two-shot kernel reduces in place, and the next forward clears the buffer
             colsum, part = red[:B], red[B:B + 1]
             ops.mark("colsum_ar")
         else:
